@@ -1,0 +1,186 @@
+"""Seeded synthetic configs, weights, inputs and ground truth.
+
+Everything here is generated on the CPU with explicit ``torch.Generator`` /
+``numpy.random.Generator`` seeds so the same bytes are produced in the build
+container (where the reference is imported to make golden vectors) and on the GPU
+box (where ``/root/reference`` does not exist).
+"""
+from __future__ import annotations
+
+import math
+from types import SimpleNamespace
+from typing import Dict, Tuple
+
+import numpy as np
+import torch
+
+from .spec import crog_tensor_specs
+
+SOT_TOKEN = 49406
+EOT_TOKEN = 49407
+
+
+def default_cfg(word_len: int = 17, **over) -> SimpleNamespace:
+    """Model keys of config/OCID-VLG/crog_multiple_r50.yaml:8-22,46-48."""
+    cfg = SimpleNamespace(
+        clip_pretrain="synthetic", input_size=416, word_len=word_len, word_dim=1024, vis_dim=512,
+        fpn_in=[512, 1024, 1024], fpn_out=[256, 512, 1024], num_layers=3, num_head=8, dim_ffn=2048,
+        dropout=0.1, intermediate=False, use_contrastive=True, use_pretrained_clip=False,
+        use_grasp_masks=True, lr_multi=0.1, base_lr=1e-4)
+    for k, v in over.items():
+        setattr(cfg, k, v)
+    return cfg
+
+
+def make_state_dict(cfg, seed: int = 0, mode: str = "perturbed") -> Dict[str, torch.Tensor]:
+    """Deterministic random weights for every tensor of the CROG state-dict.
+
+    mode="init":      distributions of the reference's random init
+                      (model/clip.py:378-420 + torch defaults): BN = identity, every
+                      ``bn3.weight`` of the residual stages is zero.
+    mode="perturbed": He-scaled convs and randomised BN affine/statistics so that all
+                      16 bottleneck branches and both BN terms are exercised
+                      (SURVEY.md §7 "Random-init hides bugs").
+    """
+    assert mode in ("init", "perturbed")
+    g = torch.Generator().manual_seed(seed)
+    sd: Dict[str, torch.Tensor] = {}
+
+    def randn(shape, std):
+        return torch.randn(shape, generator=g) * std
+
+    def rand(shape, lo, hi):
+        return torch.rand(shape, generator=g) * (hi - lo) + lo
+
+    for s in crog_tensor_specs(cfg):
+        n = s.name
+        if s.role == "conv" or s.role == "linear_w" or s.role == "proj":
+            if mode == "init":
+                if ".attnpool." in n and n.endswith("_proj.weight"):
+                    t = randn(s.shape, 2048 ** -0.5)
+                elif "backbone.transformer" in n:
+                    wdt = 512
+                    std = {"in_proj_weight": wdt ** -0.5, "out_proj.weight": wdt ** -0.5 * 24 ** -0.5,
+                           "c_fc.weight": (2 * wdt) ** -0.5, "c_proj.weight": wdt ** -0.5 * 24 ** -0.5}
+                    t = randn(s.shape, next(v for k, v in std.items() if n.endswith(k)))
+                elif s.role == "proj":
+                    t = randn(s.shape, 512 ** -0.5)
+                else:
+                    b = 1.0 / math.sqrt(s.fan_in)
+                    t = rand(s.shape, -b, b)
+            else:
+                gain = 2.0 if s.role == "conv" else 1.0
+                if n == "proj.txt.weight":
+                    gain = 1.0 / 256.0  # keeps the dynamic-conv logits O(1..10)
+                t = randn(s.shape, math.sqrt(gain / s.fan_in))
+        elif s.role == "bias":
+            b = 1.0 / math.sqrt(max(s.fan_in, 1))
+            t = rand(s.shape, -b, b) if mode == "init" else randn(s.shape, 0.05)
+        elif s.role == "bn_w":
+            if mode == "init":
+                zero = "backbone.visual.layer" in n and n.endswith("bn3.weight")
+                t = torch.zeros(s.shape) if zero else torch.ones(s.shape)
+            elif "backbone.visual.layer" in n and n.endswith("bn3.weight"):
+                t = rand(s.shape, 0.1, 0.5)  # non-zero residual branches without blowing up the trunk
+            else:
+                t = rand(s.shape, 0.5, 1.5)
+        elif s.role == "bn_b":
+            t = torch.zeros(s.shape) if mode == "init" else randn(s.shape, 0.1)
+        elif s.role == "bn_mean":
+            t = torch.zeros(s.shape) if mode == "init" else randn(s.shape, 0.1)
+        elif s.role == "bn_var":
+            t = torch.ones(s.shape) if mode == "init" else rand(s.shape, 0.5, 1.5)
+        elif s.role == "bn_count":
+            t = torch.zeros((), dtype=torch.int64)
+        elif s.role == "ln_w":
+            t = torch.ones(s.shape) if mode == "init" else rand(s.shape, 0.8, 1.2)
+        elif s.role == "ln_b":
+            t = torch.zeros(s.shape) if mode == "init" else randn(s.shape, 0.05)
+        elif s.role == "embed":
+            t = randn(s.shape, 0.02 if mode == "init" else 0.5)
+        elif s.role == "pos":
+            if "attnpool" in n:
+                t = randn(s.shape, s.shape[1] ** -0.5 if mode == "init" else 0.3)
+            else:
+                t = randn(s.shape, 0.01 if mode == "init" else 0.3)
+        elif s.role == "scalar":
+            t = torch.tensor(math.log(1 / 0.07))
+        else:  # pragma: no cover
+            raise KeyError(s.role)
+        sd[n] = t.contiguous()
+    return sd
+
+
+def make_inputs(batch: int, word_len: int, size: int = 416, seed_img: int = 1,
+                seed_txt: int = 2) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Config-1/2 inputs: ``img`` ~ N(0,1) fp32 B×3×S×S; ``word`` int64 B×L =
+    ``[SOT, t_1..t_n, EOT, 0...]`` with n in [3, 12] (EOT is the arg-max, pads exercise
+    ``pad_mask``; model/crog.py:55, model/clip.py:451)."""
+    gi = torch.Generator().manual_seed(seed_img)
+    img = torch.randn((batch, 3, size, size), generator=gi)
+    gt = torch.Generator().manual_seed(seed_txt)
+    word = torch.zeros((batch, word_len), dtype=torch.int64)
+    for b in range(batch):
+        n = int(torch.randint(3, 13, (1,), generator=gt))
+        n = min(n, word_len - 2)
+        toks = torch.randint(1, SOT_TOKEN, (n,), generator=gt)
+        word[b, 0] = SOT_TOKEN
+        word[b, 1:1 + n] = toks
+        word[b, 1 + n] = EOT_TOKEN
+    return img, word
+
+
+def make_gt_rects(batch: int, max_gt: int = 64, seed: int = 4, size: int = 416
+                  ) -> Tuple[np.ndarray, np.ndarray]:
+    """Config-3 ground truth: per sample M~U{1..max_gt} rectangles
+    ``[cx, cy, w, h, theta_deg, cls]`` float64, padded to ``max_gt`` rows.
+    w>100 and h!=20 exercise the in-place clip/overwrite of grasp_eval.py:367-368."""
+    rng = np.random.default_rng(seed)
+    gt = np.zeros((batch, max_gt, 6), dtype=np.float64)
+    cnt = rng.integers(1, max_gt + 1, size=batch).astype(np.int32)
+    lo, hi = 40.0, size - 40.0
+    for b in range(batch):
+        m = int(cnt[b])
+        gt[b, :m, 0] = rng.uniform(lo, hi, m)
+        gt[b, :m, 1] = rng.uniform(lo, hi, m)
+        gt[b, :m, 2] = rng.uniform(10, 120, m)
+        gt[b, :m, 3] = rng.uniform(10, 40, m)
+        gt[b, :m, 4] = rng.uniform(-90, 90, m)
+        gt[b, :m, 5] = 1.0
+    return gt, cnt
+
+
+def make_tail_maps(n: int, kind: str = "blobs", seed: int = 7, size: int = 416
+                   ) -> Tuple[np.ndarray, np.ndarray, np.ndarray, np.ndarray]:
+    """Config-5 synthetic quality / sin / cos / width maps, float32 n×S×S.
+
+    kind="blobs":  q = clip(sum of <=8 Gaussians + N(0,0.01), 0, 1); smooth angle field.
+    kind="stress": q ~ U(0,1) iid (thousands of candidate peaks, near-ties); every 20th
+                   map is quantised to 1/16 to create plateaus (tie / spacing rules).
+    """
+    rng = np.random.default_rng(seed)
+    yy, xx = np.mgrid[0:size, 0:size].astype(np.float32)
+    q = np.empty((n, size, size), np.float32)
+    s = np.empty_like(q); c = np.empty_like(q); w = np.empty_like(q)
+    for i in range(n):
+        if kind == "blobs":
+            acc = np.zeros((size, size), np.float32)
+            for _ in range(int(rng.integers(1, 9))):
+                a = rng.uniform(0.45, 1.0); sg = rng.uniform(3, 10)
+                mx, my = rng.uniform(10, size - 10, 2)
+                acc += (a * np.exp(-((xx - mx) ** 2 + (yy - my) ** 2) / (2 * sg * sg))).astype(np.float32)
+            acc += rng.normal(0, 0.01, acc.shape).astype(np.float32)
+            q[i] = np.clip(acc, 0, 1)
+        elif kind == "stress":
+            m = rng.random((size, size), dtype=np.float32)
+            if i % 20 == 19:
+                m = np.floor(m * 16).astype(np.float32) / 16
+            q[i] = m
+        else:
+            raise ValueError(kind)
+        kx, ky, ph = rng.uniform(-0.02, 0.02), rng.uniform(-0.02, 0.02), rng.uniform(-np.pi, np.pi)
+        phi = (kx * xx + ky * yy + ph).astype(np.float32)
+        s[i] = np.sin(2 * phi) + rng.normal(0, 0.05, phi.shape).astype(np.float32)
+        c[i] = np.cos(2 * phi) + rng.normal(0, 0.05, phi.shape).astype(np.float32)
+        w[i] = (0.5 + 0.5 * np.sin(rng.uniform(0.005, 0.03) * xx + rng.uniform(0.005, 0.03) * yy)).astype(np.float32)
+    return q, s, c, w

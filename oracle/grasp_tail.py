@@ -1,0 +1,198 @@
+"""ORACLE (test infrastructure, never shipped, never on the product path).
+
+CPU restatement of the reference's grasp-decode + Jaccard tail,
+``utils/grasp_eval.py:289-374``.  The reference file cannot be imported here: it
+needs scikit-image 0.20.0 / matplotlib (absent, no network) and uses ``np.int0`` /
+NumPy-1.x scalar promotion.  The arithmetic lives in third-party code that is NOT
+under /root/reference (environment.yml:49,61,75,76):
+
+  scikit-image==0.20.0  feature.peak_local_max, draw.polygon (O'Rourke point-in-polygon)
+  scipy==1.9.1          ndimage.maximum_filter (used by peak_local_max)
+  opencv-python==4.7.0.72  cv2.boxPoints
+  numpy==1.24.3         legacy value-based scalar promotion (float32 scalar * python float -> float64)
+
+so this file restates their published algorithms.
+
+PARITY PINNING STATUS: **parity unpinned** for the scikit-image parts — the reference
+has no tests or golden vectors for this path and scikit-image is not installable
+here.  What *is* pinned (tests/test_oracle_tail.py): the two upstream docstring
+known-answer vectors (A.6), ``cv2.boxPoints`` of the installed OpenCV bit-for-bit,
+``scipy.ndimage.maximum_filter`` for the 5x5 max filter, and agreement between this
+numpy restatement and the independent plain-C restatement in oracle/grasp_tail.c.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline/reference arm may
+import this file.
+"""
+from __future__ import annotations
+
+import math
+from typing import List, Sequence, Tuple
+
+import numpy as np
+
+RASTER_SHAPE = (480, 640)  # grasp_eval.py:305 default ``shape``
+
+
+# --------------------------------------------------------------------------- peaks
+def max_filter5(img: np.ndarray) -> np.ndarray:
+    """5x5 maximum filter with edge replication == scipy.ndimage.maximum_filter(
+    img, footprint=ones((5,5)), mode='nearest') (skimage peak.py _get_peak_mask)."""
+    H, W = img.shape
+    p = np.pad(img, 2, mode="edge")
+    out = p[2:2 + H, 2:2 + W].copy()
+    for dy in range(5):
+        for dx in range(5):
+            np.maximum(out, p[dy:dy + H, dx:dx + W], out=out)
+    return out
+
+
+def peak_local_max(img: np.ndarray, min_distance: int = 2, threshold_abs: float = 0.4,
+                   num_peaks: int = 5) -> np.ndarray:
+    """skimage.feature.peak_local_max(img, min_distance=2, threshold_abs, num_peaks)
+    with defaults exclude_border=True, p_norm=inf (App. A.1).  Returns int64 [n,2] (row, col)."""
+    assert min_distance == 2, "oracle restates the min_distance=2 call of grasp_eval.py:292"
+    img = np.asarray(img)
+    H, W = img.shape
+    thr = img.dtype.type(threshold_abs)
+    mask = img == max_filter5(img)
+    if mask.all():  # "no peak for a trivial image"
+        mask[:] = False
+    mask &= img > thr
+    b = min_distance  # exclude_border=True -> border width = min_distance
+    mask[:b, :] = False; mask[H - b:, :] = False
+    mask[:, :b] = False; mask[:, W - b:] = False
+    rr, cc = np.nonzero(mask)
+    if rr.size == 0:
+        return np.zeros((0, 2), np.int64)
+    order = np.argsort(-img[rr, cc], kind="stable")
+    rr, cc = rr[order], cc[order]
+    # ensure_spacing(spacing=2, p_norm=inf, max_out=num_peaks): greedy; an accepted point
+    # rejects later points at Chebyshev distance < 2.  The batching in skimage only
+    # changes cost, not the result (App. A.1 step 5).
+    kept: List[Tuple[int, int]] = []
+    for r, c in zip(rr.tolist(), cc.tolist()):
+        ok = True
+        for (kr, kc) in kept:
+            if max(abs(kr - r), abs(kc - c)) < 2:
+                ok = False
+                break
+        if ok:
+            kept.append((r, c))
+            if len(kept) >= num_peaks:
+                break
+    return np.asarray(kept, np.int64).reshape(-1, 2)
+
+
+def detect_grasps(q, sin, cos, wid, num_grasps: int = 5):
+    """grasp_eval.py:289-302.  Rows are [x(col), y(row), width*100, 20, angle_deg] as
+    float64 (NumPy 1.24.3 promotion, App. A.3).  The second return value is the
+    whole-map float32 angle field like the reference's."""
+    peaks = peak_local_max(np.asarray(q), 2, 0.4, num_grasps)
+    ang = (np.arctan2(np.asarray(sin, np.float64), np.asarray(cos, np.float64)).astype(np.float32)
+           * np.float32(0.5))
+    grasps = []
+    for r, c in peaks:
+        a = float(np.float64(ang[r, c]) / np.pi * 180)
+        w = float(np.float64(np.float32(wid[r, c])) * 100)
+        grasps.append([float(c), float(r), w, 20, a])
+    return grasps, ang
+
+
+# ----------------------------------------------------------------------- rectangles
+def box_points(cx, cy, w, h, angle_deg) -> np.ndarray:
+    """cv2.boxPoints(((cx,cy),(w,h),angle)) restated in float32 (App. A.4 step 2)."""
+    f = np.float32
+    cx, cy, w, h, ang = f(cx), f(cy), f(w), f(h), f(angle_deg)
+    rad = float(ang) * math.pi / 180.0
+    b = f(f(math.cos(rad)) * f(0.5))
+    a = f(f(math.sin(rad)) * f(0.5))
+    p0x = f(f(cx - f(a * h)) - f(b * w))
+    p0y = f(f(cy + f(b * h)) - f(a * w))
+    p1x = f(f(cx + f(a * h)) - f(b * w))
+    p1y = f(f(cy - f(b * h)) - f(a * w))
+    p2x = f(f(f(2) * cx) - p0x); p2y = f(f(f(2) * cy) - p0y)
+    p3x = f(f(f(2) * cx) - p1x); p3y = f(f(f(2) * cy) - p1y)
+    return np.array([[p0x, p0y], [p1x, p1y], [p2x, p2y], [p3x, p3y]], np.float32)
+
+
+def _point_in_polygon(xp: Sequence[int], yp: Sequence[int], x: int, y: int) -> int:
+    """skimage/_shared/_geometry (pnpoly): 0 outside, 1 inside, 2 vertex, 3 edge.
+    Integer vertices -> exact in Python ints."""
+    n = len(xp)
+    r_cross = l_cross = 0
+    x1, y1 = xp[n - 1] - x, yp[n - 1] - y
+    for i in range(n):
+        x0, y0 = xp[i] - x, yp[i] - y
+        if x0 == 0 and y0 == 0:
+            return 2
+        if (y0 > 0) != (y1 > 0):
+            num, den = x0 * y1 - x1 * y0, y1 - y0
+            if (num > 0 and den > 0) or (num < 0 and den < 0):
+                r_cross += 1
+        if (y0 < 0) != (y1 < 0):
+            num, den = x0 * y1 - x1 * y0, y1 - y0
+            if (num > 0 and den < 0) or (num < 0 and den > 0):
+                l_cross += 1
+        x1, y1 = x0, y0
+    if (r_cross & 1) != (l_cross & 1):
+        return 3
+    return 1 if (r_cross & 1) else 0
+
+
+def polygon(r, c, shape=None) -> Tuple[np.ndarray, np.ndarray]:
+    """skimage.draw.polygon(r, c, shape) (App. A.4 step 3) for integer vertices."""
+    r = [int(v) for v in r]; c = [int(v) for v in c]
+    minr, maxr = max(0, min(r)), max(r)
+    minc, maxc = max(0, min(c)), max(c)
+    if shape is not None:
+        maxr = min(shape[0] - 1, maxr)
+        maxc = min(shape[1] - 1, maxc)
+    rr, cc = [], []
+    for ri in range(minr, maxr + 1):
+        for ci in range(minc, maxc + 1):
+            if _point_in_polygon(c, r, ci, ri):
+                rr.append(ri); cc.append(ci)
+    return np.asarray(rr, np.int64), np.asarray(cc, np.int64)
+
+
+def rect_pixels(rect, shape=RASTER_SHAPE) -> set:
+    """Lattice points one rectangle paints in calculate_iou (grasp_eval.py:309-335):
+    boxPoints -> int truncation -> polygon(x as row, y as col, shape) -> rr<shape[1], cc<shape[0]."""
+    cx, cy, w, h, th = [float(v) for v in rect[:5]]
+    box = box_points(cx, cy, w, h, -th).astype(np.int64)  # np.int0 truncates toward zero
+    rr, cc = polygon(box[:, 0], box[:, 1], shape)
+    keep = (rr < shape[1]) & (cc < shape[0])
+    return set(zip(cc[keep].tolist(), rr[keep].tolist()))  # canvas index [cc, rr]
+
+
+def iou_counts(rect_p, rect_gt, shape=RASTER_SHAPE, angle_threshold=30) -> Tuple[int, int]:
+    """(intersection, union) pixel counts of grasp_eval.py:305-347; (0, 0) if angle-gated."""
+    if abs(rect_p[4] - rect_gt[4]) > angle_threshold and abs(rect_p[4] + rect_gt[4]) > angle_threshold:
+        return 0, 0
+    a = rect_pixels(rect_gt, shape)
+    b = rect_pixels(rect_p, shape)
+    return len(a & b), len(a | b)
+
+
+def calculate_iou(rect_p, rect_gt, shape=RASTER_SHAPE, angle_threshold=30):
+    inter, union = iou_counts(rect_p, rect_gt, shape, angle_threshold)
+    return 0 if union <= 0 else inter / union
+
+
+def calculate_max_iou(rects_p, rects_gt):
+    best = 0
+    for g in rects_gt:
+        for p in rects_p:
+            v = calculate_iou(p, g)
+            if v > best:
+                best = v
+    return best
+
+
+def calculate_jacquard_index(grasp_preds, grasp_targets, iou_threshold=0.25) -> int:
+    """grasp_eval.py:362-374, including the in-place edit of ``grasp_targets``."""
+    grasp_preds = np.asarray(grasp_preds)
+    grasp_targets = np.asarray(grasp_targets)
+    grasp_targets[:, 3] = 20
+    grasp_targets[:, 2] = np.clip(grasp_targets[:, 2], 0, 100)
+    return 1 if calculate_max_iou(grasp_preds, grasp_targets) > iou_threshold else 0
