@@ -1,0 +1,132 @@
+// Softmax attention for head_dim 64 (text causal L<=77, attention-pool 169 tokens, decoder
+// self-attention 676 tokens, decoder cross-attention 676 x L with key padding).
+// v1: CUDA-core streaming softmax, one query per thread, K/V tiles of 64 keys staged in shared
+// memory and broadcast to the warp; fp32 math throughout.
+#include "common.cuh"
+
+namespace {
+
+constexpr int HD = 64;
+constexpr int KT = 64;   // keys per smem tile
+constexpr int QB = 128;  // queries per block (one per thread)
+
+template <typename T>
+__global__ void __launch_bounds__(QB) attention_kernel(const T* __restrict__ q, int ldq, const T* __restrict__ k, int ldk,
+                                                       const T* __restrict__ v, int ldv, T* __restrict__ o, int ldo, int Tq,
+                                                       int Tk, float scale, int causal, const int64_t* __restrict__ pad_word) {
+  __shared__ float Ks[KT][HD];
+  __shared__ float Vs[KT][HD];
+  __shared__ int s_masked[KT];
+  const int b = blockIdx.z, h = blockIdx.y;
+  const int qi = blockIdx.x * QB + threadIdx.x;
+  const bool qvalid = qi < Tq;
+  float qr[HD], acc[HD];
+#pragma unroll
+  for (int d = 0; d < HD; ++d) acc[d] = 0.f;
+  if (qvalid) {
+    const T* qp = q + ((long long)b * Tq + qi) * ldq + h * HD;
+#pragma unroll
+    for (int d = 0; d < HD; d += 8) {
+      float t[8]; load8(qp + d, t);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) qr[d + j] = t[j] * scale;
+    }
+  } else {
+#pragma unroll
+    for (int d = 0; d < HD; ++d) qr[d] = 0.f;
+  }
+  float mx = -INFINITY, den = 0.f;
+  const int q_hi = min(blockIdx.x * QB + QB - 1, Tq - 1);
+  const int k_end = causal ? min(Tk, q_hi + 1) : Tk;
+  for (int k0 = 0; k0 < k_end; k0 += KT) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < KT * (HD / 8); i += QB) {
+      const int kr = i / (HD / 8), d8 = (i % (HD / 8)) * 8;
+      float tk[8], tv[8];
+      if (k0 + kr < Tk) {
+        load8(k + ((long long)b * Tk + k0 + kr) * ldk + h * HD + d8, tk);
+        load8(v + ((long long)b * Tk + k0 + kr) * ldv + h * HD + d8, tv);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { tk[j] = 0.f; tv[j] = 0.f; }
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { Ks[kr][d8 + j] = tk[j]; Vs[kr][d8 + j] = tv[j]; }
+    }
+    for (int i = threadIdx.x; i < KT; i += QB) {
+      const int kk = k0 + i;
+      s_masked[i] = (kk >= Tk) || (pad_word && pad_word[(long long)b * Tk + kk] == 0);
+    }
+    __syncthreads();
+    const int kn = min(KT, k_end - k0);
+    for (int j0 = 0; j0 < kn; j0 += 8) {
+      float s[8];
+#pragma unroll
+      for (int jj = 0; jj < 8; ++jj) {
+        const int j = j0 + jj;
+        float d0 = 0.f, d1 = 0.f;
+#pragma unroll
+        for (int d = 0; d < HD; d += 8) {
+          const float4 a = *reinterpret_cast<const float4*>(&Ks[j][d]);
+          const float4 c = *reinterpret_cast<const float4*>(&Ks[j][d + 4]);
+          d0 = fmaf(qr[d], a.x, d0); d1 = fmaf(qr[d + 1], a.y, d1); d0 = fmaf(qr[d + 2], a.z, d0); d1 = fmaf(qr[d + 3], a.w, d1);
+          d0 = fmaf(qr[d + 4], c.x, d0); d1 = fmaf(qr[d + 5], c.y, d1); d0 = fmaf(qr[d + 6], c.z, d0); d1 = fmaf(qr[d + 7], c.w, d1);
+        }
+        const bool dead = (j >= kn) || s_masked[j] || (causal && (k0 + j) > qi);
+        s[jj] = dead ? -INFINITY : (d0 + d1);
+      }
+      float tmax = s[0];
+#pragma unroll
+      for (int jj = 1; jj < 8; ++jj) tmax = fmaxf(tmax, s[jj]);
+      if (tmax == -INFINITY) continue;  // all eight keys masked for this query
+      const float nm = fmaxf(mx, tmax);
+      const float corr = __expf(mx - nm);  // mx=-inf -> 0
+      den *= corr;
+#pragma unroll
+      for (int d = 0; d < HD; ++d) acc[d] *= corr;
+      mx = nm;
+#pragma unroll
+      for (int jj = 0; jj < 8; ++jj) {
+        const float p = __expf(s[jj] - nm);  // -inf -> 0
+        den += p;
+        const int j = min(j0 + jj, KT - 1);
+#pragma unroll
+        for (int d = 0; d < HD; d += 4) {
+          const float4 vv = *reinterpret_cast<const float4*>(&Vs[j][d]);
+          acc[d] = fmaf(p, vv.x, acc[d]); acc[d + 1] = fmaf(p, vv.y, acc[d + 1]);
+          acc[d + 2] = fmaf(p, vv.z, acc[d + 2]); acc[d + 3] = fmaf(p, vv.w, acc[d + 3]);
+        }
+      }
+    }
+  }
+  if (qvalid) {
+    const float inv = 1.f / den;
+    T* op = o + ((long long)b * Tq + qi) * ldo + h * HD;
+#pragma unroll
+    for (int d = 0; d < HD; d += 8) {
+      float t[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) t[j] = acc[d + j] * inv;
+      store8(op + d, t);
+    }
+  }
+}
+
+}  // namespace
+
+extern "C" int crog_attention(const void* q, int32_t ldq, const void* k, int32_t ldk, const void* v, int32_t ldv, void* o,
+                              int32_t ldo, int32_t B, int32_t heads, int32_t Tq, int32_t Tk, float scale, int32_t causal,
+                              const int64_t* pad_word, int32_t dtype, void* stream) {
+  CROG_REQUIRE(ldq % 8 == 0 && ldk % 8 == 0 && ldv % 8 == 0 && ldo % 8 == 0, CROG_E_BADSHAPE, "attention: ld %% 8");
+  CROG_REQUIRE(aligned16(q) && aligned16(k) && aligned16(v) && aligned16(o), CROG_E_BADALIGN, "attention: 16B alignment");
+  if (B == 0 || Tq == 0) return CROG_OK;
+  CROG_REQUIRE(B <= 65535 && heads <= 65535, CROG_E_BADSHAPE, "attention: grid too large");
+  dim3 grid((Tq + QB - 1) / QB, heads, B);
+  cudaStream_t s = (cudaStream_t)stream;
+  if (dtype == CROG_F32)
+    attention_kernel<float><<<grid, QB, 0, s>>>((const float*)q, ldq, (const float*)k, ldk, (const float*)v, ldv, (float*)o, ldo, Tq, Tk, scale, causal, pad_word);
+  else
+    attention_kernel<bf16><<<grid, QB, 0, s>>>((const bf16*)q, ldq, (const bf16*)k, ldk, (const bf16*)v, ldv, (bf16*)o, ldo, Tq, Tk, scale, causal, pad_word);
+  CROG_LAUNCH_OK("attention");
+  return CROG_OK;
+}

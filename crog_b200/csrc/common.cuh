@@ -1,0 +1,217 @@
+// Shared device/host helpers for the crog_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/crog_b200.h"
+
+typedef __nv_bfloat16 bf16;
+
+// ---------------------------------------------------------------- host-side error plumbing
+void crog_set_error(const char* fmt, ...);
+#define CROG_FAIL(code, ...)          \
+  do {                                \
+    crog_set_error(__VA_ARGS__);      \
+    return (code);                    \
+  } while (0)
+#define CROG_REQUIRE(cond, code, ...) \
+  do {                                \
+    if (!(cond)) CROG_FAIL(code, __VA_ARGS__); \
+  } while (0)
+#define CROG_CUDA_OK(expr)                                                           \
+  do {                                                                               \
+    cudaError_t e__ = (expr);                                                        \
+    if (e__ != cudaSuccess) CROG_FAIL(CROG_E_CUDA, "%s: %s", #expr, cudaGetErrorString(e__)); \
+  } while (0)
+#define CROG_LAUNCH_OK(name)                                                        \
+  do {                                                                               \
+    cudaError_t e__ = cudaGetLastError();                                            \
+    if (e__ != cudaSuccess) CROG_FAIL(CROG_E_CUDA, "launch %s: %s", name, cudaGetErrorString(e__)); \
+  } while (0)
+
+static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+// ---------------------------------------------------------------- 8-wide vector access
+__device__ __forceinline__ void load8(const float* p, float (&v)[8]) {
+  float4 a = *reinterpret_cast<const float4*>(p);
+  float4 b = *reinterpret_cast<const float4*>(p + 4);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+__device__ __forceinline__ void load8(const bf16* p, float (&v)[8]) {
+  uint4 u = *reinterpret_cast<const uint4*>(p);
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float2 f = __bfloat1622float2(h[i]);
+    v[2 * i] = f.x; v[2 * i + 1] = f.y;
+  }
+}
+__device__ __forceinline__ void store8(float* p, const float (&v)[8]) {
+  *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
+}
+__device__ __forceinline__ void store8(bf16* p, const float (&v)[8]) {
+  uint4 u;
+  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+  *reinterpret_cast<uint4*>(p) = u;
+}
+__device__ __forceinline__ float to_f(float x) { return x; }
+__device__ __forceinline__ float to_f(bf16 x) { return __bfloat162float(x); }
+template <typename T> __device__ __forceinline__ T from_f(float x);
+template <> __device__ __forceinline__ float from_f<float>(float x) { return x; }
+template <> __device__ __forceinline__ bf16 from_f<bf16>(float x) { return __float2bfloat16_rn(x); }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// ---------------------------------------------------------------- GEMM row mapping + epilogue
+// (shared by the SIMT and tcgen05 kernels so both produce the same bytes for the same accumulators)
+struct RowMap {
+  int valid;        // row produces output
+  int b;            // sample index
+  int sp;           // interior pixel index (y*W+x) or row-in-sample
+  long long orow;   // output row
+};
+
+__device__ __forceinline__ RowMap map_row(const CrogGemm& g, long long r, long long row_end) {
+  RowMap m;
+  m.valid = r < row_end;
+  m.b = 0; m.sp = 0; m.orow = r;
+  if (!m.valid) return m;
+  if (g.H == 0) {
+    if (g.sample_rows > 0) { m.b = (int)(r / g.sample_rows); m.sp = (int)(r % g.sample_rows); }
+    else m.sp = (int)r;
+    return m;
+  }
+  int y, x;
+  if (g.in_padded) {
+    const int PW = g.W + 2, P = (g.H + 2) * PW;
+    m.b = (int)(r / P);
+    const int rem = (int)(r % P);
+    const int yy = rem / PW, xx = rem % PW;
+    m.valid = (yy >= 1) && (yy <= g.H) && (xx >= 1) && (xx <= g.W);
+    y = yy - 1; x = xx - 1;
+  } else {
+    const int P = g.H * g.W;
+    m.b = (int)(r / P);
+    const int rem = (int)(r % P);
+    y = rem / g.W; x = rem % g.W;
+  }
+  m.sp = y * g.W + x;
+  m.orow = g.out_padded ? ((long long)(m.b * (g.H + 2) + y + 1) * (g.W + 2) + x + 1)
+                        : ((long long)(m.b * g.H + y) * g.W + x);
+  return m;
+}
+
+__device__ __forceinline__ float apply_act(float v, int act) {
+  if (act == CROG_ACT_RELU) return fmaxf(v, 0.f);
+  if (act == CROG_ACT_QUICKGELU) return v / (1.f + __expf(-1.702f * v));
+  return v;
+}
+
+// Epilogue for CNT (multiple of 8) consecutive columns starting at n0 of one valid row.
+// sc/bi point at scale/bias for column n0 (global or shared), or nullptr.
+template <int CNT>
+__device__ __forceinline__ void epilogue_row(const CrogGemm& g, const RowMap& m, int n0, float (&acc)[CNT],
+                                             const float* sc, const float* bi) {
+  const int nvalid = min(CNT, g.N - n0);
+  if (nvalid <= 0) return;
+  if (g.addmat) {
+    const float* ad = g.addmat + (long long)m.sp * g.N + n0;
+#pragma unroll
+    for (int j = 0; j < CNT; ++j) if (j < nvalid) acc[j] += __ldg(ad + j);
+  }
+#pragma unroll
+  for (int j = 0; j < CNT; ++j) {
+    float v = acc[j];
+    if (sc) v *= sc[j];
+    if (bi) v += bi[j];
+    acc[j] = apply_act(v, g.act);
+  }
+  if (g.gate) {
+    const float* gt = g.gate + (long long)m.b * g.N + n0;
+#pragma unroll
+    for (int j = 0; j < CNT; ++j) if (j < nvalid)
+      acc[j] = fmaxf((acc[j] * __ldg(gt + j)) * __ldg(g.scale2 + n0 + j) + __ldg(g.bias2 + n0 + j), 0.f);
+  }
+  const bool full = (nvalid == CNT);
+  if (g.out_dtype == CROG_BF16) {
+    bf16* o = reinterpret_cast<bf16*>(g.out) + m.orow * g.out_ld + n0;
+    const bf16* rs = g.residual ? reinterpret_cast<const bf16*>(g.residual) + m.orow * g.res_ld + n0 : nullptr;
+    if (full) {
+#pragma unroll
+      for (int j = 0; j < CNT; j += 8) {
+        float v[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = acc[j + i];
+        if (rs) {
+          float r8[8]; load8(rs + j, r8);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) { v[i] += r8[i]; if (g.residual_relu) v[i] = fmaxf(v[i], 0.f); }
+        }
+        store8(o + j, v);
+      }
+    } else {
+      for (int j = 0; j < nvalid; ++j) {
+        float v = acc[j];
+        if (rs) { v += to_f(rs[j]); if (g.residual_relu) v = fmaxf(v, 0.f); }
+        o[j] = __float2bfloat16_rn(v);
+      }
+    }
+  } else {
+    float* o = reinterpret_cast<float*>(g.out) + m.orow * g.out_ld + n0;
+    const float* rs = g.residual ? reinterpret_cast<const float*>(g.residual) + m.orow * g.res_ld + n0 : nullptr;
+    if (full) {
+#pragma unroll
+      for (int j = 0; j < CNT; j += 4) {
+        float4 v = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
+        if (rs) {
+          float4 r4 = *reinterpret_cast<const float4*>(rs + j);
+          v.x += r4.x; v.y += r4.y; v.z += r4.z; v.w += r4.w;
+          if (g.residual_relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+        }
+        *reinterpret_cast<float4*>(o + j) = v;
+      }
+    } else {
+      for (int j = 0; j < nvalid; ++j) {
+        float v = acc[j];
+        if (rs) { v += rs[j]; if (g.residual_relu) v = fmaxf(v, 0.f); }
+        o[j] = v;
+      }
+    }
+  }
+}
+
+// tile -> rows. With per-sample weights tiles never straddle samples.
+struct TileRows { long long row0, row_end; int wsample; };
+__device__ __forceinline__ TileRows tile_rows(const CrogGemm& g, int m_tile, int BM) {
+  TileRows t;
+  if (g.w_sample_stride > 0) {
+    const int tps = (g.sample_rows + BM - 1) / BM;
+    t.wsample = m_tile / tps;
+    t.row0 = (long long)t.wsample * g.sample_rows + (long long)(m_tile % tps) * BM;
+    t.row_end = min((long long)(t.wsample + 1) * g.sample_rows, (long long)g.M);
+  } else {
+    t.wsample = 0; t.row0 = (long long)m_tile * BM; t.row_end = g.M;
+  }
+  return t;
+}
+static inline int num_m_tiles(const CrogGemm& g, int BM) {
+  if (g.w_sample_stride > 0) return (g.M / g.sample_rows) * ((g.sample_rows + BM - 1) / BM);
+  return (g.M + BM - 1) / BM;
+}
+__host__ __device__ __forceinline__ int tap_shift(int taps, int tap, int W) {
+  return taps == 9 ? (tap / 3 - 1) * (W + 2) + (tap % 3 - 1) : 0;
+}

@@ -1,0 +1,366 @@
+// Memory-bound glue kernels of the forward: layout / resampling, stem conv1, LayerNorm,
+// embedding, EOT gather, projector weight folding, head split, sigmoid + bicubic.
+// All are coalesced over the channel (innermost NHWC) dimension with 8-wide vector access.
+#include "common.cuh"
+
+namespace {
+
+// ------------------------------------------------------------------ resample (copy / avgpool2 / bilinear x2)
+__device__ __forceinline__ long long pix_row(int b, int y, int x, int H, int W, int padded) {
+  return padded ? ((long long)(b * (H + 2) + y + 1) * (W + 2) + x + 1) : ((long long)(b * H + y) * W + x);
+}
+
+template <typename T, int MODE>
+__global__ void resample_kernel(const T* __restrict__ in, int in_ld, int in_padded, T* __restrict__ out, int out_ld,
+                                int out_padded, int B, int H, int W, int C) {
+  const int OH = MODE == 1 ? H / 2 : (MODE == 2 ? 2 * H : H);
+  const int OW = MODE == 1 ? W / 2 : (MODE == 2 ? 2 * W : W);
+  const int cgs = C / 8;
+  const long long total = (long long)B * OH * OW * cgs;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int cg = (int)(i % cgs);
+    long long p = i / cgs;
+    const int ox = (int)(p % OW); p /= OW;
+    const int oy = (int)(p % OH);
+    const int b = (int)(p / OH);
+    float v[8];
+    if (MODE == 0) {
+      load8(in + pix_row(b, oy, ox, H, W, in_padded) * in_ld + cg * 8, v);
+    } else if (MODE == 1) {
+      float a[8], c[8], d[8];
+      load8(in + pix_row(b, 2 * oy, 2 * ox, H, W, in_padded) * in_ld + cg * 8, v);
+      load8(in + pix_row(b, 2 * oy, 2 * ox + 1, H, W, in_padded) * in_ld + cg * 8, a);
+      load8(in + pix_row(b, 2 * oy + 1, 2 * ox, H, W, in_padded) * in_ld + cg * 8, c);
+      load8(in + pix_row(b, 2 * oy + 1, 2 * ox + 1, H, W, in_padded) * in_ld + cg * 8, d);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = (v[j] + a[j] + c[j] + d[j]) * 0.25f;
+    } else {
+      // F.interpolate(scale_factor=2, mode='bilinear', align_corners=False)
+      const float sy = fmaxf((oy + 0.5f) * 0.5f - 0.5f, 0.f), sx = fmaxf((ox + 0.5f) * 0.5f - 0.5f, 0.f);
+      const int y0 = (int)sy, x0 = (int)sx;
+      const int y1 = min(y0 + 1, H - 1), x1 = min(x0 + 1, W - 1);
+      const float ly = sy - y0, lx = sx - x0, hy = 1.f - ly, hx = 1.f - lx;
+      float a[8], c[8], d[8];
+      load8(in + pix_row(b, y0, x0, H, W, in_padded) * in_ld + cg * 8, v);
+      load8(in + pix_row(b, y0, x1, H, W, in_padded) * in_ld + cg * 8, a);
+      load8(in + pix_row(b, y1, x0, H, W, in_padded) * in_ld + cg * 8, c);
+      load8(in + pix_row(b, y1, x1, H, W, in_padded) * in_ld + cg * 8, d);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = hy * (hx * v[j] + lx * a[j]) + ly * (hx * c[j] + lx * d[j]);
+    }
+    store8(out + pix_row(b, oy, ox, OH, OW, out_padded) * out_ld + cg * 8, v);
+  }
+}
+
+// ------------------------------------------------------------------ stem conv1 (3->cout, 3x3, stride 2, pad 1)
+template <typename T>
+__global__ void stem_conv1_kernel(const float* __restrict__ img, int B, int Hin, int Win, const float* __restrict__ w,
+                                  const float* __restrict__ scale, const float* __restrict__ bias, int cout,
+                                  T* __restrict__ out, int out_ld) {
+  extern __shared__ float sw[];  // [27][cout] + scale + bias
+  for (int i = threadIdx.x; i < 27 * cout; i += blockDim.x) {
+    const int co = i % cout, k = i / cout;
+    sw[i] = w[co * 27 + k];
+  }
+  for (int i = threadIdx.x; i < cout; i += blockDim.x) { sw[27 * cout + i] = scale[i]; sw[28 * cout + i] = bias[i]; }
+  __syncthreads();
+  const int OH = Hin / 2, OW = Win / 2;
+  const long long total = (long long)B * OH * OW;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int ox = (int)(i % OW);
+    const int oy = (int)((i / OW) % OH);
+    const int b = (int)(i / ((long long)OW * OH));
+    float x[27];
+#pragma unroll
+    for (int ci = 0; ci < 3; ++ci)
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+          const int iy = 2 * oy + ky - 1, ix = 2 * ox + kx - 1;
+          x[ci * 9 + ky * 3 + kx] = (iy >= 0 && iy < Hin && ix >= 0 && ix < Win)
+                                        ? __ldg(img + ((long long)(b * 3 + ci) * Hin + iy) * Win + ix) : 0.f;
+        }
+    T* o = out + pix_row(b, oy, ox, OH, OW, 1) * out_ld;
+    for (int c0 = 0; c0 < out_ld; c0 += 8) {
+      float v[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int co = c0 + j;
+        float acc = 0.f;
+        if (co < cout) {
+#pragma unroll
+          for (int k = 0; k < 27; ++k) acc = fmaf(x[k], sw[k * cout + co], acc);
+          acc = fmaxf(acc * sw[27 * cout + co] + sw[28 * cout + co], 0.f);
+        }
+        v[j] = acc;
+      }
+      store8(o + c0, v);
+    }
+  }
+}
+
+// ------------------------------------------------------------------ LayerNorm (one warp per row)
+template <typename TI, typename TO, int CH>  // D = CH * 256
+__global__ void layernorm_kernel(const TI* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                 const float* __restrict__ residual, TO* __restrict__ out, long long rows, float eps) {
+  constexpr int D = CH * 256;
+  const int lane = threadIdx.x & 31;
+  const long long row = blockIdx.x * (long long)(blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  float v[CH][8];
+  float s = 0.f;
+#pragma unroll
+  for (int c = 0; c < CH; ++c) {
+    load8(x + row * D + (c * 32 + lane) * 8, v[c]);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s += v[c][j];
+  }
+  const float mean = warp_sum(s) * (1.f / D);
+  float q = 0.f;
+#pragma unroll
+  for (int c = 0; c < CH; ++c)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { const float d = v[c][j] - mean; q += d * d; }
+  const float rstd = rsqrtf(warp_sum(q) * (1.f / D) + eps);
+#pragma unroll
+  for (int c = 0; c < CH; ++c) {
+    const int col = (c * 32 + lane) * 8;
+    float g8[8], b8[8], o8[8];
+    load8(gamma + col, g8); load8(beta + col, b8);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o8[j] = (v[c][j] - mean) * rstd * g8[j] + b8[j];
+    if (residual) {
+      float r8[8]; load8(residual + row * D + col, r8);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o8[j] += r8[j];
+    }
+    store8(out + row * D + col, o8);
+  }
+}
+
+// ------------------------------------------------------------------ text embedding / EOT gather
+__global__ void embed_kernel(const int64_t* __restrict__ word, const float* __restrict__ emb, const float* __restrict__ pos,
+                             float* __restrict__ out, int B, int L, int D) {
+  const int row = blockIdx.x, l = row % L;
+  const long long id = word[row];
+  for (int c = threadIdx.x * 4; c < D; c += blockDim.x * 4) {
+    const float4 e = *reinterpret_cast<const float4*>(emb + id * D + c);
+    const float4 p = *reinterpret_cast<const float4*>(pos + (long long)l * D + c);
+    *reinterpret_cast<float4*>(out + (long long)row * D + c) = make_float4(e.x + p.x, e.y + p.y, e.z + p.z, e.w + p.w);
+  }
+}
+
+template <typename TI, typename TO>
+__global__ void gather_eot_kernel(const int64_t* __restrict__ word, const TI* __restrict__ x, TO* __restrict__ out, int L, int D) {
+  const int b = blockIdx.x;
+  __shared__ int s_arg;
+  if (threadIdx.x == 0) {
+    int arg = 0; long long best = word[(long long)b * L];
+    for (int l = 1; l < L; ++l) { const long long t = word[(long long)b * L + l]; if (t > best) { best = t; arg = l; } }
+    s_arg = arg;
+  }
+  __syncthreads();
+  const TI* src = x + ((long long)b * L + s_arg) * D;
+  for (int c = threadIdx.x; c < D; c += blockDim.x) out[(long long)b * D + c] = from_f<TO>(to_f(src[c]));
+}
+
+// ------------------------------------------------------------------ projector: txt linear + fold with vis.4
+template <typename T>
+__global__ void txt_linear_kernel(const T* __restrict__ state, const float* __restrict__ w, const float* __restrict__ bias,
+                                  float* __restrict__ out, int B, int K, int O) {
+  const int lane = threadIdx.x & 31;
+  const long long wid = blockIdx.x * (long long)(blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (wid >= (long long)B * O) return;
+  const int o = (int)(wid % O), b = (int)(wid / O);
+  float acc = 0.f;
+  for (int k = lane; k < K; k += 32) acc = fmaf(to_f(state[(long long)b * K + k]), __ldg(w + (long long)o * K + k), acc);
+  acc = warp_sum(acc);
+  if (lane == 0) out[(long long)b * O + o] = acc + bias[o];
+}
+
+template <typename T>
+__global__ void dynw_fold_kernel(const float* __restrict__ t, const float* __restrict__ vw, const float* __restrict__ vb,
+                                 T* __restrict__ wfold, int B, int C, int NH, int NH_pad, int Cpad) {
+  // one block per (b, h, tap); threads over j
+  const int tap = blockIdx.x % 9, h = (blockIdx.x / 9) % NH_pad, b = blockIdx.x / (9 * NH_pad);
+  const int O = 9 * C + 1;
+  extern __shared__ float s_w[];  // w_dyn[b, :, tap]
+  for (int c = threadIdx.x; c < C; c += blockDim.x) s_w[c] = t[(long long)b * O + c * 9 + tap];
+  __syncthreads();
+  T* dst = wfold + ((long long)(b * NH_pad + h) * 9 + tap) * Cpad;
+  for (int j = threadIdx.x; j < Cpad; j += blockDim.x) {
+    float acc = 0.f;
+    if (h < NH) {
+      if (j < C) {
+        for (int c = 0; c < C; ++c) acc = fmaf(s_w[c], __ldg(vw + (long long)(h * C + c) * C + j), acc);
+      } else if (j == C) {
+        for (int c = 0; c < C; ++c) acc = fmaf(s_w[c], __ldg(vb + h * C + c), acc);
+        if (tap == 4) acc += t[(long long)b * O + 9 * C];
+      }
+    }
+    dst[j] = from_f<T>(acc);
+  }
+}
+
+__global__ void split_heads_kernel(const float* __restrict__ in, int ld, float* __restrict__ out, long long rows, int NH) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= rows) return;
+  for (int h = 0; h < NH; ++h) out[(long long)h * rows + i] = in[i * ld + h];
+}
+
+// ------------------------------------------------------------------ sigmoid + bicubic (align_corners=True, A=-0.75)
+__device__ __forceinline__ float cc1(float x) { const float A = -0.75f; return ((A + 2.f) * x - (A + 3.f)) * x * x + 1.f; }
+__device__ __forceinline__ float cc2(float x) { const float A = -0.75f; return ((A * x - 5.f * A) * x + 8.f * A) * x - 4.f * A; }
+
+__global__ void sigmoid_bicubic_kernel(const float* __restrict__ in, float* __restrict__ out, int NP, int B, int Hin, int Win,
+                                       int Hout, int Wout, uint32_t sig_mask, float sh, float sw) {
+  const long long total = (long long)NP * B * Hout * Wout;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int ox = (int)(i % Wout);
+    const int oy = (int)((i / Wout) % Hout);
+    const long long pl = i / ((long long)Wout * Hout);  // plane index p*B + b
+    const int p = (int)(pl / B);
+    const bool sig = (sig_mask >> p) & 1u;
+    const float ry = sh * oy, rx = sw * ox;
+    const int iy = (int)floorf(ry), ix = (int)floorf(rx);
+    const float ty = ry - iy, tx = rx - ix;
+    const float wx[4] = {cc2(tx + 1.f), cc1(tx), cc1(1.f - tx), cc2(2.f - tx)};
+    const float wy[4] = {cc2(ty + 1.f), cc1(ty), cc1(1.f - ty), cc2(2.f - ty)};
+    const float* src = in + pl * (long long)Hin * Win;
+    float acc = 0.f;
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+      const int yy = min(max(iy - 1 + a, 0), Hin - 1);
+      float r = 0.f;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const int xx = min(max(ix - 1 + c, 0), Win - 1);
+        float v = __ldg(src + (long long)yy * Win + xx);
+        if (sig) v = 1.f / (1.f + expf(-v));
+        r += v * wx[c];
+      }
+      acc += r * wy[a];
+    }
+    out[i] = acc;
+  }
+}
+
+inline int grid_for(long long total, int block) {
+  long long g = (total + block - 1) / block;
+  const long long cap = 148LL * 32;
+  return (int)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+}  // namespace
+
+extern "C" int crog_resample(const void* in, int32_t in_ld, int32_t in_padded, void* out, int32_t out_ld, int32_t out_padded,
+                             int32_t B, int32_t H, int32_t W, int32_t C, int32_t mode, int32_t dtype, void* stream) {
+  CROG_REQUIRE(C % 8 == 0 && in_ld % 8 == 0 && out_ld % 8 == 0, CROG_E_BADSHAPE, "resample: channels must be multiples of 8");
+  CROG_REQUIRE(aligned16(in) && aligned16(out), CROG_E_BADALIGN, "resample: pointers must be 16B aligned");
+  CROG_REQUIRE(mode >= 0 && mode <= 2, CROG_E_BADSHAPE, "resample: bad mode %d", mode);
+  if (mode == 1) CROG_REQUIRE(H % 2 == 0 && W % 2 == 0, CROG_E_BADSHAPE, "avgpool2 needs even H,W");
+  const int OH = mode == 1 ? H / 2 : (mode == 2 ? 2 * H : H), OW = mode == 1 ? W / 2 : (mode == 2 ? 2 * W : W);
+  const long long total = (long long)B * OH * OW * (C / 8);
+  if (total == 0) return CROG_OK;
+  const int g = grid_for(total, 256);
+  cudaStream_t s = (cudaStream_t)stream;
+#define RS(T, M) resample_kernel<T, M><<<g, 256, 0, s>>>((const T*)in, in_ld, in_padded, (T*)out, out_ld, out_padded, B, H, W, C)
+  if (dtype == CROG_F32) { if (mode == 0) RS(float, 0); else if (mode == 1) RS(float, 1); else RS(float, 2); }
+  else { if (mode == 0) RS(bf16, 0); else if (mode == 1) RS(bf16, 1); else RS(bf16, 2); }
+#undef RS
+  CROG_LAUNCH_OK("resample");
+  return CROG_OK;
+}
+
+extern "C" int crog_stem_conv1(const float* img, int32_t B, int32_t Hin, int32_t Win, const float* w, const float* scale,
+                               const float* bias, int32_t cout, void* out, int32_t out_ld, int32_t out_dtype, void* stream) {
+  CROG_REQUIRE(Hin % 2 == 0 && Win % 2 == 0 && out_ld % 8 == 0 && cout <= out_ld, CROG_E_BADSHAPE, "stem_conv1: bad shape");
+  const long long total = (long long)B * (Hin / 2) * (Win / 2);
+  if (total == 0) return CROG_OK;
+  const int g = grid_for(total, 128);
+  const size_t sm = (size_t)(29 * cout) * sizeof(float);
+  if (out_dtype == CROG_F32)
+    stem_conv1_kernel<float><<<g, 128, sm, (cudaStream_t)stream>>>(img, B, Hin, Win, w, scale, bias, cout, (float*)out, out_ld);
+  else
+    stem_conv1_kernel<bf16><<<g, 128, sm, (cudaStream_t)stream>>>(img, B, Hin, Win, w, scale, bias, cout, (bf16*)out, out_ld);
+  CROG_LAUNCH_OK("stem_conv1");
+  return CROG_OK;
+}
+
+extern "C" int crog_layernorm(const void* x, int32_t x_dtype, const float* gamma, const float* beta, const float* residual,
+                              void* out, int32_t out_dtype, int64_t rows, int32_t D, float eps, void* stream) {
+  CROG_REQUIRE(D == 512 || D == 2048 || D == 1024 || D == 256, CROG_E_BADSHAPE, "layernorm: D=%d unsupported", D);
+  if (rows == 0) return CROG_OK;
+  const int wpb = 8;
+  const int g = (int)((rows + wpb - 1) / wpb);
+  cudaStream_t s = (cudaStream_t)stream;
+#define LN(TI, TO, CH) layernorm_kernel<TI, TO, CH><<<g, wpb * 32, 0, s>>>((const TI*)x, gamma, beta, residual, (TO*)out, rows, eps)
+#define LN_D(TI, TO) do { if (D == 256) LN(TI, TO, 1); else if (D == 512) LN(TI, TO, 2); else if (D == 1024) LN(TI, TO, 4); else LN(TI, TO, 8); } while (0)
+  if (x_dtype == CROG_F32 && out_dtype == CROG_F32) LN_D(float, float);
+  else if (x_dtype == CROG_F32) LN_D(float, bf16);
+  else if (out_dtype == CROG_F32) LN_D(bf16, float);
+  else LN_D(bf16, bf16);
+#undef LN_D
+#undef LN
+  CROG_LAUNCH_OK("layernorm");
+  return CROG_OK;
+}
+
+extern "C" int crog_embed_tokens(const int64_t* word, const float* emb, const float* pos, float* out, int32_t B, int32_t L,
+                                 int32_t D, void* stream) {
+  CROG_REQUIRE(D % 4 == 0, CROG_E_BADSHAPE, "embed: D %% 4");
+  if (B * L == 0) return CROG_OK;
+  embed_kernel<<<B * L, 128, 0, (cudaStream_t)stream>>>(word, emb, pos, out, B, L, D);
+  CROG_LAUNCH_OK("embed");
+  return CROG_OK;
+}
+
+extern "C" int crog_gather_eot(const int64_t* word, const void* x, int32_t x_dtype, void* out, int32_t out_dtype, int32_t B,
+                               int32_t L, int32_t D, void* stream) {
+  if (B == 0) return CROG_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (x_dtype == CROG_F32 && out_dtype == CROG_F32) gather_eot_kernel<float, float><<<B, 128, 0, s>>>(word, (const float*)x, (float*)out, L, D);
+  else if (x_dtype == CROG_F32) gather_eot_kernel<float, bf16><<<B, 128, 0, s>>>(word, (const float*)x, (bf16*)out, L, D);
+  else if (out_dtype == CROG_F32) gather_eot_kernel<bf16, float><<<B, 128, 0, s>>>(word, (const bf16*)x, (float*)out, L, D);
+  else gather_eot_kernel<bf16, bf16><<<B, 128, 0, s>>>(word, (const bf16*)x, (bf16*)out, L, D);
+  CROG_LAUNCH_OK("gather_eot");
+  return CROG_OK;
+}
+
+extern "C" int crog_dynw_fold(const void* state, int32_t state_dtype, const float* txt_w, const float* txt_b, const float* v_w,
+                              const float* v_b, float* scratch, void* wfold, int32_t dtype, int32_t B, int32_t word_dim,
+                              int32_t C, int32_t NH, int32_t NH_pad, int32_t Cpad, void* stream) {
+  CROG_REQUIRE(Cpad > C && NH <= NH_pad, CROG_E_BADSHAPE, "dynw_fold: Cpad must exceed C (ones channel)");
+  if (B == 0) return CROG_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  const int O = 9 * C + 1;
+  const long long warps = (long long)B * O;
+  const int g1 = (int)((warps + 7) / 8);
+  if (state_dtype == CROG_F32) txt_linear_kernel<float><<<g1, 256, 0, s>>>((const float*)state, txt_w, txt_b, scratch, B, word_dim, O);
+  else txt_linear_kernel<bf16><<<g1, 256, 0, s>>>((const bf16*)state, txt_w, txt_b, scratch, B, word_dim, O);
+  CROG_LAUNCH_OK("txt_linear");
+  const int g2 = B * NH_pad * 9;
+  if (dtype == CROG_F32) dynw_fold_kernel<float><<<g2, 128, C * sizeof(float), s>>>(scratch, v_w, v_b, (float*)wfold, B, C, NH, NH_pad, Cpad);
+  else dynw_fold_kernel<bf16><<<g2, 128, C * sizeof(float), s>>>(scratch, v_w, v_b, (bf16*)wfold, B, C, NH, NH_pad, Cpad);
+  CROG_LAUNCH_OK("dynw_fold");
+  return CROG_OK;
+}
+
+extern "C" int crog_split_heads(const float* in, int32_t ld, float* out, int64_t rows, int32_t NH, void* stream) {
+  if (rows == 0) return CROG_OK;
+  split_heads_kernel<<<(int)((rows + 255) / 256), 256, 0, (cudaStream_t)stream>>>(in, ld, out, rows, NH);
+  CROG_LAUNCH_OK("split_heads");
+  return CROG_OK;
+}
+
+extern "C" int crog_sigmoid_bicubic(const float* in, float* out, int32_t NP, int32_t B, int32_t Hin, int32_t Win, int32_t Hout,
+                                    int32_t Wout, uint32_t sigmoid_mask, void* stream) {
+  const long long total = (long long)NP * B * Hout * Wout;
+  if (total == 0) return CROG_OK;
+  const float sh = Hout > 1 ? (float)(Hin - 1) / (float)(Hout - 1) : 0.f;
+  const float sw = Wout > 1 ? (float)(Win - 1) / (float)(Wout - 1) : 0.f;
+  sigmoid_bicubic_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(in, out, NP, B, Hin, Win, Hout, Wout, sigmoid_mask, sh, sw);
+  CROG_LAUNCH_OK("sigmoid_bicubic");
+  return CROG_OK;
+}

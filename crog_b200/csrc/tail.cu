@@ -1,0 +1,516 @@
+// Grasp decode + Jaccard tail (utils/grasp_eval.py:289-374 of the reference) on the device.
+//
+//  K9  peak_scan_kernel   streaming 5x5 max-filter equality + threshold + border test; every warp
+//                         owns a 128-column strip of a row band, keeps a 5-row window in registers
+//                         (float4 per lane, neighbours by shuffle) and ballot-compacts candidates
+//                         into a per-warp shared-memory list, then keeps its best TSEL keys.
+//  K10 peak_select_kernel one warp per map: merges the per-warp lists, runs the greedy min-distance
+//                         suppression in key order (value desc, row-major index asc), proves the
+//                         result exact (or flags the map), gathers sin/cos/width and decodes grasps.
+//      peak_exact_kernel  exact fallback for flagged maps (heavy plateaus): K full-map arg-max sweeps.
+//  K11 jaccard_kernel     one CTA per sample: integer rasterisation of rotated rectangles as
+//                         128 x 160-bit row masks in shared memory, popc(A&B) / popc(A|B), J flags,
+//                         counters accumulated with one atomicAdd per sample.
+#include <math.h>
+
+#include "common.cuh"
+#include "tail_geom.h"
+
+namespace {
+
+constexpr int BAND = 32;       // output rows per CTA band
+constexpr int STRIP = 128;     // columns per warp
+constexpr int CAPW = 512;      // per-warp candidate list capacity
+constexpr int TSEL = 32;       // keys kept per warp segment
+constexpr int MAXK = 32;
+
+struct SegHeader {
+  int count;
+  int truncated;
+  unsigned long long worst_kept;  // valid when truncated
+  float vmin, vmax;
+  int pad[2];
+};
+constexpr int SEG_BYTES = (int)sizeof(SegHeader) + TSEL * 8;
+
+__device__ __forceinline__ uint32_t f2ord(float f) {
+  uint32_t u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float ord2f(uint32_t u) {
+  return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
+}
+__device__ __forceinline__ unsigned long long make_key(float v, int idx) {
+  return ((unsigned long long)f2ord(v) << 32) | (unsigned long long)(0xffffffffu - (uint32_t)idx);
+}
+__device__ __forceinline__ int key_idx(unsigned long long k) { return (int)(0xffffffffu - (uint32_t)(k & 0xffffffffull)); }
+__device__ __forceinline__ float key_val(unsigned long long k) { return ord2f((uint32_t)(k >> 32)); }
+__device__ __forceinline__ unsigned long long warp_max_u64(unsigned long long k) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const unsigned long long t = __shfl_xor_sync(0xffffffffu, k, o);
+    k = t > k ? t : k;
+  }
+  return k;
+}
+__device__ __forceinline__ float max3(float a, float b, float c) { return fmaxf(fmaxf(a, b), c); }
+
+// keep the best `keep` keys of list[0..n) (n <= CAPW) at the front, in descending order
+__device__ void warp_select_top(unsigned long long* list, int n, int keep, unsigned long long* top, int lane) {
+  for (int t = 0; t < keep; ++t) {
+    unsigned long long best = 0ull;
+    for (int i = lane; i < n; i += 32) { const unsigned long long k = list[i]; best = k > best ? k : best; }
+    best = warp_max_u64(best);
+    for (int i = lane; i < n; i += 32) if (list[i] == best) list[i] = 0ull;  // keys are unique
+    if (lane == 0) top[t] = best;
+    __syncwarp();
+  }
+  for (int i = lane; i < keep; i += 32) list[i] = top[i];
+  __syncwarp();
+}
+
+__global__ void __launch_bounds__(256) peak_scan_kernel(const float* __restrict__ q, int H, int W, float thr, int nwarps,
+                                                        uint8_t* __restrict__ ws) {
+  extern __shared__ unsigned long long s_lists[];  // [warps][CAPW + TSEL]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp >= nwarps) return;
+  const int band = blockIdx.x, b = blockIdx.y, nbands = gridDim.x;
+  unsigned long long* list = s_lists + warp * (CAPW + TSEL);
+  unsigned long long* top = list + CAPW;
+  const float* img = q + (long long)b * H * W;
+  const int c0 = warp * STRIP + lane * 4;
+  const int y0 = band * BAND, y1 = min(y0 + BAND, H);
+  const bool vec = (W % 4 == 0);
+  const float NEG = -INFINITY;
+
+  float4 raw[5], hm[5];
+#pragma unroll
+  for (int u = 0; u < 5; ++u) { raw[u] = make_float4(NEG, NEG, NEG, NEG); hm[u] = raw[u]; }
+  int count = 0, truncated = 0;
+  float vmin = INFINITY, vmax = -INFINITY;
+
+  for (int rbase = y0 - 2; rbase < y1 + 2; rbase += 5) {
+#pragma unroll
+    for (int u = 0; u < 5; ++u) {
+      const int r = rbase + u;
+      if (r >= y1 + 2) break;  // warp-uniform
+      float4 v = make_float4(NEG, NEG, NEG, NEG);
+      float l2 = NEG, l1 = NEG, r1 = NEG, r2 = NEG;
+      if (r >= 0 && r < H) {
+        const float* rowp = img + (long long)r * W;
+        if (vec && c0 + 3 < W) v = __ldg(reinterpret_cast<const float4*>(rowp + c0));
+        else {
+          if (c0 < W) v.x = __ldg(rowp + c0);
+          if (c0 + 1 < W) v.y = __ldg(rowp + c0 + 1);
+          if (c0 + 2 < W) v.z = __ldg(rowp + c0 + 2);
+          if (c0 + 3 < W) v.w = __ldg(rowp + c0 + 3);
+        }
+        if (lane == 0 && c0 >= 2) { l2 = __ldg(rowp + c0 - 2); l1 = __ldg(rowp + c0 - 1); }
+        if (lane == 31) { if (c0 + 4 < W) r1 = __ldg(rowp + c0 + 4); if (c0 + 5 < W) r2 = __ldg(rowp + c0 + 5); }
+      }
+      {
+        const float sl2 = __shfl_up_sync(0xffffffffu, v.z, 1), sl1 = __shfl_up_sync(0xffffffffu, v.w, 1);
+        const float sr1 = __shfl_down_sync(0xffffffffu, v.x, 1), sr2 = __shfl_down_sync(0xffffffffu, v.y, 1);
+        if (lane != 0) { l2 = sl2; l1 = sl1; }
+        if (lane != 31) { r1 = sr1; r2 = sr2; }
+      }
+      if (r >= y0 && r < y1) {  // strip min/max over owned pixels (trivial-image test)
+        if (c0 < W) { vmin = fminf(vmin, v.x); vmax = fmaxf(vmax, v.x); }
+        if (c0 + 1 < W) { vmin = fminf(vmin, v.y); vmax = fmaxf(vmax, v.y); }
+        if (c0 + 2 < W) { vmin = fminf(vmin, v.z); vmax = fmaxf(vmax, v.z); }
+        if (c0 + 3 < W) { vmin = fminf(vmin, v.w); vmax = fmaxf(vmax, v.w); }
+      }
+      const float mxyz = max3(v.x, v.y, v.z), myzw = max3(v.y, v.z, v.w);
+      raw[u] = v;
+      hm[u] = make_float4(max3(mxyz, l2, l1), max3(mxyz, l1, v.w), max3(myzw, v.x, r1), max3(myzw, r1, r2));
+      // centre row r-2 now has its five horizontal maxima (rows r-4..r) in the ring
+      const int rc = r - 2;
+      if (rc >= y0 && rc < y1 && rc >= 2 && rc < H - 2) {
+        const float4 ctr = raw[(u + 3) % 5];
+        float4 vm;
+        vm.x = max3(max3(hm[0].x, hm[1].x, hm[2].x), hm[3].x, hm[4].x);
+        vm.y = max3(max3(hm[0].y, hm[1].y, hm[2].y), hm[3].y, hm[4].y);
+        vm.z = max3(max3(hm[0].z, hm[1].z, hm[2].z), hm[3].z, hm[4].z);
+        vm.w = max3(max3(hm[0].w, hm[1].w, hm[2].w), hm[3].w, hm[4].w);
+        const bool k0 = ctr.x == vm.x && ctr.x > thr && c0 >= 2 && c0 < W - 2;
+        const bool k1 = ctr.y == vm.y && ctr.y > thr && c0 + 1 >= 2 && c0 + 1 < W - 2;
+        const bool k2 = ctr.z == vm.z && ctr.z > thr && c0 + 2 < W - 2;
+        const bool k3 = ctr.w == vm.w && ctr.w > thr && c0 + 3 < W - 2;
+        if (__ballot_sync(0xffffffffu, k0 | k1 | k2 | k3)) {
+          if (count + 128 > CAPW) {  // make room: keep the best TSEL so far
+            __syncwarp();
+            warp_select_top(list, count, TSEL, top, lane);
+            count = TSEL; truncated = 1;
+          }
+          const uint32_t lt = (1u << lane) - 1u;
+          const bool kk[4] = {k0, k1, k2, k3};
+          const float cv[4] = {ctr.x, ctr.y, ctr.z, ctr.w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint32_t m = __ballot_sync(0xffffffffu, kk[j]);
+            if (kk[j]) list[count + __popc(m & lt)] = make_key(cv[j], rc * W + c0 + j);
+            count += __popc(m);
+          }
+        }
+      }
+    }
+  }
+  __syncwarp();
+  if (count > TSEL) { warp_select_top(list, count, TSEL, top, lane); count = TSEL; truncated = 1; }
+  vmin = -warp_max(-vmin); vmax = warp_max(vmax);
+  uint8_t* seg = ws + ((long long)(b * nbands + band) * nwarps + warp) * SEG_BYTES;
+  if (lane == 0) {
+    SegHeader h;
+    h.count = count; h.truncated = truncated;
+    h.worst_kept = truncated ? list[TSEL - 1] : 0ull;
+    h.vmin = vmin; h.vmax = vmax; h.pad[0] = h.pad[1] = 0;
+    *reinterpret_cast<SegHeader*>(seg) = h;
+  }
+  unsigned long long* keys = reinterpret_cast<unsigned long long*>(seg + sizeof(SegHeader));
+  for (int i = lane; i < count; i += 32) keys[i] = list[i];
+}
+
+// float32(atan2(double, double)) * 0.5f, then the NumPy-1.24 float64 promotions (App. A.3)
+__device__ __forceinline__ void decode_grasp(const float* s, const float* c, const float* w, long long o, int row, int col,
+                                             double* g) {
+  const float ang = __fmul_rn((float)atan2((double)s[o], (double)c[o]), 0.5f);
+  g[0] = (double)col; g[1] = (double)row;
+  g[2] = (double)w[o] * 100.0;
+  g[3] = 20.0;
+  g[4] = (double)ang / 3.141592653589793 * 180.0;
+}
+
+__global__ void peak_select_kernel(const float* __restrict__ sin_m, const float* __restrict__ cos_m,
+                                   const float* __restrict__ wid, int B, int H, int W, int K, int nseg,
+                                   const uint8_t* __restrict__ ws, int* __restrict__ flags, int* __restrict__ peaks,
+                                   int* __restrict__ n_peaks, double* __restrict__ grasps) {
+  const int lane = threadIdx.x & 31;
+  const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (b >= B) return;
+  const uint8_t* base = ws + (long long)b * nseg * SEG_BYTES;
+  // bound D: best "worst kept" key over truncated segments; min/max for the trivial-image rule
+  unsigned long long D = 0ull;
+  float vmin = INFINITY, vmax = -INFINITY;
+  for (int s = lane; s < nseg; s += 32) {
+    const SegHeader* h = reinterpret_cast<const SegHeader*>(base + (long long)s * SEG_BYTES);
+    if (h->truncated && h->worst_kept > D) D = h->worst_kept;
+    vmin = fminf(vmin, h->vmin); vmax = fmaxf(vmax, h->vmax);
+  }
+  D = warp_max_u64(D);
+  vmin = -warp_max(-vmin); vmax = warp_max(vmax);
+  const bool trivial = (vmin == vmax);
+  int acc_r[MAXK], acc_c[MAXK];
+  int nacc = 0, flag = 0;
+  unsigned long long prev = ~0ull;
+  while (!trivial && nacc < K) {
+    unsigned long long best = 0ull;
+    for (int e = lane; e < nseg * TSEL; e += 32) {
+      const int s = e / TSEL, i = e % TSEL;
+      const SegHeader* h = reinterpret_cast<const SegHeader*>(base + (long long)s * SEG_BYTES);
+      if (i < h->count) {
+        const unsigned long long k = reinterpret_cast<const unsigned long long*>(base + (long long)s * SEG_BYTES + sizeof(SegHeader))[i];
+        if (k < prev && k > best) best = k;
+      }
+    }
+    best = warp_max_u64(best);
+    if (best == 0ull) { if (D != 0ull) flag = 1; break; }  // exhausted; dropped candidates may remain
+    if (best < D) { flag = 1; break; }                      // a dropped candidate could precede this one
+    prev = best;
+    const int idx = key_idx(best), r = idx / W, c = idx % W;
+    bool ok = true;
+    for (int j = 0; j < nacc; ++j) ok = ok && (max(abs(acc_r[j] - r), abs(acc_c[j] - c)) >= 2);
+    if (ok) { acc_r[nacc] = r; acc_c[nacc] = c; ++nacc; }
+  }
+  if (lane == 0) {
+    flags[b] = flag;
+    n_peaks[b] = nacc;
+    const long long plane = (long long)b * H * W;
+    for (int j = 0; j < K; ++j) {
+      double* g = grasps + ((long long)b * K + j) * 5;
+      if (j < nacc) {
+        peaks[((long long)b * K + j) * 2] = acc_r[j]; peaks[((long long)b * K + j) * 2 + 1] = acc_c[j];
+        decode_grasp(sin_m + plane, cos_m + plane, wid + plane, (long long)acc_r[j] * W + acc_c[j], acc_r[j], acc_c[j], g);
+      } else {
+        peaks[((long long)b * K + j) * 2] = -1; peaks[((long long)b * K + j) * 2 + 1] = -1;
+        g[0] = g[1] = g[2] = g[3] = g[4] = 0.0;
+      }
+    }
+  }
+}
+
+// Exact fallback: one CTA per flagged map, K sweeps of "best remaining candidate".
+__global__ void __launch_bounds__(256) peak_exact_kernel(const float* __restrict__ q, const float* __restrict__ sin_m,
+                                                         const float* __restrict__ cos_m, const float* __restrict__ wid,
+                                                         int H, int W, int K, float thr, const int* __restrict__ flags,
+                                                         int* __restrict__ peaks, int* __restrict__ n_peaks,
+                                                         double* __restrict__ grasps) {
+  const int b = blockIdx.x;
+  if (!flags[b]) return;
+  __shared__ unsigned long long s_red[8];
+  __shared__ int s_r[MAXK], s_c[MAXK];
+  __shared__ int s_n;
+  const float* img = q + (long long)b * H * W;
+  if (threadIdx.x == 0) s_n = 0;
+  __syncthreads();
+  unsigned long long prev = ~0ull;
+  for (int sweep = 0; sweep < K * 9 + 1; ++sweep) {  // every acceptance rejects at most 8 others
+    const int nacc = s_n;
+    if (nacc >= K) break;
+    unsigned long long best = 0ull;
+    for (int p = threadIdx.x; p < H * W; p += blockDim.x) {
+      const int r = p / W, c = p % W;
+      if (r < 2 || r >= H - 2 || c < 2 || c >= W - 2) continue;
+      const float v = img[p];
+      if (!(v > thr)) continue;
+      const unsigned long long k = make_key(v, p);
+      if (k >= prev || k <= best) continue;
+      bool ismax = true;
+      for (int dy = -2; dy <= 2 && ismax; ++dy)
+        for (int dx = -2; dx <= 2; ++dx)
+          if (img[(r + dy) * W + c + dx] > v) { ismax = false; break; }
+      if (ismax) best = k;
+    }
+    best = warp_max_u64(best);
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = best;
+    __syncthreads();
+    best = 0ull;
+    for (int i = 0; i < (blockDim.x >> 5); ++i) best = s_red[i] > best ? s_red[i] : best;
+    __syncthreads();
+    if (best == 0ull) break;
+    prev = best;
+    if (threadIdx.x == 0) {
+      const int idx = key_idx(best), r = idx / W, c = idx % W;
+      bool ok = true;
+      for (int j = 0; j < nacc; ++j) ok = ok && (max(abs(s_r[j] - r), abs(s_c[j] - c)) >= 2);
+      if (ok) { s_r[nacc] = r; s_c[nacc] = c; s_n = nacc + 1; }
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    const int nacc = s_n;
+    n_peaks[b] = nacc;
+    const long long plane = (long long)b * H * W;
+    for (int j = 0; j < K; ++j) {
+      double* g = grasps + ((long long)b * K + j) * 5;
+      if (j < nacc) {
+        peaks[((long long)b * K + j) * 2] = s_r[j]; peaks[((long long)b * K + j) * 2 + 1] = s_c[j];
+        decode_grasp(sin_m + plane, cos_m + plane, wid + plane, (long long)s_r[j] * W + s_c[j], s_r[j], s_c[j], g);
+      } else {
+        peaks[((long long)b * K + j) * 2] = -1; peaks[((long long)b * K + j) * 2 + 1] = -1;
+        g[0] = g[1] = g[2] = g[3] = g[4] = 0.0;
+      }
+    }
+  }
+}
+
+__global__ void angle_map_kernel(const float* __restrict__ s, const float* __restrict__ c, float* __restrict__ out, long long n) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    out[i] = __fmul_rn((float)atan2((double)s[i], (double)c[i]), 0.5f);
+}
+
+// ------------------------------------------------------------------ Jaccard
+constexpr int JT = 128;  // threads per sample CTA
+
+__device__ __forceinline__ int block_sum(int v, int* s_red) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  int t = 0;
+  for (int i = 0; i < (JT >> 5); ++i) t += s_red[i];
+  return t;
+}
+
+// pixel count of one rectangle / of the intersection of two, exact for any size (slow path)
+__device__ int slow_count(const TgRect* A, const TgRect* Bq, int* s_red) {
+  const int x0 = Bq ? max(A->x0, Bq->x0) : A->x0, x1 = Bq ? min(A->x1, Bq->x1) : A->x1;
+  const int y0 = Bq ? max(A->y0, Bq->y0) : A->y0, y1 = Bq ? min(A->y1, Bq->y1) : A->y1;
+  int cnt = 0;
+  if (x0 <= x1 && y0 <= y1) {
+    const int wdt = y1 - y0 + 1, tot = (x1 - x0 + 1) * wdt;
+    for (int p = threadIdx.x; p < tot; p += JT) {
+      const int X = x0 + p / wdt, Y = y0 + p % wdt;
+      if (tg_point_painted(A, X, Y) && (!Bq || tg_point_painted(Bq, X, Y))) ++cnt;
+    }
+  }
+  return block_sum(cnt, s_red);
+}
+
+__global__ void __launch_bounds__(JT) jaccard_kernel(const double* __restrict__ grasps, const int* __restrict__ n_peaks, int K,
+                                                     double* __restrict__ gt, const int* __restrict__ gt_count, int Mmax,
+                                                     int* __restrict__ inter_out, int* __restrict__ uni_out,
+                                                     int* __restrict__ j_flags, long long* __restrict__ counters, int edit_gt) {
+  extern __shared__ uint32_t s_mask[];  // [K][TG_MAXROWS][TG_WORDS]
+  __shared__ TgRect s_pred[MAXK];
+  __shared__ int s_parea[MAXK];
+  __shared__ TgRect s_gt;
+  __shared__ int s_red[JT / 32];
+  __shared__ int s_j1, s_jk;
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const int n = min(n_peaks ? n_peaks[b] : K, K);
+  const int M = min(gt_count[b], Mmax);
+  double* G = gt + (long long)b * Mmax * 6;
+  const double* P = grasps + (long long)b * K * 5;
+  // grasp_eval.py:367-368, in place
+  for (int m = tid; edit_gt && m < M; m += JT) {
+    G[m * 6 + 3] = 20.0;
+    const double w = G[m * 6 + 2];
+    G[m * 6 + 2] = w < 0.0 ? 0.0 : (w > 100.0 ? 100.0 : w);  // NaN stays NaN like np.clip
+  }
+  if (tid == 0) { s_j1 = 0; s_jk = 0; }
+  if (tid < n) tg_make_rect(P + tid * 5, &s_pred[tid]);
+  __syncthreads();
+  // predicted rectangles: row masks + areas
+  for (int k = 0; k < n; ++k) {
+    const TgRect* R = &s_pred[k];
+    int cnt = 0;
+    if (R->fast) {
+      const int X = R->x0 + tid;
+      uint32_t* row = s_mask + ((long long)k * TG_MAXROWS + tid) * TG_WORDS;
+      if (X <= R->x1) {
+        tg_row_mask(R, X, row);
+#pragma unroll
+        for (int w = 0; w < TG_WORDS; ++w) cnt += __popc(row[w]);
+      }
+      cnt = block_sum(cnt, s_red);
+    } else {
+      cnt = slow_count(R, nullptr, s_red);
+    }
+    if (tid == 0) s_parea[k] = cnt;
+  }
+  __syncthreads();
+  for (int m = 0; m < M; ++m) {
+    const double* g = G + m * 6;
+    // which predictions pass the angle gate (grasp_eval.py:306)
+    uint32_t pass = 0;
+    for (int k = 0; k < n; ++k) {
+      const double tp = P[k * 5 + 4], tg = g[4];
+      if (!(fabs(tp - tg) > 30.0 && fabs(tp + tg) > 30.0)) pass |= 1u << k;
+    }
+    if (inter_out) for (int k = tid; k < K; k += JT) {
+      inter_out[((long long)b * K + k) * Mmax + m] = 0; uni_out[((long long)b * K + k) * Mmax + m] = 0;
+    }
+    if (!pass) continue;  // block-uniform
+    __syncthreads();
+    if (tid == 0) tg_make_rect(g, &s_gt);
+    __syncthreads();
+    const TgRect* Gr = &s_gt;
+    // GT row mask for this thread's scanline (fast path) + area
+    uint32_t grow[TG_WORDS];
+#pragma unroll
+    for (int w = 0; w < TG_WORDS; ++w) grow[w] = 0u;
+    int garea;
+    if (Gr->fast) {
+      int cnt = 0;
+      const int X = Gr->x0 + tid;
+      if (X <= Gr->x1) {
+        tg_row_mask(Gr, X, grow);
+#pragma unroll
+        for (int w = 0; w < TG_WORDS; ++w) cnt += __popc(grow[w]);
+      }
+      garea = block_sum(cnt, s_red);
+    } else {
+      garea = slow_count(Gr, nullptr, s_red);
+    }
+    for (int k = 0; k < n; ++k) {
+      if (!((pass >> k) & 1u)) continue;
+      const TgRect* R = &s_pred[k];
+      int inter;
+      if (R->fast && Gr->fast) {
+        int cnt = 0;
+        const int X = Gr->x0 + tid;  // this thread's GT scanline
+        if (X <= Gr->x1 && X >= R->x0 && X <= R->x1) {
+          const uint32_t* prow = s_mask + ((long long)k * TG_MAXROWS + (X - R->x0)) * TG_WORDS;
+          const int dw = Gr->yw0 - R->yw0;  // word offset between the two anchors
+#pragma unroll
+          for (int w = 0; w < TG_WORDS; ++w) {
+            const int pw = w + dw;
+            if (pw >= 0 && pw < TG_WORDS) cnt += __popc(grow[w] & prow[pw]);
+          }
+        }
+        inter = block_sum(cnt, s_red);
+      } else {
+        inter = slow_count(R, Gr, s_red);
+      }
+      const int uni = s_parea[k] + garea - inter;
+      if (tid == 0) {
+        if (inter_out) { inter_out[((long long)b * K + k) * Mmax + m] = inter; uni_out[((long long)b * K + k) * Mmax + m] = uni; }
+        if (uni > 0 && 4LL * inter > (long long)uni) { s_jk = 1; if (k == 0) s_j1 = 1; }
+      }
+    }
+  }
+  __syncthreads();
+  if (tid == 0) {
+    j_flags[b * 2] = s_j1; j_flags[b * 2 + 1] = s_jk;
+    if (counters) {
+      atomicAdd(reinterpret_cast<unsigned long long*>(counters) + 0, (unsigned long long)s_j1);
+      atomicAdd(reinterpret_cast<unsigned long long*>(counters) + 1, 1ull);
+      atomicAdd(reinterpret_cast<unsigned long long*>(counters) + 2, (unsigned long long)s_jk);
+      atomicAdd(reinterpret_cast<unsigned long long*>(counters) + 3, 1ull);
+    }
+  }
+}
+
+inline void scan_geometry(int H, int W, int* nbands, int* nwarps) {
+  *nbands = (H + BAND - 1) / BAND;
+  *nwarps = (W + STRIP - 1) / STRIP;
+}
+
+}  // namespace
+
+extern "C" int64_t crog_detect_workspace_bytes(int32_t B, int32_t H, int32_t W, int32_t K) {
+  int nb, nw;
+  scan_geometry(H, W, &nb, &nw);
+  (void)K;
+  return (int64_t)B * nb * nw * SEG_BYTES + (int64_t)B * 4 + 256;
+}
+
+extern "C" int crog_detect_grasps(const float* q, const float* sin_m, const float* cos_m, const float* wid, int32_t B, int32_t H,
+                                  int32_t W, int32_t K, float threshold, int32_t* peaks, int32_t* n_peaks, double* grasps,
+                                  void* workspace, void* stream) {
+  CROG_REQUIRE(K >= 1 && K <= MAXK, CROG_E_BADSHAPE, "detect_grasps: 1 <= num_grasps <= %d", MAXK);
+  CROG_REQUIRE(H >= 1 && W >= 1 && W <= 8 * STRIP && (long long)H * W < (1LL << 31), CROG_E_BADSHAPE, "detect_grasps: map %dx%d unsupported", H, W);
+  CROG_REQUIRE(B <= 65535, CROG_E_BADSHAPE, "detect_grasps: at most 65535 maps per call");
+  CROG_REQUIRE(aligned16(q) && aligned16(workspace), CROG_E_BADALIGN, "detect_grasps: 16B alignment");
+  if (B == 0) return CROG_OK;
+  int nb, nw;
+  scan_geometry(H, W, &nb, &nw);
+  cudaStream_t s = (cudaStream_t)stream;
+  uint8_t* ws = (uint8_t*)workspace;
+  int* flags = (int*)(ws + (((int64_t)B * nb * nw * SEG_BYTES + 15) / 16) * 16);
+  const size_t smem = (size_t)nw * (CAPW + TSEL) * 8;
+  static bool attr = false;
+  if (!attr) { CROG_CUDA_OK(cudaFuncSetAttribute(peak_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * (CAPW + TSEL) * 8)); attr = true; }
+  peak_scan_kernel<<<dim3(nb, B), nw * 32, smem, s>>>(q, H, W, threshold, nw, ws);
+  CROG_LAUNCH_OK("peak_scan");
+  peak_select_kernel<<<(B + 3) / 4, 128, 0, s>>>(sin_m, cos_m, wid, B, H, W, K, nb * nw, ws, flags, peaks, n_peaks, grasps);
+  CROG_LAUNCH_OK("peak_select");
+  peak_exact_kernel<<<B, 256, 0, s>>>(q, sin_m, cos_m, wid, H, W, K, threshold, flags, peaks, n_peaks, grasps);
+  CROG_LAUNCH_OK("peak_exact");
+  return CROG_OK;
+}
+
+extern "C" int crog_angle_map(const float* sin_m, const float* cos_m, float* out, int64_t n, void* stream) {
+  if (n == 0) return CROG_OK;
+  long long g = (n + 255) / 256;
+  if (g > 148 * 16) g = 148 * 16;
+  angle_map_kernel<<<(int)g, 256, 0, (cudaStream_t)stream>>>(sin_m, cos_m, out, n);
+  CROG_LAUNCH_OK("angle_map");
+  return CROG_OK;
+}
+
+extern "C" int crog_jaccard(const double* grasps, const int32_t* n_peaks, int32_t K, double* gt, const int32_t* gt_count,
+                            int32_t Mmax, int32_t B, int32_t* inter, int32_t* uni, int32_t* j_flags, int64_t* counters,
+                            int32_t edit_gt, void* stream) {
+  CROG_REQUIRE(K >= 1 && K <= MAXK, CROG_E_BADSHAPE, "jaccard: 1 <= K <= %d", MAXK);
+  CROG_REQUIRE((inter == nullptr) == (uni == nullptr), CROG_E_BADSHAPE, "jaccard: inter/uni must both be given or both NULL");
+  if (B == 0) return CROG_OK;
+  const size_t smem = (size_t)K * TG_MAXROWS * TG_WORDS * 4;
+  static bool attr = false;
+  if (!attr) { CROG_CUDA_OK(cudaFuncSetAttribute(jaccard_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MAXK * TG_MAXROWS * TG_WORDS * 4)); attr = true; }
+  jaccard_kernel<<<B, JT, smem, (cudaStream_t)stream>>>(grasps, n_peaks, K, gt, gt_count, Mmax, inter, uni, j_flags,
+                                                        (long long*)counters, edit_gt);
+  CROG_LAUNCH_OK("jaccard");
+  return CROG_OK;
+}

@@ -1,0 +1,77 @@
+"""Device-resident restatement of the per-batch evaluation body of the reference engine,
+``engine/crog_engine.py:386-556`` (``inference_with_grasp``), for the synthetic-benchmark
+contract of SURVEY.md §8(d): maps are decoded at the network resolution (identity
+``ori_size``; the inverse letterbox warp is row f-1 of the scope table and not built yet).
+
+    model(img, word) -> sigmoid(mask, qua, wid) + bicubic x4 (align_corners=True)   [crog_engine.py:446-474]
+                     -> detect_grasps(K=1 and K=5) per sample                      [:519-522]
+                     -> calculate_jacquard_index against the sample's GT           [:524-527]
+                     -> correct/total counters for J@1 and J@5                     [:526-527,535-537]
+
+Everything between the model and the counters stays in HBM; the reference instead copies ten
+maps per sample to the host and loops in Python.  J@1 uses the first of the top-5 peaks: the
+greedy peak order does not depend on K, so ``detect_grasps(K=1)`` is the first row of K=5.
+"""
+from __future__ import annotations
+
+from typing import Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib as L
+from .utils import grasp_eval as GE
+
+SIGMOID_PLANES = 0b10011  # mask, qua, wid get a sigmoid; sin, cos stay raw (crog_engine.py:446-448)
+
+
+def postprocess(maps: Sequence[torch.Tensor], size: Tuple[int, int]) -> torch.Tensor:
+    """5 logits maps B x 1 x h x w (any contiguous layout) -> tensor [5, B, H, W] of sigmoid + bicubic maps."""
+    lib = L.lib()
+    stacked = maps if torch.is_tensor(maps) else torch.stack([m.reshape(m.shape[0], m.shape[-2], m.shape[-1]) for m in maps])
+    stacked = stacked.reshape(len(maps), -1, stacked.shape[-2], stacked.shape[-1]).contiguous().float()
+    NP, B, h, w = stacked.shape
+    out = torch.empty((NP, B, size[0], size[1]), dtype=torch.float32, device=stacked.device)
+    with torch.cuda.device(stacked.device):
+        L.check(lib.crog_sigmoid_bicubic(stacked.data_ptr(), out.data_ptr(), NP, B, h, w, size[0], size[1],
+                                         SIGMOID_PLANES if NP == 5 else 0b1, L.stream_ptr()))
+    return out
+
+
+class GraspEvaluator:
+    """Accumulates J@1 / J@5 over batches on the device; ``reduce()`` sums the int64[4] counters over ranks
+    (one all-reduce per evaluation — the reference leaves the per-rank counters un-reduced)."""
+
+    def __init__(self, model, num_grasps: int = 5, device: Optional[torch.device] = None):
+        self.model = model
+        self.K = num_grasps
+        dev = device or next(model.parameters()).device
+        self.counters = torch.zeros(4, dtype=torch.int64, device=dev)
+
+    @torch.no_grad()
+    def step(self, img: torch.Tensor, word: torch.Tensor, gt: torch.Tensor, gt_count: torch.Tensor):
+        """img B x 3 x S x S, word B x L, gt B x M x 6 float64 (edited in place like the reference), gt_count B int32.
+        Returns (post [5,B,S,S], peaks, n_peaks, grasps, j_flags)."""
+        maps, _ = self.model(img, word)
+        post = postprocess(maps, (img.shape[-2], img.shape[-1]))
+        peaks, n, grasps = GE.detect_grasps_batched(post[1], post[2], post[3], post[4], self.K)
+        flags = GE.jacquard_batched(grasps, n, gt, gt_count, counters=self.counters)
+        return post, peaks, n, grasps, flags
+
+    def reduce(self) -> torch.Tensor:
+        import torch.distributed as dist
+
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            dist.all_reduce(self.counters, op=dist.ReduceOp.SUM)
+        return self.counters
+
+    def j_index(self):
+        c = self.counters.tolist()
+        return (c[0] / max(c[1], 1), c[2] / max(c[3], 1))
+
+
+def shard_range(n: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous shard of ``n`` samples for ``rank``; the remainder goes to the low ranks and no sample is
+    duplicated (unlike DistributedSampler's padding, which would change J)."""
+    base, rem = divmod(n, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)

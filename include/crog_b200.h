@@ -1,0 +1,175 @@
+/* crog_b200 C ABI — hand-written sm_100a kernels for CROG's batched referring-grasp
+ * inference path (model forward + engine glue + grasp decode / Jaccard tail).
+ *
+ * The reference (HilbertXu/CROG) has no FFI boundary: its "operator API" is the Python
+ * nn.Module surface (model/crog.py:47, model/__init__.py:6) and utils/grasp_eval.py
+ * (:289,:305,:350,:362), everything below being torch -> cuDNN/cuBLAS or numpy/skimage on
+ * the host.  This header is what a replacement binds instead; each entry
+ * point cites the reference code it replaces.  Python binds it with ctypes
+ * (crog_b200/_lib.py); see INTEGRATION.md for the reference-side stub.
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer borrowed for the call unless it says "host";
+ *  - calls are asynchronous on `stream` (a cudaStream_t passed as void*), never allocate,
+ *    never synchronise, and are re-entrant across streams / devices;
+ *  - return 0 on success, a negative CROG_E_* code otherwise; crog_last_error() gives the
+ *    thread-local message;
+ *  - there is no CPU fallback and no pre-sm_100 path (CROG_E_UNSUPPORTED_ARCH).
+ */
+#ifndef CROG_B200_H_
+#define CROG_B200_H_
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum {
+  CROG_OK = 0,
+  CROG_E_BADSHAPE = -1,
+  CROG_E_BADALIGN = -2,
+  CROG_E_UNSUPPORTED_ARCH = -3,
+  CROG_E_CUDA = -4,
+};
+enum { CROG_F32 = 0, CROG_BF16 = 1 };
+enum { CROG_ACT_NONE = 0, CROG_ACT_RELU = 1, CROG_ACT_QUICKGELU = 2 };
+enum { CROG_IMPL_AUTO = 0, CROG_IMPL_SIMT = 1, CROG_IMPL_TCGEN05 = 2 };
+
+const char* crog_last_error(void);
+int crog_abi_version(void);
+/* 0 if the current device is sm_100 (B200), CROG_E_UNSUPPORTED_ARCH otherwise. */
+int crog_check_device(void);
+
+/* ------------------------------------------------------------------ contractions
+ * One descriptor covers every dense contraction of the forward: 1x1 / 3x3 convolutions
+ * as implicit GEMM over NHWC activations and all linear layers.
+ *   replaces: nn.Conv2d+BatchNorm2d+ReLU (model/clip.py:44-57,208-213; model/layers.py:8-11),
+ *             nn.Linear / MHA in/out projections (model/clip.py:239-265; model/layers.py:280-339),
+ *             the FPN text gate (model/layers.py:376-379) and CoordConv (model/layers.py:19-44).
+ *
+ * out[map(r), n] = epi( sum_{t<taps} sum_{c<cin} A[r + shift_t, c] * Wt[n, t*cin + c] )
+ *
+ * Activations are row-major [rows, ld] matrices of NHWC pixels.  A "padded" tensor stores
+ * every sample as (H+2)x(W+2) pixels with a zero halo, so the 9 taps of a 3x3/pad-1
+ * convolution are nine row-shifted views of the same matrix (shift = (ky-1)*(W+2)+(kx-1));
+ * halo rows are never written by the epilogue and must have been zeroed once.
+ * epi(v): v += addmat[sp(r), n]; v = v*scale[n] + bias[n]; v = act(v);
+ *         if gate: v = relu((v * gate[b(r), n]) * scale2[n] + bias2[n]);
+ *         v += residual[map(r), n]   (then act2 = relu if residual_relu)
+ */
+typedef struct CrogGemm {
+  const void* a;          /* activations [a_rows, a_ld] */
+  int64_t a_rows;
+  int32_t a_ld;           /* elements */
+  int32_t cin;            /* channels contracted per tap (multiple of 64 for tcgen05) */
+  int32_t taps;           /* 1 or 9 */
+  int32_t dtype;          /* CROG_F32 | CROG_BF16: type of a and w */
+  int32_t M;              /* rows enumerated */
+  int32_t sample_rows;    /* enumerated rows per sample (0: no sample structure) */
+  int32_t H, W;           /* interior spatial dims (0,0: plain matrix rows) */
+  int32_t in_padded;      /* enumerated rows are padded-layout rows */
+  int32_t out_padded;     /* output (and residual) rows are padded-layout rows */
+  const void* w;          /* weights [N, taps*cin], K-major */
+  int32_t N;
+  int64_t w_sample_stride;/* elements between per-sample weight matrices (0: shared) */
+  const float* scale;     /* [N] or NULL (=1) */
+  const float* bias;      /* [N] or NULL (=0) */
+  const float* addmat;    /* [addmat_rows, N] fp32 added before scale, or NULL */
+  int32_t addmat_rows;    /* period: indexed by the interior pixel index / row-in-sample */
+  int32_t act;            /* CROG_ACT_* */
+  const float* gate;      /* [num_samples, N] or NULL */
+  const float* scale2;    /* [N] (with gate) */
+  const float* bias2;     /* [N] (with gate) */
+  const void* residual;   /* [*, res_ld] of out_dtype, or NULL */
+  int32_t res_ld;
+  int32_t residual_relu;
+  void* out;
+  int32_t out_ld;
+  int32_t out_dtype;      /* CROG_F32 | CROG_BF16 */
+  int32_t impl;           /* CROG_IMPL_* */
+} CrogGemm;
+int crog_gemm(const CrogGemm* g, void* stream);
+
+/* ------------------------------------------------------------------ layout / resampling
+ * replaces: nn.AvgPool2d(2) (clip.py:23,35,184; layers.py:386), F.interpolate(scale_factor=2,
+ * mode='bilinear') (layers.py:54,56,382,393), torch.cat along channels (writes a channel
+ * slice: pass out already offset, out_ld = full width).  mode: 0 copy, 1 avgpool2, 2 bilinear x2. */
+int crog_resample(const void* in, int32_t in_ld, int32_t in_padded, void* out, int32_t out_ld,
+                  int32_t out_padded, int32_t B, int32_t H, int32_t W, int32_t C, int32_t mode,
+                  int32_t dtype, void* stream);
+
+/* Stem conv1: 3x3 stride 2 pad 1 on NCHW fp32 images + folded BN + ReLU, writing the padded
+ * NHWC layout (model/clip.py:165-170,208-211). w [cout,3,3,3] fp32. out channels >= cout are zeroed. */
+int crog_stem_conv1(const float* img, int32_t B, int32_t Hin, int32_t Win, const float* w,
+                    const float* scale, const float* bias, int32_t cout, void* out, int32_t out_ld,
+                    int32_t out_dtype, void* stream);
+
+/* LayerNorm over the last dim (clip.py:226-231, layers.py:288-311): y = LN(x)*g + b, optional
+ * out = residual + y (fp32 residual stream).  x_dtype/out_dtype are CROG_F32|CROG_BF16. */
+int crog_layernorm(const void* x, int32_t x_dtype, const float* gamma, const float* beta, const float* residual,
+                   void* out, int32_t out_dtype, int64_t rows, int32_t D, float eps, void* stream);
+
+/* Token embedding + positional embedding (clip.py:440-443): out[b*L+l] = emb[word[b,l]] + pos[l], fp32. */
+int crog_embed_tokens(const int64_t* word, const float* emb, const float* pos, float* out, int32_t B,
+                      int32_t L, int32_t D, void* stream);
+/* EOT gather (clip.py:450-451): out[b] = x[b*L + argmax_l word[b,l]]. */
+int crog_gather_eot(const int64_t* word, const void* x, int32_t x_dtype, void* out, int32_t out_dtype,
+                    int32_t B, int32_t L, int32_t D, void* stream);
+
+/* Softmax attention, head_dim 64 (clip.py:123-140,258-262; layers.py:313-333).
+ * q [B*Tq, ldq], k/v [B*Tk, ldk/ldv], head h uses columns [h*64, h*64+64); o [B*Tq, ldo].
+ * causal: key j visible to query i iff j <= i.  pad_word: optional int64 [B,Tk]; keys with id 0 masked. */
+int crog_attention(const void* q, int32_t ldq, const void* k, int32_t ldk, const void* v, int32_t ldv,
+                   void* o, int32_t ldo, int32_t B, int32_t heads, int32_t Tq, int32_t Tk, float scale,
+                   int32_t causal, const int64_t* pad_word, int32_t dtype, void* stream);
+
+/* Projector text branch (layers.py:91-93) folded with vis.4 (layers.py:58,70-77):
+ * t = Linear(state); w_dyn = t[:, :-1] as [C,3,3]; b_dyn = t[:, -1];
+ * wfold[b, h, tap*Cpad + j] = sum_c w_dyn[b,c,tap] * V[h*C + c, j]   (j < C)
+ * wfold[b, h, tap*Cpad + C] = sum_c w_dyn[b,c,tap] * vb[h*C + c] (+ b_dyn[b] on the centre tap)
+ * so that the five dynamic convolutions become one per-sample 3x3 convolution over the
+ * C feature channels plus a constant-one channel.  wfold: [B, NH_pad, 9*Cpad] of dtype. */
+int crog_dynw_fold(const void* state, int32_t state_dtype, const float* txt_w, const float* txt_b,
+                   const float* v_w, const float* v_b, float* scratch /*[B, 9*C+1]*/, void* wfold,
+                   int32_t dtype, int32_t B, int32_t word_dim, int32_t C, int32_t NH, int32_t NH_pad,
+                   int32_t Cpad, void* stream);
+
+/* Element-wise dtype conversion (CROG_F32 <-> CROG_BF16) of n contiguous elements. */
+int crog_cast(const void* in, int32_t in_dtype, void* out, int32_t out_dtype, int64_t n, void* stream);
+
+/* [B*HW, ld] fp32 head columns -> NH planes [NH][B, HW] fp32 (the five B x 1 x 104 x 104 logits). */
+int crog_split_heads(const float* in, int32_t ld, float* out, int64_t rows, int32_t NH, void* stream);
+
+/* ------------------------------------------------------------------ engine glue
+ * engine/crog_engine.py:183-211: sigmoid (planes flagged in sigmoid_mask bit i) + bicubic
+ * (A=-0.75, align_corners=True) resize of NP planes [NP][B,Hin,Win] -> [NP][B,Hout,Wout], fp32. */
+int crog_sigmoid_bicubic(const float* in, float* out, int32_t NP, int32_t B, int32_t Hin, int32_t Win,
+                         int32_t Hout, int32_t Wout, uint32_t sigmoid_mask, void* stream);
+
+/* ------------------------------------------------------------------ grasp decode + Jaccard tail
+ * utils/grasp_eval.py:289-302 (detect_grasps = skimage peak_local_max(min_distance=2,
+ * threshold_abs, num_peaks=K) + angle/width gather) batched over B maps of H x W fp32.
+ *   peaks  [B,K,2] int32 (row, col), -1 padded;  n_peaks [B] int32
+ *   grasps [B,K,5] float64 rows [x, y, width*100, 20, angle_deg]
+ * workspace: crog_detect_workspace_bytes(B,H,W,K) bytes. */
+int64_t crog_detect_workspace_bytes(int32_t B, int32_t H, int32_t W, int32_t K);
+int crog_detect_grasps(const float* q, const float* sin_m, const float* cos_m, const float* wid, int32_t B,
+                       int32_t H, int32_t W, int32_t K, float threshold, int32_t* peaks, int32_t* n_peaks,
+                       double* grasps, void* workspace, void* stream);
+/* Whole-map angle field, the second return value of detect_grasps (grasp_eval.py:293). */
+int crog_angle_map(const float* sin_m, const float* cos_m, float* out, int64_t n, void* stream);
+
+/* utils/grasp_eval.py:305-374 batched: for every sample the K predicted rectangles against its
+ * M ground-truth rectangles [B,Mmax,6] float64 (gt_count [B]); GT is edited in place like the
+ * reference (h:=20, w:=clip(w,0,100)) when edit_gt != 0 (calculate_jacquard_index); with edit_gt == 0 the
+ * rectangles are used as given (calculate_iou).  Outputs: inter/uni [B,K,Mmax] int32 pixel counts
+ * (0,0 when angle-gated), j_flags [B,2] int32 = {J@1 (first prediction only), J@K (all)},
+ * counters int64[4] += {correct@1, total@1, correct@K, total@K}.  inter/uni may be NULL. */
+int crog_jaccard(const double* grasps, const int32_t* n_peaks, int32_t K, double* gt, const int32_t* gt_count,
+                 int32_t Mmax, int32_t B, int32_t* inter, int32_t* uni, int32_t* j_flags, int64_t* counters,
+                 int32_t edit_gt, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CROG_B200_H_ */
