@@ -1,0 +1,293 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: CROG R50 batched referring-grasp inference (img + expression -> 5 maps
+-> sigmoid/bicubic -> grasp decode -> Jaccard J@1/J@5), BASELINE.json configs[1]/[2].
+
+    python bench.py --gpus N --steps K --warmup W            # our arm (one process per GPU under torchrun)
+    python bench.py --impl reference --steps K --warmup W     # the reference's CPU path (oracle port) on host cores
+
+One "step" = one pass over one batch of `--batch` synthetic samples per GPU (weak scaling: the batch per
+GPU is fixed).  `value` is samples/s with inputs resident in HBM; `e2e` is the same metric through the public
+API with pinned HOST buffers (H2D of img/word/GT and D2H of grasps/J flags inside the timed region).
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from crog_b200 import synth  # noqa: E402
+
+ALG_GFLOP_PER_SAMPLE = {17: 137.56, 20: 137.80}  # SURVEY.md §8(d) / BASELINE.md §3 (2*MAC of the reference forward)
+METRIC = "samples/sec (img+expr -> grasps)"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get("bf16_tflops_sustained", d.get("bf16_tflops")), d.get("hbm_gbs"), "measured"
+    return 1400.0, 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        busy = sorted(sm)[len(sm) // 2:] if sm else []  # upper half = samples under load
+        return {"sm_mhz": float(np.median(busy)) if busy else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_port_samples_per_sec(word_len: int, n_samples: int, threads: int):
+    """The reference's CPU path restated (oracle port): fp32 torch forward + sigmoid/bicubic + serial decode/Jaccard loop."""
+    from oracle import crog_forward as O
+    from oracle import grasp_tail_c as TC
+
+    torch.set_num_threads(threads)
+    cfg = synth.default_cfg(word_len)
+    sd = synth.make_state_dict(cfg, 0, "perturbed")
+    img, word = synth.make_inputs(n_samples, word_len)
+    gt, cnt = synth.make_gt_rects(n_samples, 64, seed=4)
+    O.crog_forward(sd, cfg, img[:1], word[:1])  # warm-up (thread pool, allocator)
+    t0 = time.perf_counter()
+    for b in range(n_samples):  # the reference evaluates with batch_size=1 (test_crog.py:62)
+        maps, _ = O.crog_forward(sd, cfg, img[b:b + 1], word[b:b + 1])
+        post = [p.numpy() for p in O.postprocess(maps, (416, 416))]
+        TC.tail_batch(post[1], post[2], post[3], post[4], gt[b:b + 1], cnt[b:b + 1])
+    dt = time.perf_counter() - t0
+    return n_samples / dt, dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    n = args.cpu_samples
+    vals = []
+    for _ in range(args.warmup):
+        cpu_port_samples_per_sec(args.word_len, 1, threads)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        v, _ = cpu_port_samples_per_sec(args.word_len, n, threads)
+        vals.append(v)
+    total = time.perf_counter() - t0
+    value = float(np.median(vals))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * total / max(args.steps, 1), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"CROG R50 inference + grasp decode + Jaccard, 416x416, L={args.word_len}, CPU fp32, batch 1 per forward"},
+        "cpu_baseline": {"value": value, "unit": "samples/s", "cores": threads, "kind": "port",
+                         "sample": f"{n} samples per step: oracle/crog_forward.py (torch CPU fp32) + oracle/grasp_tail.c, serial loop"},
+        "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=64, help="samples per GPU per step")
+    ap.add_argument("--word-len", type=int, default=17)
+    ap.add_argument("--cpu-samples", type=int, default=4, help="bounded CPU-baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--dump-ops", default=None, help="write the per-op CUDA-event table (eager replay) to this file")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 0)
+    if args.impl == "reference":
+        return run_reference(args)
+    args.warmup = max(args.warmup, 3)
+
+    import torch.distributed as dist
+
+    from crog_b200.engine import GraspEvaluator
+    from crog_b200.model import CROG
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    B, Lw, S = args.batch, args.word_len, 416
+    cfg = synth.default_cfg(Lw)
+    model = CROG(cfg, precision="bf16")
+    model.load_state_dict(synth.make_state_dict(cfg, 0, "perturbed"), strict=True)
+    model = model.to(dev)
+    # every rank owns a contiguous shard of the global batch (different seeds per rank => different samples)
+    img, word = synth.make_inputs(B, Lw, seed_img=1 + 1000 * rank, seed_txt=2 + 1000 * rank)
+    gt, cnt = synth.make_gt_rects(B, 64, seed=4 + 1000 * rank)
+    h_img, h_word = img.pin_memory(), word.pin_memory()
+    h_gt, h_cnt = torch.from_numpy(gt).pin_memory(), torch.from_numpy(cnt).pin_memory()
+    d_img, d_word, d_gt0, d_cnt = h_img.to(dev), h_word.to(dev), h_gt.to(dev), h_cnt.to(dev)
+    d_gt = d_gt0.clone()
+    ev = GraspEvaluator(model, device=dev)
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        sync_all()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        sync_all()
+        return float(ms.item())
+
+    # ---- device-resident arm
+    def step_resident():
+        ev.step(d_img, d_word, d_gt, d_cnt)
+
+    for _ in range(args.warmup):
+        step_resident()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ms = timed(step_resident, args.steps)
+    clocks = sampler.stop() if rank == 0 else None
+    value = world * B * args.steps / (ms / 1e3)
+    ev.reduce()
+    counters = ev.counters.tolist()
+
+    # ---- end-to-end arm: pinned host buffers in, grasps / flags out, every step
+    e2e = None
+    if not args.no_e2e:
+        h_out_g = torch.empty((B, 5, 5), dtype=torch.float64).pin_memory()
+        h_out_f = torch.empty((B, 2), dtype=torch.int32).pin_memory()
+        h_out_n = torch.empty((B,), dtype=torch.int32).pin_memory()
+
+        def step_e2e():
+            i = h_img.to(dev, non_blocking=True); w = h_word.to(dev, non_blocking=True)
+            g = h_gt.to(dev, non_blocking=True); c = h_cnt.to(dev, non_blocking=True)
+            _, _, n, grasps, flags = ev.step(i, w, g, c)
+            h_out_g.copy_(grasps, non_blocking=True); h_out_f.copy_(flags, non_blocking=True); h_out_n.copy_(n, non_blocking=True)
+            torch.cuda.current_stream().synchronize()  # the caller reads the result of every step
+
+        for _ in range(2):
+            step_e2e()
+        ms_e = timed(step_e2e, args.steps)
+        h2d = h_img.numel() * 4 + h_word.numel() * 8 + h_gt.numel() * 8 + h_cnt.numel() * 4
+        d2h = h_out_g.numel() * 8 + h_out_f.numel() * 4 + h_out_n.numel() * 4
+        e2e = {"value": world * B * args.steps / (ms_e / 1e3), "unit": "samples/s", "h2d_bytes_per_step": h2d,
+               "d2h_bytes_per_step": d2h, "ms_per_step": ms_e / args.steps}
+
+    # ---- roofline of the dominant kernel family (tcgen05 implicit GEMM): per-op CUDA events on an eager replay
+    plan = model.plan_for(B, S)
+    roof = op_table = None
+    if rank == 0:
+        tf_peak, hbm_peak, which = peaks()
+        names, durs = plan.op_names, np.zeros(len(plan.ops))
+        reps = 3
+        from crog_b200 import _lib as L
+        for _ in range(reps):
+            evs = [torch.cuda.Event(enable_timing=True) for _ in range(len(plan.ops) + 1)]
+            s = L.stream_ptr()
+            evs[0].record()
+            for i, fn in enumerate(plan.ops):
+                fn(s)
+                evs[i + 1].record()
+            torch.cuda.synchronize()
+            durs += np.array([evs[i].elapsed_time(evs[i + 1]) for i in range(len(plan.ops))])
+        durs /= reps
+        is_gemm = np.array([n in plan.gemm_alg_flops for n in names])
+        alg = sum(plan.gemm_alg_flops.values())
+        t_gemm = float(durs[is_gemm].sum()) / 1e3
+        achieved = alg / t_gemm / 1e12
+        roof = {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05 implicit GEMM, all conv/linear layers)",
+                "achieved": achieved, "peak": tf_peak, "unit": "TFLOP/s", "frac": achieved / tf_peak, "peak_source": which + " sustained",
+                "traffic": None, "launches": int(is_gemm.sum()), "alg_gflop_per_launch_avg": alg / 1e9 / max(int(is_gemm.sum()), 1),
+                "share_of_forward": t_gemm / (float(durs.sum()) / 1e3),
+                "whole_step_frac_of_peak": ALG_GFLOP_PER_SAMPLE.get(Lw, 137.56) * 1e9 * (value / world) / 1e12 / tf_peak}
+        order = np.argsort(-durs)[:12]
+        op_table = [{"op": names[i], "ms": round(float(durs[i]), 4)} for i in order]
+        if args.dump_ops:
+            with open(args.dump_ops, "w") as f:
+                for i, n in enumerate(names):
+                    gf = plan.gemm_alg_flops.get(n, 0) / 1e9
+                    f.write(f"{i:4d} {n:50s} {durs[i]:9.4f} ms {gf:10.2f} GF {gf / max(durs[i], 1e-9):9.1f} TF/s\n")
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        v, dt = cpu_port_samples_per_sec(Lw, args.cpu_samples, threads)
+        cpu = {"value": v, "unit": "samples/s", "cores": threads, "kind": "port",
+               "sample": f"{args.cpu_samples} samples, batch 1 per forward ({dt:.1f} s): oracle torch-CPU fp32 forward + C decode/Jaccard"}
+
+    if rank == 0:
+        launches_per_step = plan.n_launches + 1 + 3 + 1  # forward + sigmoid/bicubic + (scan, select, exact) + jaccard
+        line = {
+            "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+            "data": "synthetic",
+            "config": {"workload": f"CROG R50 (crog_multiple_r50.yaml shapes) batched inference + grasp decode + Jaccard, batch {B}/GPU, "
+                                   f"416x416, L={Lw}, bf16, random-init (seeded) weights",
+                       "global_batch": B * world, "parallelism": f"dp{world}",
+                       "l2": "no explicit flush: one step streams ~6 GB of activations, far above the 126 MB L2"},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": launches_per_step * args.steps,
+            "roofline": roof, "cpu_baseline": cpu, "j_counters": counters, "top_ops_ms": op_table,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

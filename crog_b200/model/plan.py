@@ -129,6 +129,7 @@ class ForwardPlan:
         self._hold: List[object] = []  # keeps packed weights / descriptors alive
         self.n_launches = 0
         self.gemm_flops = 0
+        self.gemm_alg_flops: Dict[str, int] = {}
         sd = {k: v.detach().to(self.dev) for k, v in sd.items()}
         self.sd = sd
         S = input_size
@@ -146,7 +147,9 @@ class ForwardPlan:
             n = rows
         else:
             n = self.B * ((H + 2) * (W + 2) if padded else H * W)
-        return Act(torch.zeros((n, Cc), device=self.dev, dtype=dtype), self.B, H, W, padded, Cc)
+        t = torch.zeros((n, Cc), device=self.dev, dtype=dtype)
+        self._hold.append(t)  # ops capture raw pointers: the plan owns every buffer for its lifetime
+        return Act(t, self.B, H, W, padded, Cc)
 
     def wt(self, t: torch.Tensor) -> torch.Tensor:
         t = t.to(self.dev, self.adt).contiguous()
@@ -166,7 +169,8 @@ class ForwardPlan:
     # ------------------------------------------------------------------ op recorders
     def gemm(self, name: str, a: Act, w: torch.Tensor, N: int, out: Act, taps: int = 1, scale=None, bias=None,
              act: int = L.ACT_NONE, residual: Optional[Act] = None, residual_relu: bool = False, addmat=None,
-             gate=None, scale2=None, bias2=None, w_sample_stride: int = 0, cin: Optional[int] = None):
+             gate=None, scale2=None, bias2=None, w_sample_stride: int = 0, cin: Optional[int] = None,
+             alg_n: Optional[int] = None, alg_cin: Optional[int] = None):
         g = L.CrogGemm()
         cin = cin if cin is not None else a.C
         assert w.shape[-1] == taps * cin, (name, tuple(w.shape), taps, cin)
@@ -195,6 +199,8 @@ class ForwardPlan:
         self._add(name, lambda s: L.check(lib.crog_gemm(ref, s)))
         rows_eff = a.B * a.H * a.W if a.H > 0 else a.rows
         self.gemm_flops += 2 * rows_eff * N * taps * cin
+        # algorithmic FLOPs of the reference op (no channel padding, no halo rows) for roofline accounting
+        self.gemm_alg_flops[name] = 2 * rows_eff * (alg_n or N) * taps * (alg_cin or cin)
         if self._keep_all:
             self.keep[name] = out
 
@@ -243,13 +249,14 @@ class ForwardPlan:
         sc, bi = _bn_fold(sd, v + ".bn2")
         s2 = self.new(H1, H1, 64, padded=True)
         self.gemm("stem.conv2", s1, self.wt(_conv_w(sd[v + ".conv2.weight"], 64, 64)), 64, s2, taps=9,
-                  scale=self.f32(_pad_vec(sc, 64, 1.0)), bias=self.f32(_pad_vec(bi, 64, 0.0)), act=RELU)
+                  scale=self.f32(_pad_vec(sc, 64, 1.0)), bias=self.f32(_pad_vec(bi, 64, 0.0)), act=RELU, alg_n=32, alg_cin=32)
         sc, bi = _bn_fold(sd, v + ".bn3")
         s3 = self.new(H1, H1, 64)
         self.gemm("stem.conv3", s2, self.wt(_conv_w(sd[v + ".conv3.weight"], 64)), 64, s3, taps=9,
-                  scale=self.f32(sc), bias=self.f32(bi), act=RELU)
+                  scale=self.f32(sc), bias=self.f32(bi), act=RELU, alg_cin=32)
         x = self.new(H1 // 2, H1 // 2, 64)
         self.resample("stem.avgpool", s3, x, L.RS_AVGPOOL2)
+        self.keep["stem"] = x
         # ---- residual stages (clip.py:44-57, 187-203)
         feats = []
         inpl = 64
@@ -265,7 +272,6 @@ class ForwardPlan:
         self.keep.update(c3=c3, c4=c4, c5=c5)
         wordfeat, state32, state_a = self._text()
         fq = self._neck(c3, c4, c5, state_a)
-        self.keep["fq_neck"] = fq
         if cfg.use_contrastive:
             fq = self._decoder(fq, wordfeat)
             self.keep["fq_dec"] = fq
@@ -509,7 +515,8 @@ class ForwardPlan:
         self._hold.extend([wfold, scratch])
         self._add("proj.dynw_fold", lambda s: L.check(lib.crog_dynw_fold(*a, s)), launches=2)
         heads = self.new(H2, W2, NHP, dtype=torch.float32)
-        self.gemm("proj.dynconv", feat, wfold, NHP, heads, taps=9, w_sample_stride=NHP * 9 * CP, cin=CP)
+        self.gemm("proj.dynconv", feat, wfold, NHP, heads, taps=9, w_sample_stride=NHP * 9 * CP, cin=CP,
+                  alg_n=NH, alg_cin=Cc)
         self.out = torch.zeros((NH, B, 1, H2, W2), device=self.dev, dtype=torch.float32)
         a2 = (heads.ptr, heads.ld, self.out.data_ptr(), B * H2 * W2, NH)
         self._add("proj.split", lambda s: L.check(lib.crog_split_heads(*a2, s)))
