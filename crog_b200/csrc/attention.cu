@@ -114,6 +114,9 @@ __global__ void __launch_bounds__(QB) attention_kernel(const T* __restrict__ q, 
 
 }  // namespace
 
+int crog_attention_tc(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, void* o, int ldo, int B, int heads,
+                      int Tq, int Tk, float scale, cudaStream_t stream);
+
 extern "C" int crog_attention(const void* q, int32_t ldq, const void* k, int32_t ldk, const void* v, int32_t ldv, void* o,
                               int32_t ldo, int32_t B, int32_t heads, int32_t Tq, int32_t Tk, float scale, int32_t causal,
                               const int64_t* pad_word, int32_t dtype, void* stream) {
@@ -121,8 +124,12 @@ extern "C" int crog_attention(const void* q, int32_t ldq, const void* k, int32_t
   CROG_REQUIRE(aligned16(q) && aligned16(k) && aligned16(v) && aligned16(o), CROG_E_BADALIGN, "attention: 16B alignment");
   if (B == 0 || Tq == 0) return CROG_OK;
   CROG_REQUIRE(B <= 65535 && heads <= 65535, CROG_E_BADSHAPE, "attention: grid too large");
-  dim3 grid((Tq + QB - 1) / QB, heads, B);
   cudaStream_t s = (cudaStream_t)stream;
+  // dense bf16 attentions with enough keys to fill a tensor-core tile go to the tcgen05 kernel; the causal text
+  // attention (L <= 77) and the cross attention over <= 77 word tokens stay on CUDA cores
+  if (dtype == CROG_BF16 && !causal && pad_word == nullptr && Tk >= 128)
+    return crog_attention_tc(q, ldq, k, ldk, v, ldv, o, ldo, B, heads, Tq, Tk, scale, s);
+  dim3 grid((Tq + QB - 1) / QB, heads, B);
   if (dtype == CROG_F32)
     attention_kernel<float><<<grid, QB, 0, s>>>((const float*)q, ldq, (const float*)k, ldk, (const float*)v, ldv, (float*)o, ldo, Tq, Tk, scale, causal, pad_word);
   else

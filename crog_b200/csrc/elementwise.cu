@@ -246,6 +246,59 @@ __global__ void sigmoid_bicubic_kernel(const float* __restrict__ in, float* __re
   }
 }
 
+// Tiled variant: one CTA produces a 64 x 32 output tile from a <= 32 x 16 source tile staged (with the sigmoid
+// applied once per source pixel) in shared memory; stores are coalesced 128 B rows.
+constexpr int BT_OW = 64, BT_OH = 32, BT_SW = 32, BT_SH = 16;
+__global__ void __launch_bounds__(256) sigmoid_bicubic_tiled_kernel(const float* __restrict__ in, float* __restrict__ out, int B,
+                                                                    int Hin, int Win, int Hout, int Wout, uint32_t sig_mask,
+                                                                    float sh, float sw) {
+  __shared__ float tile[BT_SH][BT_SW + 1];
+  const int pl = blockIdx.z, p = pl / B;
+  const bool sig = (sig_mask >> p) & 1u;
+  const int ox0 = blockIdx.x * BT_OW, oy0 = blockIdx.y * BT_OH;
+  const int ix_lo = (int)floorf(sw * ox0) - 1, iy_lo = (int)floorf(sh * oy0) - 1;
+  const float* src = in + (long long)pl * Hin * Win;
+  for (int i = threadIdx.x; i < BT_SH * BT_SW; i += 256) {
+    const int ty = i / BT_SW, tx = i % BT_SW;
+    const int yy = min(max(iy_lo + ty, 0), Hin - 1), xx = min(max(ix_lo + tx, 0), Win - 1);
+    float v = __ldg(src + (long long)yy * Win + xx);
+    if (sig) v = 1.f / (1.f + expf(-v));
+    tile[ty][tx] = v;
+  }
+  __syncthreads();
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  float* dst = out + (long long)pl * Hout * Wout;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int oy = oy0 + ty + 8 * j;
+    if (oy >= Hout) continue;
+    const float ry = sh * oy;
+    const int iy = (int)floorf(ry);
+    const float fy = ry - iy;
+    const float wy[4] = {cc2(fy + 1.f), cc1(fy), cc1(1.f - fy), cc2(2.f - fy)};
+    const int sy = iy - 1 - iy_lo;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int ox = ox0 + tx + 32 * i;
+      if (ox >= Wout) continue;
+      const float rx = sw * ox;
+      const int ix = (int)floorf(rx);
+      const float fx = rx - ix;
+      const float wx[4] = {cc2(fx + 1.f), cc1(fx), cc1(1.f - fx), cc2(2.f - fx)};
+      const int sx = ix - 1 - ix_lo;
+      float acc = 0.f;
+#pragma unroll
+      for (int a = 0; a < 4; ++a) {
+        float r = 0.f;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) r += tile[sy + a][sx + c] * wx[c];
+        acc += r * wy[a];
+      }
+      dst[(long long)oy * Wout + ox] = acc;
+    }
+  }
+}
+
 inline int grid_for(long long total, int block) {
   long long g = (total + block - 1) / block;
   const long long cap = 148LL * 32;
@@ -360,7 +413,14 @@ extern "C" int crog_sigmoid_bicubic(const float* in, float* out, int32_t NP, int
   if (total == 0) return CROG_OK;
   const float sh = Hout > 1 ? (float)(Hin - 1) / (float)(Hout - 1) : 0.f;
   const float sw = Wout > 1 ? (float)(Win - 1) / (float)(Wout - 1) : 0.f;
-  sigmoid_bicubic_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(in, out, NP, B, Hin, Win, Hout, Wout, sigmoid_mask, sh, sw);
+  // source extent of one output tile (+1 on each side for the 4-tap support, +1 for floor slack)
+  const bool fits = (int)(sw * (BT_OW - 1)) + 5 <= BT_SW && (int)(sh * (BT_OH - 1)) + 5 <= BT_SH && (long long)NP * B <= 65535;
+  if (fits) {
+    dim3 grid((Wout + BT_OW - 1) / BT_OW, (Hout + BT_OH - 1) / BT_OH, NP * B);
+    sigmoid_bicubic_tiled_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(in, out, B, Hin, Win, Hout, Wout, sigmoid_mask, sh, sw);
+  } else {
+    sigmoid_bicubic_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(in, out, NP, B, Hin, Win, Hout, Wout, sigmoid_mask, sh, sw);
+  }
   CROG_LAUNCH_OK("sigmoid_bicubic");
   return CROG_OK;
 }
