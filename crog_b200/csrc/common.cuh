@@ -121,17 +121,24 @@ __device__ __forceinline__ float apply_act(float v, int act) {
   return v;
 }
 
-// Epilogue for CNT (multiple of 8) consecutive columns starting at n0 of one valid row.
-// sc/bi point at scale/bias for column n0 (global or shared), or nullptr.
+// Epilogue math for CNT (multiple of 8) consecutive columns starting at n0 of one valid row: everything except the
+// residual add and the store.  sc/bi point at scale/bias for column n0 (global or shared), or nullptr.
 template <int CNT>
-__device__ __forceinline__ void epilogue_row(const CrogGemm& g, const RowMap& m, int n0, float (&acc)[CNT],
-                                             const float* sc, const float* bi) {
+__device__ __forceinline__ void epilogue_math(const CrogGemm& g, const RowMap& m, int n0, float (&acc)[CNT], const float* sc,
+                                              const float* bi) {
   const int nvalid = min(CNT, g.N - n0);
-  if (nvalid <= 0) return;
   if (g.addmat) {
     const float* ad = g.addmat + (long long)m.sp * g.N + n0;
+    if (nvalid == CNT) {
 #pragma unroll
-    for (int j = 0; j < CNT; ++j) if (j < nvalid) acc[j] += __ldg(ad + j);
+      for (int j = 0; j < CNT; j += 4) {
+        const float4 a4 = __ldg(reinterpret_cast<const float4*>(ad + j));
+        acc[j] += a4.x; acc[j + 1] += a4.y; acc[j + 2] += a4.z; acc[j + 3] += a4.w;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < CNT; ++j) if (j < nvalid) acc[j] += __ldg(ad + j);
+    }
   }
 #pragma unroll
   for (int j = 0; j < CNT; ++j) {
@@ -146,6 +153,15 @@ __device__ __forceinline__ void epilogue_row(const CrogGemm& g, const RowMap& m,
     for (int j = 0; j < CNT; ++j) if (j < nvalid)
       acc[j] = fmaxf((acc[j] * __ldg(gt + j)) * __ldg(g.scale2 + n0 + j) + __ldg(g.bias2 + n0 + j), 0.f);
   }
+}
+
+// Full epilogue (math + residual + store) for one valid row; used by the CUDA-core GEMM.
+template <int CNT>
+__device__ __forceinline__ void epilogue_row(const CrogGemm& g, const RowMap& m, int n0, float (&acc)[CNT],
+                                             const float* sc, const float* bi) {
+  const int nvalid = min(CNT, g.N - n0);
+  if (nvalid <= 0) return;
+  epilogue_math<CNT>(g, m, n0, acc, sc, bi);
   const bool full = (nvalid == CNT);
   if (g.out_dtype == CROG_BF16) {
     bf16* o = reinterpret_cast<bf16*>(g.out) + m.orow * g.out_ld + n0;

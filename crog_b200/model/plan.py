@@ -128,6 +128,8 @@ class ForwardPlan:
         self._keep_all = keep
         self._hold: List[object] = []  # keeps packed weights / descriptors alive
         self.n_launches = 0
+        self._side = None
+        self._ev = None
         self.gemm_flops = 0
         self.gemm_alg_flops: Dict[str, int] = {}
         sd = {k: v.detach().to(self.dev) for k, v in sd.items()}
@@ -270,7 +272,9 @@ class ForwardPlan:
         c3, c4, x4 = feats[1], feats[2], feats[3]
         c5 = self._attnpool(x4)
         self.keep.update(c3=c3, c4=c4, c5=c5)
+        t_begin = len(self.ops)
         wordfeat, state32, state_a = self._text()
+        self.text_range = (t_begin, len(self.ops))  # independent of the image tower: may run on a forked stream
         fq = self._neck(c3, c4, c5, state_a)
         if cfg.use_contrastive:
             fq = self._decoder(fq, wordfeat)
@@ -523,10 +527,29 @@ class ForwardPlan:
         self.NH = NH
 
     # ------------------------------------------------------------------ execution
-    def run(self, stream: Optional[int] = None):
-        s = stream if stream is not None else L.stream_ptr()
-        for fn in self.ops:
-            fn(s)
+    def run(self, stream: Optional[int] = None, fork_text: bool = True):
+        """Replay the recorded launches on the current stream.  The text encoder does not depend on the image tower
+        until the neck, so it is forked onto a side stream (under CUDA-graph capture this becomes a parallel branch)."""
+        if stream is not None or not fork_text:
+            s = stream if stream is not None else L.stream_ptr()
+            for fn in self.ops:
+                fn(s)
+            return
+        main = torch.cuda.current_stream()
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=self.dev)
+            self._ev = (torch.cuda.Event(), torch.cuda.Event())
+        t0, t1 = self.text_range
+        self._ev[0].record(main)
+        self._side.wait_event(self._ev[0])
+        for fn in self.ops[t0:t1]:
+            fn(self._side.cuda_stream)
+        self._ev[1].record(self._side)
+        for fn in self.ops[:t0]:
+            fn(main.cuda_stream)
+        main.wait_event(self._ev[1])
+        for fn in self.ops[t1:]:
+            fn(main.cuda_stream)
 
     def run_debug(self):
         """Run op by op with a device sync after each, naming the op that faults."""
