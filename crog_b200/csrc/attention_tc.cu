@@ -25,7 +25,7 @@ __global__ void __launch_bounds__(192, 2) attention_tc_kernel(const __grid_const
                                                                const __grid_constant__ CUtensorMap tmV, bf16* __restrict__ o,
                                                                int ldo, int Tq, int Tk, float scale_log2e) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SM_BAR);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + SM_BAR + 96);
   const uint32_t b_qfull = smem_u32(bars + 0), b_kfull = smem_u32(bars + 1), b_vfull = smem_u32(bars + 2),

@@ -115,14 +115,11 @@ __device__ __forceinline__ RowMap map_row(const CrogGemm& g, long long r, long l
   return m;
 }
 
-__device__ __forceinline__ float apply_act(float v, int act) {
-  if (act == CROG_ACT_RELU) return fmaxf(v, 0.f);
-  if (act == CROG_ACT_QUICKGELU) return v / (1.f + __expf(-1.702f * v));
-  return v;
-}
+__device__ __forceinline__ float quickgelu(float v) { return __fdividef(v, 1.f + __expf(-1.702f * v)); }
 
 // Epilogue math for CNT (multiple of 8) consecutive columns starting at n0 of one valid row: everything except the
-// residual add and the store.  sc/bi point at scale/bias for column n0 (global or shared), or nullptr.
+// residual add and the store.  sc/bi point at scale/bias for column n0 (16-byte aligned; shared memory in the tcgen05
+// kernel, global in the CUDA-core kernel), or nullptr.  All mode tests are hoisted out of the per-element loops.
 template <int CNT>
 __device__ __forceinline__ void epilogue_math(const CrogGemm& g, const RowMap& m, int n0, float (&acc)[CNT], const float* sc,
                                               const float* bi) {
@@ -140,12 +137,26 @@ __device__ __forceinline__ void epilogue_math(const CrogGemm& g, const RowMap& m
       for (int j = 0; j < CNT; ++j) if (j < nvalid) acc[j] += __ldg(ad + j);
     }
   }
+  if (sc) {
 #pragma unroll
-  for (int j = 0; j < CNT; ++j) {
-    float v = acc[j];
-    if (sc) v *= sc[j];
-    if (bi) v += bi[j];
-    acc[j] = apply_act(v, g.act);
+    for (int j = 0; j < CNT; j += 4) {
+      const float4 s4 = *reinterpret_cast<const float4*>(sc + j);
+      acc[j] *= s4.x; acc[j + 1] *= s4.y; acc[j + 2] *= s4.z; acc[j + 3] *= s4.w;
+    }
+  }
+  if (bi) {
+#pragma unroll
+    for (int j = 0; j < CNT; j += 4) {
+      const float4 b4 = *reinterpret_cast<const float4*>(bi + j);
+      acc[j] += b4.x; acc[j + 1] += b4.y; acc[j + 2] += b4.z; acc[j + 3] += b4.w;
+    }
+  }
+  if (g.act == CROG_ACT_RELU) {
+#pragma unroll
+    for (int j = 0; j < CNT; ++j) acc[j] = fmaxf(acc[j], 0.f);
+  } else if (g.act == CROG_ACT_QUICKGELU) {
+#pragma unroll
+    for (int j = 0; j < CNT; ++j) acc[j] = quickgelu(acc[j]);
   }
   if (g.gate) {
     const float* gt = g.gate + (long long)m.b * g.N + n0;

@@ -29,7 +29,7 @@ struct Cfg {
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + ((B_BYTES + 1023) / 1024) * 1024;
   static constexpr int HALF = BN >= 32 ? BN / 2 : BN;        // columns per epilogue warp
-  static constexpr int SUB = HALF > 64 ? 64 : HALF;           // columns staged at a time
+  static constexpr int SUB = HALF > 32 ? 32 : HALF;           // columns staged at a time
   static constexpr int PITCH = SUB * 4 + 16;                  // staging row pitch (bytes): 16B-phase conflict free
   static constexpr int STG_BYTES = 32 * PITCH;                // per warp
   static constexpr int STG_OFF = STAGES * STAGE_BYTES;
@@ -47,7 +47,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
                                                                    const CrogGemm g, int n_tiles, int total_tiles) {
   using L = Cfg<BN, STAGES>;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  // 1024-byte alignment for SWIZZLE_128B tiles; plain pointer arithmetic keeps the shared address space so the
+  // epilogue's staging / scale / bias accesses compile to LDS / STS instead of generic loads
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::BAR_OFF);  // full[S], empty[S], tfull[2], tempty[2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L::BAR_OFF + (2 * STAGES + 4) * 8);
   float* s_sb = reinterpret_cast<float*>(smem + L::SB_OFF);
@@ -300,9 +302,12 @@ int crog_gemm_tc(const CrogGemm* g, cudaStream_t stream) {
   if (g->w_sample_stride > 0)
     CROG_REQUIRE(g->w_sample_stride % ((long long)g->taps * g->cin) == 0 && g->sample_rows > 0, CROG_E_BADSHAPE,
                  "gemm_tc: per-sample weights need whole rows");
-  if (g->N <= 16) return launch<16, 4>(g, stream);
-  if (g->N <= 64) return launch<64, 4>(g, stream);
-  return launch<128, 4>(g, stream);
+  if (g->N <= 16) return launch<16, 8>(g, stream);
+  if (g->N <= 64) return launch<64, 6>(g, stream);
+  // 128 x 256 tiles cut the L2 -> smem operand traffic per FLOP by 25 % ((BM+BN)/(BM*BN)); worth it when the
+  // contraction is long enough to be tensor/L2 bound rather than epilogue bound
+  if (g->N % 256 == 0 && (long long)g->taps * g->cin >= 1024) return launch<256, 3>(g, stream);
+  return launch<128, 5>(g, stream);
 }
 
 int crog_encode_2d_bf16(CUtensorMap* tm, const void* base, uint64_t cols, uint64_t rows, uint64_t ld_elems, uint32_t box_rows) {

@@ -14,6 +14,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import os
 from typing import Callable, Dict, List, Optional
 
 import torch
@@ -530,7 +531,7 @@ class ForwardPlan:
     def run(self, stream: Optional[int] = None, fork_text: bool = True):
         """Replay the recorded launches on the current stream.  The text encoder does not depend on the image tower
         until the neck, so it is forked onto a side stream (under CUDA-graph capture this becomes a parallel branch)."""
-        if stream is not None or not fork_text:
+        if stream is not None or not fork_text or os.environ.get("CROG_NO_FORK"):
             s = stream if stream is not None else L.stream_ptr()
             for fn in self.ops:
                 fn(s)
