@@ -10,45 +10,61 @@ __device__ __forceinline__ long long pix_row(int b, int y, int x, int H, int W, 
   return padded ? ((long long)(b * (H + 2) + y + 1) * (W + 2) + x + 1) : ((long long)(b * H + y) * W + x);
 }
 
+// One CTA per output row (b, oy): 32-bit index math only, threads sweep (ox, 8-channel group) with the channel
+// group fastest so every warp access is a contiguous run of 16-byte vectors.
 template <typename T, int MODE>
-__global__ void resample_kernel(const T* __restrict__ in, int in_ld, int in_padded, T* __restrict__ out, int out_ld,
-                                int out_padded, int B, int H, int W, int C) {
+__global__ void __launch_bounds__(256) resample_kernel(const T* __restrict__ in, int in_ld, int in_padded, T* __restrict__ out,
+                                                       int out_ld, int out_padded, int B, int H, int W, int C) {
   const int OH = MODE == 1 ? H / 2 : (MODE == 2 ? 2 * H : H);
   const int OW = MODE == 1 ? W / 2 : (MODE == 2 ? 2 * W : W);
   const int cgs = C / 8;
-  const long long total = (long long)B * OH * OW * cgs;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int cg = (int)(i % cgs);
-    long long p = i / cgs;
-    const int ox = (int)(p % OW); p /= OW;
-    const int oy = (int)(p % OH);
-    const int b = (int)(p / OH);
-    float v[8];
-    if (MODE == 0) {
-      load8(in + pix_row(b, oy, ox, H, W, in_padded) * in_ld + cg * 8, v);
-    } else if (MODE == 1) {
-      float a[8], c[8], d[8];
-      load8(in + pix_row(b, 2 * oy, 2 * ox, H, W, in_padded) * in_ld + cg * 8, v);
-      load8(in + pix_row(b, 2 * oy, 2 * ox + 1, H, W, in_padded) * in_ld + cg * 8, a);
-      load8(in + pix_row(b, 2 * oy + 1, 2 * ox, H, W, in_padded) * in_ld + cg * 8, c);
-      load8(in + pix_row(b, 2 * oy + 1, 2 * ox + 1, H, W, in_padded) * in_ld + cg * 8, d);
+  const int b = blockIdx.x / OH, oy = blockIdx.x % OH;
+  const T* ip = in;
+  T* op = out + pix_row(b, oy, 0, OH, OW, out_padded) * out_ld;
+  const int n = OW * cgs;
+  if (MODE == 0) {
+    ip = in + pix_row(b, oy, 0, H, W, in_padded) * in_ld;
+    for (int i = threadIdx.x; i < n; i += 256) {
+      const int ox = i / cgs, cg = i - ox * cgs;
+      float v[8];
+      load8(ip + (long long)ox * in_ld + cg * 8, v);
+      store8(op + (long long)ox * out_ld + cg * 8, v);
+    }
+  } else if (MODE == 1) {
+    const T* r0 = in + pix_row(b, 2 * oy, 0, H, W, in_padded) * in_ld;
+    const T* r1 = in + pix_row(b, 2 * oy + 1, 0, H, W, in_padded) * in_ld;
+    for (int i = threadIdx.x; i < n; i += 256) {
+      const int ox = i / cgs, cg = i - ox * cgs;
+      float v[8], a[8], c[8], d[8];
+      load8(r0 + (long long)(2 * ox) * in_ld + cg * 8, v);
+      load8(r0 + (long long)(2 * ox + 1) * in_ld + cg * 8, a);
+      load8(r1 + (long long)(2 * ox) * in_ld + cg * 8, c);
+      load8(r1 + (long long)(2 * ox + 1) * in_ld + cg * 8, d);
 #pragma unroll
       for (int j = 0; j < 8; ++j) v[j] = (v[j] + a[j] + c[j] + d[j]) * 0.25f;
-    } else {
-      // F.interpolate(scale_factor=2, mode='bilinear', align_corners=False)
-      const float sy = fmaxf((oy + 0.5f) * 0.5f - 0.5f, 0.f), sx = fmaxf((ox + 0.5f) * 0.5f - 0.5f, 0.f);
-      const int y0 = (int)sy, x0 = (int)sx;
-      const int y1 = min(y0 + 1, H - 1), x1 = min(x0 + 1, W - 1);
-      const float ly = sy - y0, lx = sx - x0, hy = 1.f - ly, hx = 1.f - lx;
-      float a[8], c[8], d[8];
-      load8(in + pix_row(b, y0, x0, H, W, in_padded) * in_ld + cg * 8, v);
-      load8(in + pix_row(b, y0, x1, H, W, in_padded) * in_ld + cg * 8, a);
-      load8(in + pix_row(b, y1, x0, H, W, in_padded) * in_ld + cg * 8, c);
-      load8(in + pix_row(b, y1, x1, H, W, in_padded) * in_ld + cg * 8, d);
+      store8(op + (long long)ox * out_ld + cg * 8, v);
+    }
+  } else {
+    // F.interpolate(scale_factor=2, mode='bilinear', align_corners=False)
+    const float sy = fmaxf((oy + 0.5f) * 0.5f - 0.5f, 0.f);
+    const int y0 = (int)sy, y1 = min(y0 + 1, H - 1);
+    const float ly = sy - y0, hy = 1.f - ly;
+    const T* r0 = in + pix_row(b, y0, 0, H, W, in_padded) * in_ld;
+    const T* r1 = in + pix_row(b, y1, 0, H, W, in_padded) * in_ld;
+    for (int i = threadIdx.x; i < n; i += 256) {
+      const int ox = i / cgs, cg = i - ox * cgs;
+      const float sx = fmaxf((ox + 0.5f) * 0.5f - 0.5f, 0.f);
+      const int x0 = (int)sx, x1 = min(x0 + 1, W - 1);
+      const float lx = sx - x0, hx = 1.f - lx;
+      float v[8], a[8], c[8], d[8];
+      load8(r0 + (long long)x0 * in_ld + cg * 8, v);
+      load8(r0 + (long long)x1 * in_ld + cg * 8, a);
+      load8(r1 + (long long)x0 * in_ld + cg * 8, c);
+      load8(r1 + (long long)x1 * in_ld + cg * 8, d);
 #pragma unroll
       for (int j = 0; j < 8; ++j) v[j] = hy * (hx * v[j] + lx * a[j]) + ly * (hx * c[j] + lx * d[j]);
+      store8(op + (long long)ox * out_ld + cg * 8, v);
     }
-    store8(out + pix_row(b, oy, ox, OH, OW, out_padded) * out_ld + cg * 8, v);
   }
 }
 
@@ -57,7 +73,7 @@ template <typename T>
 __global__ void stem_conv1_kernel(const float* __restrict__ img, int B, int Hin, int Win, const float* __restrict__ w,
                                   const float* __restrict__ scale, const float* __restrict__ bias, int cout,
                                   T* __restrict__ out, int out_ld) {
-  extern __shared__ float sw[];  // [27][cout] + scale + bias
+  extern __shared__ __align__(16) float sw[];  // [27][cout] + scale + bias
   for (int i = threadIdx.x; i < 27 * cout; i += blockDim.x) {
     const int co = i % cout, k = i / cout;
     sw[i] = w[co * 27 + k];
@@ -85,15 +101,17 @@ __global__ void stem_conv1_kernel(const float* __restrict__ img, int B, int Hin,
     for (int c0 = 0; c0 < out_ld; c0 += 8) {
       float v[8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int co = c0 + j;
-        float acc = 0.f;
-        if (co < cout) {
+      for (int j = 0; j < 8; ++j) v[j] = 0.f;
+      if (c0 + 8 <= cout) {  // cout is a multiple of 8: whole groups only
 #pragma unroll
-          for (int k = 0; k < 27; ++k) acc = fmaf(x[k], sw[k * cout + co], acc);
-          acc = fmaxf(acc * sw[27 * cout + co] + sw[28 * cout + co], 0.f);
+        for (int k = 0; k < 27; ++k) {
+          const float4 w0 = *reinterpret_cast<const float4*>(&sw[k * cout + c0]);
+          const float4 w1 = *reinterpret_cast<const float4*>(&sw[k * cout + c0 + 4]);
+          v[0] = fmaf(x[k], w0.x, v[0]); v[1] = fmaf(x[k], w0.y, v[1]); v[2] = fmaf(x[k], w0.z, v[2]); v[3] = fmaf(x[k], w0.w, v[3]);
+          v[4] = fmaf(x[k], w1.x, v[4]); v[5] = fmaf(x[k], w1.y, v[5]); v[6] = fmaf(x[k], w1.z, v[6]); v[7] = fmaf(x[k], w1.w, v[7]);
         }
-        v[j] = acc;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j] * sw[27 * cout + c0 + j] + sw[28 * cout + c0 + j], 0.f);
       }
       store8(o + c0, v);
     }
@@ -314,9 +332,8 @@ extern "C" int crog_resample(const void* in, int32_t in_ld, int32_t in_padded, v
   CROG_REQUIRE(mode >= 0 && mode <= 2, CROG_E_BADSHAPE, "resample: bad mode %d", mode);
   if (mode == 1) CROG_REQUIRE(H % 2 == 0 && W % 2 == 0, CROG_E_BADSHAPE, "avgpool2 needs even H,W");
   const int OH = mode == 1 ? H / 2 : (mode == 2 ? 2 * H : H), OW = mode == 1 ? W / 2 : (mode == 2 ? 2 * W : W);
-  const long long total = (long long)B * OH * OW * (C / 8);
-  if (total == 0) return CROG_OK;
-  const int g = grid_for(total, 256);
+  if ((long long)B * OH * OW * C == 0) return CROG_OK;
+  const int g = B * OH;
   cudaStream_t s = (cudaStream_t)stream;
 #define RS(T, M) resample_kernel<T, M><<<g, 256, 0, s>>>((const T*)in, in_ld, in_padded, (T*)out, out_ld, out_padded, B, H, W, C)
   if (dtype == CROG_F32) { if (mode == 0) RS(float, 0); else if (mode == 1) RS(float, 1); else RS(float, 2); }
@@ -328,7 +345,7 @@ extern "C" int crog_resample(const void* in, int32_t in_ld, int32_t in_padded, v
 
 extern "C" int crog_stem_conv1(const float* img, int32_t B, int32_t Hin, int32_t Win, const float* w, const float* scale,
                                const float* bias, int32_t cout, void* out, int32_t out_ld, int32_t out_dtype, void* stream) {
-  CROG_REQUIRE(Hin % 2 == 0 && Win % 2 == 0 && out_ld % 8 == 0 && cout <= out_ld, CROG_E_BADSHAPE, "stem_conv1: bad shape");
+  CROG_REQUIRE(Hin % 2 == 0 && Win % 2 == 0 && out_ld % 8 == 0 && cout <= out_ld && cout % 8 == 0, CROG_E_BADSHAPE, "stem_conv1: bad shape");
   const long long total = (long long)B * (Hin / 2) * (Win / 2);
   if (total == 0) return CROG_OK;
   const int g = grid_for(total, 128);
