@@ -19,7 +19,7 @@
 namespace {
 
 constexpr int BAND = 32;       // output rows per CTA band
-constexpr int STRIP = 128;     // columns per warp
+constexpr int STRIP = 120;     // columns owned per warp (30 lanes x 4; lanes 0 and 31 carry the halo)
 constexpr int CAPW = 512;      // per-warp candidate list capacity
 constexpr int TSEL = 32;       // keys kept per warp segment
 constexpr int MAXK = 32;
@@ -69,7 +69,10 @@ __device__ void warp_select_top(unsigned long long* list, int n, int keep, unsig
   __syncwarp();
 }
 
-__global__ void __launch_bounds__(256) peak_scan_kernel(const float* __restrict__ q, int H, int W, float thr, int nwarps,
+// Lanes 1..30 of a warp own 4 columns each (a 120-column strip); lanes 0 and 31 load the 4 columns on either side and
+// only feed their neighbours through shuffles, so no lane needs extra halo loads.  Rows are software-pipelined five at a
+// time (the next five float4 loads are in flight while the current five are processed).
+__global__ void __launch_bounds__(256, 2) peak_scan_kernel(const float* __restrict__ q, int H, int W, float thr, int nwarps,
                                                         uint8_t* __restrict__ ws) {
   extern __shared__ unsigned long long s_lists[];  // [warps][CAPW + TSEL]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -78,43 +81,45 @@ __global__ void __launch_bounds__(256) peak_scan_kernel(const float* __restrict_
   unsigned long long* list = s_lists + warp * (CAPW + TSEL);
   unsigned long long* top = list + CAPW;
   const float* img = q + (long long)b * H * W;
-  const int c0 = warp * STRIP + lane * 4;
+  const int c0 = warp * STRIP + (lane - 1) * 4;  // may be negative (lane 0 of warp 0) or >= W
+  const bool owner = lane >= 1 && lane <= 30;
   const int y0 = band * BAND, y1 = min(y0 + BAND, H);
-  const bool vec = (W % 4 == 0);
+  const bool vec = (W % 4 == 0) && c0 >= 0 && c0 + 3 < W;
   const float NEG = -INFINITY;
 
-  float4 raw[5], hm[5];
+  auto load_row = [&](int r) -> float4 {
+    float4 v = make_float4(NEG, NEG, NEG, NEG);
+    if (r >= 0 && r < H && r < y1 + 2) {
+      const float* rowp = img + (long long)r * W;
+      if (vec) v = __ldg(reinterpret_cast<const float4*>(rowp + c0));
+      else {
+        if (c0 >= 0 && c0 < W) v.x = __ldg(rowp + c0);
+        if (c0 + 1 >= 0 && c0 + 1 < W) v.y = __ldg(rowp + c0 + 1);
+        if (c0 + 2 >= 0 && c0 + 2 < W) v.z = __ldg(rowp + c0 + 2);
+        if (c0 + 3 >= 0 && c0 + 3 < W) v.w = __ldg(rowp + c0 + 3);
+      }
+    }
+    return v;
+  };
+
+  float4 raw[5], hm[5], cur[5];
 #pragma unroll
-  for (int u = 0; u < 5; ++u) { raw[u] = make_float4(NEG, NEG, NEG, NEG); hm[u] = raw[u]; }
+  for (int u = 0; u < 5; ++u) { raw[u] = make_float4(NEG, NEG, NEG, NEG); hm[u] = raw[u]; cur[u] = load_row(y0 - 2 + u); }
   int count = 0, truncated = 0;
   float vmin = INFINITY, vmax = -INFINITY;
 
   for (int rbase = y0 - 2; rbase < y1 + 2; rbase += 5) {
+    float4 nxt[5];
+#pragma unroll
+    for (int u = 0; u < 5; ++u) nxt[u] = load_row(rbase + 5 + u);
 #pragma unroll
     for (int u = 0; u < 5; ++u) {
       const int r = rbase + u;
       if (r >= y1 + 2) break;  // warp-uniform
-      float4 v = make_float4(NEG, NEG, NEG, NEG);
-      float l2 = NEG, l1 = NEG, r1 = NEG, r2 = NEG;
-      if (r >= 0 && r < H) {
-        const float* rowp = img + (long long)r * W;
-        if (vec && c0 + 3 < W) v = __ldg(reinterpret_cast<const float4*>(rowp + c0));
-        else {
-          if (c0 < W) v.x = __ldg(rowp + c0);
-          if (c0 + 1 < W) v.y = __ldg(rowp + c0 + 1);
-          if (c0 + 2 < W) v.z = __ldg(rowp + c0 + 2);
-          if (c0 + 3 < W) v.w = __ldg(rowp + c0 + 3);
-        }
-        if (lane == 0 && c0 >= 2) { l2 = __ldg(rowp + c0 - 2); l1 = __ldg(rowp + c0 - 1); }
-        if (lane == 31) { if (c0 + 4 < W) r1 = __ldg(rowp + c0 + 4); if (c0 + 5 < W) r2 = __ldg(rowp + c0 + 5); }
-      }
-      {
-        const float sl2 = __shfl_up_sync(0xffffffffu, v.z, 1), sl1 = __shfl_up_sync(0xffffffffu, v.w, 1);
-        const float sr1 = __shfl_down_sync(0xffffffffu, v.x, 1), sr2 = __shfl_down_sync(0xffffffffu, v.y, 1);
-        if (lane != 0) { l2 = sl2; l1 = sl1; }
-        if (lane != 31) { r1 = sr1; r2 = sr2; }
-      }
-      if (r >= y0 && r < y1) {  // strip min/max over owned pixels (trivial-image test)
+      const float4 v = cur[u];
+      const float l2 = __shfl_up_sync(0xffffffffu, v.z, 1), l1 = __shfl_up_sync(0xffffffffu, v.w, 1);
+      const float r1 = __shfl_down_sync(0xffffffffu, v.x, 1), r2 = __shfl_down_sync(0xffffffffu, v.y, 1);
+      if (owner && r >= y0 && r < y1) {  // strip min/max over owned pixels (trivial-image test)
         if (c0 < W) { vmin = fminf(vmin, v.x); vmax = fmaxf(vmax, v.x); }
         if (c0 + 1 < W) { vmin = fminf(vmin, v.y); vmax = fmaxf(vmax, v.y); }
         if (c0 + 2 < W) { vmin = fminf(vmin, v.z); vmax = fmaxf(vmax, v.z); }
@@ -132,10 +137,10 @@ __global__ void __launch_bounds__(256) peak_scan_kernel(const float* __restrict_
         vm.y = max3(max3(hm[0].y, hm[1].y, hm[2].y), hm[3].y, hm[4].y);
         vm.z = max3(max3(hm[0].z, hm[1].z, hm[2].z), hm[3].z, hm[4].z);
         vm.w = max3(max3(hm[0].w, hm[1].w, hm[2].w), hm[3].w, hm[4].w);
-        const bool k0 = ctr.x == vm.x && ctr.x > thr && c0 >= 2 && c0 < W - 2;
-        const bool k1 = ctr.y == vm.y && ctr.y > thr && c0 + 1 >= 2 && c0 + 1 < W - 2;
-        const bool k2 = ctr.z == vm.z && ctr.z > thr && c0 + 2 < W - 2;
-        const bool k3 = ctr.w == vm.w && ctr.w > thr && c0 + 3 < W - 2;
+        const bool k0 = owner && ctr.x == vm.x && ctr.x > thr && c0 >= 2 && c0 < W - 2;
+        const bool k1 = owner && ctr.y == vm.y && ctr.y > thr && c0 + 1 >= 2 && c0 + 1 < W - 2;
+        const bool k2 = owner && ctr.z == vm.z && ctr.z > thr && c0 + 2 < W - 2;
+        const bool k3 = owner && ctr.w == vm.w && ctr.w > thr && c0 + 3 < W - 2;
         if (__ballot_sync(0xffffffffu, k0 | k1 | k2 | k3)) {
           if (count + 128 > CAPW) {  // make room: keep the best TSEL so far
             __syncwarp();
@@ -154,6 +159,8 @@ __global__ void __launch_bounds__(256) peak_scan_kernel(const float* __restrict_
         }
       }
     }
+#pragma unroll
+    for (int u = 0; u < 5; ++u) cur[u] = nxt[u];
   }
   __syncwarp();
   if (count > TSEL) { warp_select_top(list, count, TSEL, top, lane); count = TSEL; truncated = 1; }
@@ -337,6 +344,9 @@ __device__ int slow_count(const TgRect* A, const TgRect* Bq, int* s_red) {
   return block_sum(cnt, s_red);
 }
 
+// One CTA per sample.  Predicted rectangles are rasterised once into shared-memory row masks; then every warp takes
+// ground-truth rectangles round-robin (no CTA-wide barrier inside the loop): lane = scanline, row mask by exact integer
+// scanline arithmetic, popc(A & B) against the predictions that pass the angle gate, warp-shuffle reductions.
 __global__ void __launch_bounds__(JT) jaccard_kernel(const double* __restrict__ grasps, const int* __restrict__ n_peaks, int K,
                                                      double* __restrict__ gt, const int* __restrict__ gt_count, int Mmax,
                                                      int* __restrict__ inter_out, int* __restrict__ uni_out,
@@ -346,8 +356,8 @@ __global__ void __launch_bounds__(JT) jaccard_kernel(const double* __restrict__ 
   __shared__ int s_parea[MAXK];
   __shared__ TgRect s_gt;
   __shared__ int s_red[JT / 32];
-  __shared__ int s_j1, s_jk;
-  const int b = blockIdx.x, tid = threadIdx.x;
+  __shared__ int s_j1, s_jk, s_slow;
+  const int b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int n = min(n_peaks ? n_peaks[b] : K, K);
   const int M = min(gt_count[b], Mmax);
   double* G = gt + (long long)b * Mmax * 6;
@@ -358,9 +368,11 @@ __global__ void __launch_bounds__(JT) jaccard_kernel(const double* __restrict__ 
     const double w = G[m * 6 + 2];
     G[m * 6 + 2] = w < 0.0 ? 0.0 : (w > 100.0 ? 100.0 : w);  // NaN stays NaN like np.clip
   }
-  if (tid == 0) { s_j1 = 0; s_jk = 0; }
+  if (tid == 0) { s_j1 = 0; s_jk = 0; s_slow = 0; }
   if (tid < n) tg_make_rect(P + tid * 5, &s_pred[tid]);
   __syncthreads();
+  int all_fast = 1;
+  for (int k = 0; k < n; ++k) all_fast &= s_pred[k].fast;
   // predicted rectangles: row masks + areas
   for (int k = 0; k < n; ++k) {
     const TgRect* R = &s_pred[k];
@@ -380,63 +392,100 @@ __global__ void __launch_bounds__(JT) jaccard_kernel(const double* __restrict__ 
     if (tid == 0) s_parea[k] = cnt;
   }
   __syncthreads();
-  for (int m = 0; m < M; ++m) {
+  if (inter_out) {
+    for (int i = tid; i < K * Mmax; i += JT) {
+      inter_out[(long long)b * K * Mmax + i] = 0; uni_out[(long long)b * K * Mmax + i] = 0;
+    }
+    __syncthreads();
+  }
+  if (all_fast) {
+    // ---- warp-per-GT path
+    for (int m = warp; m < M; m += JT / 32) {
+      const double* g = G + m * 6;
+      uint32_t pass = 0;
+      for (int k = 0; k < n; ++k) {
+        const double tp = P[k * 5 + 4], tg = g[4];
+        if (!(fabs(tp - tg) > 30.0 && fabs(tp + tg) > 30.0)) pass |= 1u << k;
+      }
+      if (!pass) continue;  // warp-uniform
+      TgRect Gr;
+      tg_make_rect(g, &Gr);  // every lane computes the same rectangle (no shared-memory round trip)
+      if (!Gr.fast) {  // oversized GT (only possible with edit_gt == 0): handled by the CTA-synchronous path below
+        if (lane == 0) s_slow = 1;
+        continue;
+      }
+      if (!inter_out) {  // J only needs pairs that can intersect: drop gated predictions whose boxes miss this GT
+        uint32_t keep = 0;
+        for (int k = 0; k < n; ++k) if ((pass >> k) & 1u) {
+          const TgRect* R = &s_pred[k];
+          if (!(R->x1 < Gr.x0 || R->x0 > Gr.x1 || R->y1 < Gr.y0 || R->y0 > Gr.y1)) keep |= 1u << k;
+        }
+        pass = keep;
+        if (!pass) continue;
+      }
+      int garea = 0;
+      int inter[MAXK];
+#pragma unroll 1
+      for (int k = 0; k < n; ++k) inter[k] = 0;
+      for (int X = Gr.x0 + lane; X <= Gr.x1; X += 32) {
+        uint32_t grow[TG_WORDS];
+        tg_row_mask(&Gr, X, grow);
+#pragma unroll
+        for (int w = 0; w < TG_WORDS; ++w) garea += __popc(grow[w]);
+        for (int k = 0; k < n; ++k) {
+          if (!((pass >> k) & 1u)) continue;
+          const TgRect* R = &s_pred[k];
+          if (X < R->x0 || X > R->x1) continue;
+          const uint32_t* prow = s_mask + ((long long)k * TG_MAXROWS + (X - R->x0)) * TG_WORDS;
+          const int dw = Gr.yw0 - R->yw0;
+          int c = 0;
+#pragma unroll
+          for (int w = 0; w < TG_WORDS; ++w) {
+            const int pw = w + dw;
+            if (pw >= 0 && pw < TG_WORDS) c += __popc(grow[w] & prow[pw]);
+          }
+          inter[k] += c;
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) garea += __shfl_xor_sync(0xffffffffu, garea, o);
+      for (int k = 0; k < n; ++k) {
+        if (!((pass >> k) & 1u)) continue;
+        int it = inter[k];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) it += __shfl_xor_sync(0xffffffffu, it, o);
+        const int uni = s_parea[k] + garea - it;
+        if (lane == 0) {
+          if (inter_out) { inter_out[((long long)b * K + k) * Mmax + m] = it; uni_out[((long long)b * K + k) * Mmax + m] = uni; }
+          if (uni > 0 && 4LL * it > (long long)uni) { atomicOr(&s_jk, 1); if (k == 0) atomicOr(&s_j1, 1); }
+        }
+      }
+    }
+    __syncthreads();
+  }
+  // ---- CTA-synchronous path: samples with oversized predictions, and oversized GT rectangles of any sample
+  const bool need_slow = !all_fast || s_slow;  // block-uniform (read after the barrier above)
+  for (int m = 0; need_slow && m < M; ++m) {
     const double* g = G + m * 6;
-    // which predictions pass the angle gate (grasp_eval.py:306)
     uint32_t pass = 0;
     for (int k = 0; k < n; ++k) {
       const double tp = P[k * 5 + 4], tg = g[4];
       if (!(fabs(tp - tg) > 30.0 && fabs(tp + tg) > 30.0)) pass |= 1u << k;
-    }
-    if (inter_out) for (int k = tid; k < K; k += JT) {
-      inter_out[((long long)b * K + k) * Mmax + m] = 0; uni_out[((long long)b * K + k) * Mmax + m] = 0;
     }
     if (!pass) continue;  // block-uniform
     __syncthreads();
     if (tid == 0) tg_make_rect(g, &s_gt);
     __syncthreads();
     const TgRect* Gr = &s_gt;
-    // GT row mask for this thread's scanline (fast path) + area
-    uint32_t grow[TG_WORDS];
-#pragma unroll
-    for (int w = 0; w < TG_WORDS; ++w) grow[w] = 0u;
-    int garea;
-    if (Gr->fast) {
-      int cnt = 0;
-      const int X = Gr->x0 + tid;
-      if (X <= Gr->x1) {
-        tg_row_mask(Gr, X, grow);
-#pragma unroll
-        for (int w = 0; w < TG_WORDS; ++w) cnt += __popc(grow[w]);
-      }
-      garea = block_sum(cnt, s_red);
-    } else {
-      garea = slow_count(Gr, nullptr, s_red);
-    }
+    if (all_fast && Gr->fast) continue;  // already handled by the warp path (block-uniform)
+    const int garea = slow_count(Gr, nullptr, s_red);
     for (int k = 0; k < n; ++k) {
       if (!((pass >> k) & 1u)) continue;
-      const TgRect* R = &s_pred[k];
-      int inter;
-      if (R->fast && Gr->fast) {
-        int cnt = 0;
-        const int X = Gr->x0 + tid;  // this thread's GT scanline
-        if (X <= Gr->x1 && X >= R->x0 && X <= R->x1) {
-          const uint32_t* prow = s_mask + ((long long)k * TG_MAXROWS + (X - R->x0)) * TG_WORDS;
-          const int dw = Gr->yw0 - R->yw0;  // word offset between the two anchors
-#pragma unroll
-          for (int w = 0; w < TG_WORDS; ++w) {
-            const int pw = w + dw;
-            if (pw >= 0 && pw < TG_WORDS) cnt += __popc(grow[w] & prow[pw]);
-          }
-        }
-        inter = block_sum(cnt, s_red);
-      } else {
-        inter = slow_count(R, Gr, s_red);
-      }
-      const int uni = s_parea[k] + garea - inter;
+      const int it = slow_count(&s_pred[k], Gr, s_red);
+      const int uni = s_parea[k] + garea - it;
       if (tid == 0) {
-        if (inter_out) { inter_out[((long long)b * K + k) * Mmax + m] = inter; uni_out[((long long)b * K + k) * Mmax + m] = uni; }
-        if (uni > 0 && 4LL * inter > (long long)uni) { s_jk = 1; if (k == 0) s_j1 = 1; }
+        if (inter_out) { inter_out[((long long)b * K + k) * Mmax + m] = it; uni_out[((long long)b * K + k) * Mmax + m] = uni; }
+        if (uni > 0 && 4LL * it > (long long)uni) { s_jk = 1; if (k == 0) s_j1 = 1; }
       }
     }
   }
