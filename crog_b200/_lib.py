@@ -48,6 +48,7 @@ SIGNATURES = {
     "crog_gather_eot": (C.c_int, [_P, _P, _I, _P, _I, _I, _I, _I, _P]),
     "crog_attention": (C.c_int, [_P, _I, _P, _I, _P, _I, _P, _I, _I, _I, _I, _I, _F, _I, _P, _I, _P]),
     "crog_dynw_fold": (C.c_int, [_P, _I, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P]),
+    "crog_dynconv_gather": (C.c_int, [_P, _I, _P, _I, _I, _I, _I, _P]),
     "crog_cast": (C.c_int, [_P, _I, _P, _I, _L, _P]),
     "crog_split_heads": (C.c_int, [_P, _I, _P, _L, _I, _P]),
     "crog_sigmoid_bicubic": (C.c_int, [_P, _P, _I, _I, _I, _I, _I, _I, _U, _P]),

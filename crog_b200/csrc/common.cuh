@@ -82,36 +82,36 @@ struct RowMap {
   int valid;        // row produces output
   int b;            // sample index
   int sp;           // interior pixel index (y*W+x) or row-in-sample
-  long long orow;   // output row
+  int orow;         // output row (row counts fit 32 bits; multiply by the leading dimension in 64 bits)
 };
 
-__device__ __forceinline__ RowMap map_row(const CrogGemm& g, long long r, long long row_end) {
+__device__ __forceinline__ RowMap map_row(const CrogGemm& g, long long r64, long long row_end) {
   RowMap m;
-  m.valid = r < row_end;
+  const int r = (int)r64;
+  m.valid = r64 < row_end;
   m.b = 0; m.sp = 0; m.orow = r;
   if (!m.valid) return m;
   if (g.H == 0) {
-    if (g.sample_rows > 0) { m.b = (int)(r / g.sample_rows); m.sp = (int)(r % g.sample_rows); }
-    else m.sp = (int)r;
+    if (g.sample_rows > 0) { m.b = r / g.sample_rows; m.sp = r - m.b * g.sample_rows; }
+    else m.sp = r;
     return m;
   }
   int y, x;
   if (g.in_padded) {
     const int PW = g.W + 2, P = (g.H + 2) * PW;
-    m.b = (int)(r / P);
-    const int rem = (int)(r % P);
-    const int yy = rem / PW, xx = rem % PW;
+    m.b = r / P;
+    const int rem = r - m.b * P;
+    const int yy = rem / PW, xx = rem - yy * PW;
     m.valid = (yy >= 1) && (yy <= g.H) && (xx >= 1) && (xx <= g.W);
     y = yy - 1; x = xx - 1;
   } else {
     const int P = g.H * g.W;
-    m.b = (int)(r / P);
-    const int rem = (int)(r % P);
-    y = rem / g.W; x = rem % g.W;
+    m.b = r / P;
+    const int rem = r - m.b * P;
+    y = rem / g.W; x = rem - y * g.W;
   }
   m.sp = y * g.W + x;
-  m.orow = g.out_padded ? ((long long)(m.b * (g.H + 2) + y + 1) * (g.W + 2) + x + 1)
-                        : ((long long)(m.b * g.H + y) * g.W + x);
+  m.orow = g.out_padded ? ((m.b * (g.H + 2) + y + 1) * (g.W + 2) + x + 1) : ((m.b * g.H + y) * g.W + x);
   return m;
 }
 
@@ -175,8 +175,8 @@ __device__ __forceinline__ void epilogue_row(const CrogGemm& g, const RowMap& m,
   epilogue_math<CNT>(g, m, n0, acc, sc, bi);
   const bool full = (nvalid == CNT);
   if (g.out_dtype == CROG_BF16) {
-    bf16* o = reinterpret_cast<bf16*>(g.out) + m.orow * g.out_ld + n0;
-    const bf16* rs = g.residual ? reinterpret_cast<const bf16*>(g.residual) + m.orow * g.res_ld + n0 : nullptr;
+    bf16* o = reinterpret_cast<bf16*>(g.out) + (long long)m.orow * g.out_ld + n0;
+    const bf16* rs = g.residual ? reinterpret_cast<const bf16*>(g.residual) + (long long)m.orow * g.res_ld + n0 : nullptr;
     if (full) {
 #pragma unroll
       for (int j = 0; j < CNT; j += 8) {
@@ -198,8 +198,8 @@ __device__ __forceinline__ void epilogue_row(const CrogGemm& g, const RowMap& m,
       }
     }
   } else {
-    float* o = reinterpret_cast<float*>(g.out) + m.orow * g.out_ld + n0;
-    const float* rs = g.residual ? reinterpret_cast<const float*>(g.residual) + m.orow * g.res_ld + n0 : nullptr;
+    float* o = reinterpret_cast<float*>(g.out) + (long long)m.orow * g.out_ld + n0;
+    const float* rs = g.residual ? reinterpret_cast<const float*>(g.residual) + (long long)m.orow * g.res_ld + n0 : nullptr;
     if (full) {
 #pragma unroll
       for (int j = 0; j < CNT; j += 4) {

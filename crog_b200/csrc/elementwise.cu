@@ -199,25 +199,41 @@ __global__ void txt_linear_kernel(const T* __restrict__ state, const float* __re
 
 template <typename T>
 __global__ void dynw_fold_kernel(const float* __restrict__ t, const float* __restrict__ vw, const float* __restrict__ vb,
-                                 T* __restrict__ wfold, int B, int C, int NH, int NH_pad, int Cpad) {
-  // one block per (b, h, tap); threads over j
-  const int tap = blockIdx.x % 9, h = (blockIdx.x / 9) % NH_pad, b = blockIdx.x / (9 * NH_pad);
+                                 T* __restrict__ wfold, int B, int C, int NH, int rows_per_sample, int Cpad) {
+  // one block per (b, h, tap); threads over j.  Output row of sample b: h*9 + tap.
+  const int tap = blockIdx.x % 9, h = (blockIdx.x / 9) % NH, b = blockIdx.x / (9 * NH);
   const int O = 9 * C + 1;
   extern __shared__ float s_w[];  // w_dyn[b, :, tap]
   for (int c = threadIdx.x; c < C; c += blockDim.x) s_w[c] = t[(long long)b * O + c * 9 + tap];
   __syncthreads();
-  T* dst = wfold + ((long long)(b * NH_pad + h) * 9 + tap) * Cpad;
+  T* dst = wfold + ((long long)b * rows_per_sample + h * 9 + tap) * Cpad;
   for (int j = threadIdx.x; j < Cpad; j += blockDim.x) {
     float acc = 0.f;
-    if (h < NH) {
-      if (j < C) {
-        for (int c = 0; c < C; ++c) acc = fmaf(s_w[c], __ldg(vw + (long long)(h * C + c) * C + j), acc);
-      } else if (j == C) {
-        for (int c = 0; c < C; ++c) acc = fmaf(s_w[c], __ldg(vb + h * C + c), acc);
-        if (tap == 4) acc += t[(long long)b * O + 9 * C];
-      }
+    if (j < C) {
+      for (int c = 0; c < C; ++c) acc = fmaf(s_w[c], __ldg(vw + (long long)(h * C + c) * C + j), acc);
+    } else if (j == C) {
+      for (int c = 0; c < C; ++c) acc = fmaf(s_w[c], __ldg(vb + h * C + c), acc);
+      if (tap == 4) acc += t[(long long)b * O + 9 * C];
     }
     dst[j] = from_f<T>(acc);
+  }
+}
+
+// out[h][b, y, x] = sum_tap Z[padded_row(b, y+ky-1, x+kx-1), h*9 + tap]: the nine shifted reads of the per-tap partial
+// products that the per-sample 1x1 GEMM left in the zero-haloed Z matrix.
+__global__ void dynconv_gather_kernel(const float* __restrict__ z, int ldz, float* __restrict__ out, int B, int H, int W, int NH) {
+  const long long total = (long long)B * H * W;
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int x = (int)(i % W), y = (int)((i / W) % H), b = (int)(i / ((long long)W * H));
+  const int PW = W + 2;
+  const long long base = ((long long)b * (H + 2) + y) * PW + x;  // padded row of (y-1, x-1)
+  for (int h = 0; h < NH; ++h) {
+    float acc = 0.f;
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap)
+      acc += __ldg(z + (base + (tap / 3) * PW + (tap % 3)) * ldz + h * 9 + tap);
+    out[(long long)h * total + i] = acc;
   }
 }
 
@@ -401,7 +417,7 @@ extern "C" int crog_gather_eot(const int64_t* word, const void* x, int32_t x_dty
 extern "C" int crog_dynw_fold(const void* state, int32_t state_dtype, const float* txt_w, const float* txt_b, const float* v_w,
                               const float* v_b, float* scratch, void* wfold, int32_t dtype, int32_t B, int32_t word_dim,
                               int32_t C, int32_t NH, int32_t NH_pad, int32_t Cpad, void* stream) {
-  CROG_REQUIRE(Cpad > C && NH <= NH_pad, CROG_E_BADSHAPE, "dynw_fold: Cpad must exceed C (ones channel)");
+  CROG_REQUIRE(Cpad > C && 9 * NH <= NH_pad, CROG_E_BADSHAPE, "dynw_fold: need Cpad > C (ones channel) and rows_per_sample >= 9*NH");
   if (B == 0) return CROG_OK;
   cudaStream_t s = (cudaStream_t)stream;
   const int O = 9 * C + 1;
@@ -410,10 +426,18 @@ extern "C" int crog_dynw_fold(const void* state, int32_t state_dtype, const floa
   if (state_dtype == CROG_F32) txt_linear_kernel<float><<<g1, 256, 0, s>>>((const float*)state, txt_w, txt_b, scratch, B, word_dim, O);
   else txt_linear_kernel<bf16><<<g1, 256, 0, s>>>((const bf16*)state, txt_w, txt_b, scratch, B, word_dim, O);
   CROG_LAUNCH_OK("txt_linear");
-  const int g2 = B * NH_pad * 9;
+  const int g2 = B * NH * 9;
   if (dtype == CROG_F32) dynw_fold_kernel<float><<<g2, 128, C * sizeof(float), s>>>(scratch, v_w, v_b, (float*)wfold, B, C, NH, NH_pad, Cpad);
   else dynw_fold_kernel<bf16><<<g2, 128, C * sizeof(float), s>>>(scratch, v_w, v_b, (bf16*)wfold, B, C, NH, NH_pad, Cpad);
   CROG_LAUNCH_OK("dynw_fold");
+  return CROG_OK;
+}
+
+extern "C" int crog_dynconv_gather(const float* z, int32_t ldz, float* out, int32_t B, int32_t H, int32_t W, int32_t NH, void* stream) {
+  const long long total = (long long)B * H * W;
+  if (total == 0) return CROG_OK;
+  dynconv_gather_kernel<<<(int)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(z, ldz, out, B, H, W, NH);
+  CROG_LAUNCH_OK("dynconv_gather");
   return CROG_OK;
 }
 

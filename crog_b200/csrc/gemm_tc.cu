@@ -139,29 +139,51 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
       }
       epi_bar_sync();
       const RowMap m = map_row(g, tr.row0 + q * 32 + lane, tr.row_end);
-      const long long my_orow = m.valid ? m.orow : -1;
+      const int my_orow = m.valid ? m.orow : -1;
+      // phase-2 ownership: lane -> (row p*RPP + rsub, 8-column unit u) of every staged sub-block
+      const int u = lane % UPR, rsub = lane / UPR;
+      int orow[PASSES];
+#pragma unroll
+      for (int p = 0; p < PASSES; ++p) orow[p] = __shfl_sync(0xffffffffu, my_orow, p * RPP + rsub);
+      // bf16 residual tiles are fetched before the accumulator is even ready, so their HBM latency hides behind the
+      // MMA of this tile and the drain of the previous one
+      constexpr bool PREFETCH = (BN <= 128);
+      constexpr int NSUB = L::HALF / L::SUB;
+      uint4 rpre[PREFETCH ? NSUB * PASSES : 1];
+      const bool res_bf16 = g.residual != nullptr && g.out_dtype == CROG_BF16;
+      if constexpr (PREFETCH) {
+        if (res_bf16 && active) {
+#pragma unroll
+          for (int sb = 0; sb < NSUB; ++sb) {
+            const int ncol = n0 + hsel * L::HALF + sb * L::SUB + u * 8;
+#pragma unroll
+            for (int p = 0; p < PASSES; ++p)
+              rpre[sb * PASSES + p] = (ncol < g.N && orow[p] >= 0)
+                  ? __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(g.residual) + (long long)orow[p] * g.res_ld + ncol))
+                  : make_uint4(0, 0, 0, 0);
+          }
+        }
+      }
       mbar_wait(tfull0 + 8 * as, (i >> 1) & 1);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * BN + hsel * L::HALF;
-#pragma unroll 1
-      for (int sub = 0; sub < L::HALF; sub += L::SUB) {
+#pragma unroll
+      for (int sbi = 0; sbi < NSUB; ++sbi) {
+        const int sub = sbi * L::SUB;
         const int cbase = hsel * L::HALF + sub;  // column of the tile where this staged block starts
         if (active) {
           // ---- phase 1: accumulator -> registers -> epilogue math -> fp32 staging (thread = row)
           if constexpr (L::SUB >= 32) {
-#pragma unroll 1
-            for (int c = 0; c < L::SUB; c += 32) {
-              uint32_t r[32];
-              tc_ld32(taddr + sub + c, r);
-              tc_wait_ld();
-              float acc[32];
+            uint32_t r[32];
+            tc_ld32(taddr + sub, r);
+            tc_wait_ld();
+            float acc[32];
 #pragma unroll
-              for (int j = 0; j < 32; ++j) acc[j] = __uint_as_float(r[j]);
-              if (m.valid && n0 + cbase + c < g.N) epilogue_math<32>(g, m, n0 + cbase + c, acc, sc + cbase + c, bi + cbase + c);
-              float4* dst = reinterpret_cast<float4*>(stg + lane * L::PITCH + c * 4);
+            for (int j = 0; j < 32; ++j) acc[j] = __uint_as_float(r[j]);
+            if (m.valid && n0 + cbase < g.N) epilogue_math<32>(g, m, n0 + cbase, acc, sc + cbase, bi + cbase);
+            float4* dst = reinterpret_cast<float4*>(stg + lane * L::PITCH);
 #pragma unroll
-              for (int j = 0; j < 8; ++j) dst[j] = make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
-            }
+            for (int j = 0; j < 8; ++j) dst[j] = make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
           } else {
             uint32_t r[16];
             tc_ld16(taddr + sub, r);
@@ -175,25 +197,19 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
             for (int j = 0; j < 4; ++j) dst[j] = make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
           }
         }
-        if (sub + L::SUB >= L::HALF) {  // last read of this accumulator buffer: hand it back to the MMA warp
+        if (sbi == NSUB - 1) {  // last read of this accumulator buffer: hand it back to the MMA warp
           tc_fence_before();
           mbar_arrive(tempty0 + 8 * as);
         }
         __syncwarp();
         if (active) {
           // ---- phase 2: staging -> (+residual) -> global, row-contiguous 16-byte accesses
-          const int u = lane % UPR, rsub = lane / UPR;
           const int ncol = n0 + cbase + u * 8;
           const bool colok = ncol < g.N;
           float v[PASSES][8];
-          long long orow[PASSES];
 #pragma unroll
           for (int p = 0; p < PASSES; ++p) {
-            const int row = p * RPP + rsub;
-            const int lo = __shfl_sync(0xffffffffu, (int)(my_orow & 0xffffffffll), row);
-            const int hi = __shfl_sync(0xffffffffu, (int)(my_orow >> 32), row);
-            orow[p] = ((long long)hi << 32) | (unsigned int)lo;
-            const float4* src = reinterpret_cast<const float4*>(stg + row * L::PITCH + u * 32);
+            const float4* src = reinterpret_cast<const float4*>(stg + (p * RPP + rsub) * L::PITCH + u * 32);
             const float4 a = src[0], b = src[1];
             v[p][0] = a.x; v[p][1] = a.y; v[p][2] = a.z; v[p][3] = a.w; v[p][4] = b.x; v[p][5] = b.y; v[p][6] = b.z; v[p][7] = b.w;
           }
@@ -201,10 +217,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
             if (g.out_dtype == CROG_BF16) {
               uint4 rr[PASSES];
 #pragma unroll
-              for (int p = 0; p < PASSES; ++p)
-                rr[p] = (colok && orow[p] >= 0)
-                            ? __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(g.residual) + orow[p] * g.res_ld + ncol))
-                            : make_uint4(0, 0, 0, 0);
+              for (int p = 0; p < PASSES; ++p) {
+                if constexpr (PREFETCH) rr[p] = rpre[sbi * PASSES + p];
+                else
+                  rr[p] = (colok && orow[p] >= 0)
+                              ? __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(g.residual) + (long long)orow[p] * g.res_ld + ncol))
+                              : make_uint4(0, 0, 0, 0);
+              }
 #pragma unroll
               for (int p = 0; p < PASSES; ++p) {
                 const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&rr[p]);
@@ -219,7 +238,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
 #pragma unroll
               for (int p = 0; p < PASSES; ++p) {
                 if (colok && orow[p] >= 0) {
-                  const float4* rp = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(g.residual) + orow[p] * g.res_ld + ncol);
+                  const float4* rp = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(g.residual) + (long long)orow[p] * g.res_ld + ncol);
                   ra[p] = rp[0]; rb[p] = rp[1];
                 } else {
                   ra[p] = make_float4(0, 0, 0, 0); rb[p] = ra[p];
@@ -241,8 +260,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
 #pragma unroll
           for (int p = 0; p < PASSES; ++p) {
             if (!colok || orow[p] < 0) continue;
-            if (g.out_dtype == CROG_BF16) store8(reinterpret_cast<bf16*>(g.out) + orow[p] * g.out_ld + ncol, v[p]);
-            else store8(reinterpret_cast<float*>(g.out) + orow[p] * g.out_ld + ncol, v[p]);
+            if (g.out_dtype == CROG_BF16) store8(reinterpret_cast<bf16*>(g.out) + (long long)orow[p] * g.out_ld + ncol, v[p]);
+            else store8(reinterpret_cast<float*>(g.out) + (long long)orow[p] * g.out_ld + ncol, v[p]);
           }
         }
         __syncwarp();  // staging is reused by the next sub-block / tile

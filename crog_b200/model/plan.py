@@ -498,7 +498,7 @@ class ForwardPlan:
         sd, B, lib = self.sd, self.B, self.lib
         Cc = sd["proj.vis.3.0.weight"].shape[0]
         NH = sd["proj.vis.4.weight"].shape[0] // Cc
-        NHP, CP = 16, Cc + 64
+        ZR, CP = ((9 * NH + 15) // 16) * 16, Cc + 64  # Z columns (9 taps x NH heads, padded), feature channels + ones chunk
         H1, W1 = fq.H * 2, fq.W * 2
         u1 = self.new(H1, W1, fq.C, padded=True)
         self.resample("proj.up1", fq, u1, L.RS_BILINEAR2)
@@ -510,21 +510,21 @@ class ForwardPlan:
         feat = self.new(H2, W2, CP, padded=True)
         feat.t.view(B, H2 + 2, W2 + 2, CP)[:, 1:-1, 1:-1, Cc] = 1.0  # constant-one channel carrying the biases
         self._cbr("proj.vis.3", "proj.vis.3", u2, feat.cols(0, Cc), 9)
-        wfold = torch.zeros((B * NHP, 9 * CP), device=self.dev, dtype=self.adt)
+        wfold = torch.zeros((B * ZR, CP), device=self.dev, dtype=self.adt)
         scratch = torch.zeros((B, 9 * Cc + 1), device=self.dev, dtype=torch.float32)
         tw, tb = self.f32(sd["proj.txt.weight"]), self.f32(sd["proj.txt.bias"])
         vw = self.f32(sd["proj.vis.4.weight"].reshape(NH * Cc, Cc))
         vb = self.f32(sd["proj.vis.4.bias"])
         a = (state32.ptr, L.F32, tw.data_ptr(), tb.data_ptr(), vw.data_ptr(), vb.data_ptr(), scratch.data_ptr(),
-             wfold.data_ptr(), self.acode, B, state32.C, Cc, NH, NHP, CP)
+             wfold.data_ptr(), self.acode, B, state32.C, Cc, NH, ZR, CP)
         self._hold.extend([wfold, scratch])
         self._add("proj.dynw_fold", lambda s: L.check(lib.crog_dynw_fold(*a, s)), launches=2)
-        heads = self.new(H2, W2, NHP, dtype=torch.float32)
-        self.gemm("proj.dynconv", feat, wfold, NHP, heads, taps=9, w_sample_stride=NHP * 9 * CP, cin=CP,
-                  alg_n=NH, alg_cin=Cc)
+        # per-sample 1x1 GEMM: Z[p, h*9+tap] = feat[p, :] . wfold[b, h*9+tap, :]  (features are read once, not nine times)
+        z = self.new(H2, W2, ZR, padded=True, dtype=torch.float32)
+        self.gemm("proj.dynconv", feat, wfold, ZR, z, taps=1, w_sample_stride=ZR * CP, cin=CP, alg_n=9 * NH, alg_cin=Cc)
         self.out = torch.zeros((NH, B, 1, H2, W2), device=self.dev, dtype=torch.float32)
-        a2 = (heads.ptr, heads.ld, self.out.data_ptr(), B * H2 * W2, NH)
-        self._add("proj.split", lambda s: L.check(lib.crog_split_heads(*a2, s)))
+        a2 = (z.ptr, z.ld, self.out.data_ptr(), B, H2, W2, NH)
+        self._add("proj.gather", lambda s: L.check(lib.crog_dynconv_gather(*a2, s)))
         self.NH = NH
 
     # ------------------------------------------------------------------ execution

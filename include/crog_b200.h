@@ -125,14 +125,18 @@ int crog_attention(const void* q, int32_t ldq, const void* k, int32_t ldk, const
 
 /* Projector text branch (layers.py:91-93) folded with vis.4 (layers.py:58,70-77):
  * t = Linear(state); w_dyn = t[:, :-1] as [C,3,3]; b_dyn = t[:, -1];
- * wfold[b, h, tap*Cpad + j] = sum_c w_dyn[b,c,tap] * V[h*C + c, j]   (j < C)
- * wfold[b, h, tap*Cpad + C] = sum_c w_dyn[b,c,tap] * vb[h*C + c] (+ b_dyn[b] on the centre tap)
- * so that the five dynamic convolutions become one per-sample 3x3 convolution over the
- * C feature channels plus a constant-one channel.  wfold: [B, NH_pad, 9*Cpad] of dtype. */
+ * wfold[b, h*9 + tap, j] = sum_c w_dyn[b,c,tap] * V[h*C + c, j]   (j < C)
+ * wfold[b, h*9 + tap, C] = sum_c w_dyn[b,c,tap] * vb[h*C + c] (+ b_dyn[b] on the centre tap), zero for j > C
+ * wfold: [B, rows_per_sample, Cpad] of dtype (rows_per_sample >= 9*NH; rows >= 9*NH are left untouched).
+ * With a constant-one channel at index C of the feature map, Z = feat x wfold[b]^T (a per-sample 1x1 GEMM) holds the
+ * nine per-tap partial products of all NH heads, biases included, and crog_dynconv_gather sums the nine shifted
+ * reads: the five grouped 3x3 dynamic convolutions of the reference in one pass over the features. */
 int crog_dynw_fold(const void* state, int32_t state_dtype, const float* txt_w, const float* txt_b,
                    const float* v_w, const float* v_b, float* scratch /*[B, 9*C+1]*/, void* wfold,
-                   int32_t dtype, int32_t B, int32_t word_dim, int32_t C, int32_t NH, int32_t NH_pad,
+                   int32_t dtype, int32_t B, int32_t word_dim, int32_t C, int32_t NH, int32_t rows_per_sample,
                    int32_t Cpad, void* stream);
+/* z: zero-haloed [B*(H+2)*(W+2), ldz] fp32 with column h*9+tap; out: NH planes [NH][B,H,W] fp32 (the B x 1 x H x W logits). */
+int crog_dynconv_gather(const float* z, int32_t ldz, float* out, int32_t B, int32_t H, int32_t W, int32_t NH, void* stream);
 
 /* Element-wise dtype conversion (CROG_F32 <-> CROG_BF16) of n contiguous elements. */
 int crog_cast(const void* in, int32_t in_dtype, void* out, int32_t out_dtype, int64_t n, void* stream);

@@ -237,25 +237,40 @@ def test_embed_gather_cast_split():
 @pytest.mark.parametrize("dt", [torch.float32, BF])
 def test_dynw_fold(dt):
     lib = L.lib()
-    B, WD, Cc, NH, NHP, CP = 2, 1024, 256, 5, 16, 320
+    B, WD, Cc, NH, ZR, CP = 2, 1024, 256, 5, 48, 320
     state = _rand(B, WD, seed=27)
     tw, tb = _rand(9 * Cc + 1, WD, seed=28, scale=WD ** -0.5), _rand(9 * Cc + 1, seed=29)
     vw, vb = _rand(NH * Cc, Cc, seed=30, scale=Cc ** -0.5), _rand(NH * Cc, seed=31)
     scratch = torch.zeros(B, 9 * Cc + 1, device=DEV)
-    wf = torch.full((B, NHP, 9, CP), 3.0, device=DEV, dtype=dt)
+    wf = torch.full((B, ZR, CP), 3.0, device=DEV, dtype=dt)
     L.check(lib.crog_dynw_fold(state.data_ptr(), L.F32, tw.data_ptr(), tb.data_ptr(), vw.data_ptr(), vb.data_ptr(), scratch.data_ptr(),
-                               wf.data_ptr(), L.dtype_code(dt), B, WD, Cc, NH, NHP, CP, L.stream_ptr()))
+                               wf.data_ptr(), L.dtype_code(dt), B, WD, Cc, NH, ZR, CP, L.stream_ptr()))
     torch.cuda.synchronize()
     t = state @ tw.t() + tb
     assert maxerr(scratch, t) < 1e-4
     wd = t[:, :-1].view(B, Cc, 9)  # [b, c, tap]
     V = vw.view(NH, Cc, Cc)  # [h, c, j]
-    want = torch.zeros(B, NHP, 9, CP, device=DEV)
-    want[:, :NH, :, :Cc] = torch.einsum("bct,hcj->bhtj", wd, V)
-    want[:, :NH, :, Cc] = torch.einsum("bct,hc->bht", wd, vb.view(NH, Cc))
-    want[:, :NH, 4, Cc] += t[:, -1:].expand(B, NH)
-    assert relerr(wf, want) < (1e-5 if dt == torch.float32 else 5e-3)
-    assert wf[:, NH:].abs().max() == 0 and wf[:, :, :, Cc + 1:].abs().max() == 0
+    want = torch.zeros(B, NH, 9, CP, device=DEV)
+    want[..., :Cc] = torch.einsum("bct,hcj->bhtj", wd, V)
+    want[..., Cc] = torch.einsum("bct,hc->bht", wd, vb.view(NH, Cc))
+    want[:, :, 4, Cc] += t[:, -1:].expand(B, NH)
+    assert relerr(wf[:, :9 * NH], want.view(B, 9 * NH, CP)) < (1e-5 if dt == torch.float32 else 5e-3)
+    assert (wf[:, 9 * NH:] == 3.0).all() and wf[:, :9 * NH, Cc + 1:].abs().max() == 0
+
+
+def test_dynconv_gather_equals_grouped_conv():
+    """Z = per-tap partial products in a zero-haloed matrix; the gather must equal a 3x3 pad-1 convolution."""
+    lib = L.lib()
+    B, H, W, NH, ZR = 2, 9, 7, 5, 48
+    zt = _rand(B, NH, 9, H, W, seed=60)  # z[b, h, tap, y, x]
+    z = torch.zeros(B, H + 2, W + 2, ZR, device=DEV)
+    z[:, 1:-1, 1:-1, :9 * NH] = zt.permute(0, 3, 4, 1, 2).reshape(B, H, W, 9 * NH)
+    out = torch.zeros(NH, B, H, W, device=DEV)
+    L.check(lib.crog_dynconv_gather(z.data_ptr(), ZR, out.data_ptr(), B, H, W, NH, L.stream_ptr()))
+    torch.cuda.synchronize()
+    zp = F.pad(zt, (1, 1, 1, 1))
+    want = sum(zp[:, :, t, t // 3:t // 3 + H, t % 3:t % 3 + W] for t in range(9)).permute(1, 0, 2, 3)
+    assert maxerr(out, want) < 1e-5
 
 
 def test_sigmoid_bicubic():
