@@ -118,8 +118,8 @@ __device__ __forceinline__ RowMap map_row(const CrogGemm& g, long long r64, long
 __device__ __forceinline__ float quickgelu(float v) { return __fdividef(v, 1.f + __expf(-1.702f * v)); }
 
 // Epilogue math for CNT (multiple of 8) consecutive columns starting at n0 of one valid row: everything except the
-// residual add and the store.  sc/bi point at scale/bias for column n0 (16-byte aligned; shared memory in the tcgen05
-// kernel, global in the CUDA-core kernel), or nullptr.  All mode tests are hoisted out of the per-element loops.
+// residual add and the store.  sc/bi point at scale/bias for column n0 (global memory, 16-byte aligned; every lane of a
+// warp reads the same addresses, so the loads are L1 broadcasts), or nullptr.  All mode tests are hoisted out of the per-element loops.
 template <int CNT>
 __device__ __forceinline__ void epilogue_math(const CrogGemm& g, const RowMap& m, int n0, float (&acc)[CNT], const float* sc,
                                               const float* bi) {
@@ -138,17 +138,27 @@ __device__ __forceinline__ void epilogue_math(const CrogGemm& g, const RowMap& m
     }
   }
   if (sc) {
+    if (nvalid == CNT) {
 #pragma unroll
-    for (int j = 0; j < CNT; j += 4) {
-      const float4 s4 = *reinterpret_cast<const float4*>(sc + j);
-      acc[j] *= s4.x; acc[j + 1] *= s4.y; acc[j + 2] *= s4.z; acc[j + 3] *= s4.w;
+      for (int j = 0; j < CNT; j += 4) {
+        const float4 s4 = __ldg(reinterpret_cast<const float4*>(sc + j));
+        acc[j] *= s4.x; acc[j + 1] *= s4.y; acc[j + 2] *= s4.z; acc[j + 3] *= s4.w;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < CNT; ++j) if (j < nvalid) acc[j] *= __ldg(sc + j);
     }
   }
   if (bi) {
+    if (nvalid == CNT) {
 #pragma unroll
-    for (int j = 0; j < CNT; j += 4) {
-      const float4 b4 = *reinterpret_cast<const float4*>(bi + j);
-      acc[j] += b4.x; acc[j + 1] += b4.y; acc[j + 2] += b4.z; acc[j + 3] += b4.w;
+      for (int j = 0; j < CNT; j += 4) {
+        const float4 b4 = __ldg(reinterpret_cast<const float4*>(bi + j));
+        acc[j] += b4.x; acc[j + 1] += b4.y; acc[j + 2] += b4.z; acc[j + 3] += b4.w;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < CNT; ++j) if (j < nvalid) acc[j] += __ldg(bi + j);
     }
   }
   if (g.act == CROG_ACT_RELU) {

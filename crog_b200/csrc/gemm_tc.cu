@@ -5,14 +5,22 @@
 //   warp 0      TMA producer   (cp.async.bulk.tensor 2D, SWIZZLE_128B, mbarrier complete_tx) over a STAGES-deep ring
 //   warp 1      MMA issuer     (tcgen05.mma cta_group::1 kind::f16, M=128, N=BN, K=16) into one of two TMEM
 //                              accumulator buffers, so tile i+1 is being multiplied while tile i drains
-//   warps 2..9  epilogue       each warp owns 32 accumulator rows (its TMEM lane quarter) x half of the columns:
-//                phase 1  tcgen05.ld -> registers (thread = row) -> +addmat, scale/bias, act, gate -> fp32 staging in smem
-//                         (after which the accumulator buffer is handed back to the MMA warp)
-//                phase 2  staging -> (+residual) -> HBM with 16-byte accesses that are contiguous along a row, eight
-//                         lanes per 128-byte row segment, all loads of a pass issued before use
+//   warps 2..9  epilogue       two independent groups of four warps; group g drains accumulator buffer g (tiles
+//                              i = g, g+2, ...), so two tiles are in flight in the epilogue and no barrier ever
+//                              joins more than one warp.  A warp owns 32 accumulator rows (its TMEM lane quarter)
+//                              and walks the tile's columns in 128-byte chunks:
+//     TMA epilogue   (output rows == enumerated rows: every token matrix, compact->compact and padded->padded
+//                    convolutions)  tcgen05.ld -> registers (thread = row) -> +addmat, scale/bias, act, gate ->
+//                    (+ residual chunk that a TMA load prefetched into the staging buffer NBUF-1 chunks ahead) ->
+//                    packed into the SWIZZLE_128B staging tile -> one cp.async.bulk.tensor store per chunk.
+//                    Halo rows of a padded output are written as zeros, which is what they must hold.
+//     legacy epilogue (compact<->padded row remapping, per-sample weights, N <= 16)  fp32 staging, then
+//                    row-contiguous 16-byte stores with the output row looked up per staged row.
 // The K loop runs over (tap, 64-channel chunk); for a 3x3 convolution on the zero-haloed ("padded") NHWC layout
 // tap t is the same activation matrix shifted by a constant number of rows, so the A tile of every k-step is one plain
 // 2D TMA box at row (row0 + shift_t); rows outside the tensor are zero-filled by TMA.
+#include <stdlib.h>
+
 #include "tc_common.cuh"
 
 namespace {
@@ -22,49 +30,55 @@ constexpr int BK = 64;  // bf16 elements = 128 bytes = one SWIZZLE_128B atom row
 constexpr int UMMA_K = 16;
 constexpr int EPI_WARPS = 8;
 constexpr int NUM_THREADS = 64 + EPI_WARPS * 32;
+constexpr int STG_BUF = 4096;  // one staging tile: 32 rows x 128 bytes
+enum { MODE_LEGACY = 0, MODE_TMA_BF16 = 1, MODE_TMA_F32 = 2 };
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, int NBUF>
 struct Cfg {
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + ((B_BYTES + 1023) / 1024) * 1024;
-  static constexpr int HALF = BN >= 32 ? BN / 2 : BN;        // columns per epilogue warp
-  static constexpr int SUB = HALF > 32 ? 32 : HALF;           // columns staged at a time
-  static constexpr int PITCH = SUB * 4 + 16;                  // staging row pitch (bytes): 16B-phase conflict free
-  static constexpr int STG_BYTES = 32 * PITCH;                // per warp
+  static constexpr int SUB = BN > 32 ? 32 : BN;               // legacy: columns staged at a time
+  static constexpr int PITCH = SUB * 4 + 16;                  // legacy staging row pitch (bytes): 16B-phase conflict free
+  static constexpr int STG_WARP = NBUF * STG_BUF;             // per epilogue warp (>= 32 * PITCH = 4608)
   static constexpr int STG_OFF = STAGES * STAGE_BYTES;
-  static constexpr int SB_OFF = STG_OFF + EPI_WARPS * STG_BYTES;  // scale/bias: [2 acc stages][2][BN] floats
-  static constexpr int BAR_OFF = SB_OFF + 2 * 2 * BN * 4;
-  static constexpr int TOTAL = BAR_OFF + 256 + 1024;          // + alignment slack
+  static constexpr int BAR_OFF = STG_OFF + EPI_WARPS * STG_WARP;
+  static constexpr int NBARS = 2 * STAGES + 4 + EPI_WARPS * NBUF;  // full[S], empty[S], tfull[2], tempty[2], res[8][NBUF]
+  static constexpr int TOTAL = BAR_OFF + NBARS * 8 + 16 + 1024;   // + tmem slot + alignment slack
   static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
+  static_assert(NBUF >= 2 && STG_WARP >= 32 * PITCH, "staging too small");
 };
 
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory"); }
-
-template <int BN, int STAGES>
+template <int BN, int STAGES, int NBUF, int MODE>
 __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                    const __grid_constant__ CUtensorMap tmB,
+                                                                   const __grid_constant__ CUtensorMap tmOut,
+                                                                   const __grid_constant__ CUtensorMap tmRes,
                                                                    const CrogGemm g, int n_tiles, int total_tiles) {
-  using L = Cfg<BN, STAGES>;
+  using L = Cfg<BN, STAGES, NBUF>;
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment for SWIZZLE_128B tiles; plain pointer arithmetic keeps the shared address space so the
-  // epilogue's staging / scale / bias accesses compile to LDS / STS instead of generic loads
+  // epilogue's staging accesses compile to LDS / STS instead of generic loads
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::BAR_OFF);  // full[S], empty[S], tfull[2], tempty[2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L::BAR_OFF + (2 * STAGES + 4) * 8);
-  float* s_sb = reinterpret_cast<float*>(smem + L::SB_OFF);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::BAR_OFF);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L::BAR_OFF + L::NBARS * 8);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int kchunks = g.cin / BK;
   const int num_kb = g.taps * kchunks;
   const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + STAGES), tfull0 = smem_u32(bars + 2 * STAGES),
-                 tempty0 = smem_u32(bars + 2 * STAGES + 2);
+                 tempty0 = smem_u32(bars + 2 * STAGES + 2), res0 = smem_u32(bars + 2 * STAGES + 4);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    if (MODE != MODE_LEGACY) {
+      tma_prefetch_desc(&tmOut);
+      if (g.residual) tma_prefetch_desc(&tmRes);
+    }
     for (int s = 0; s < STAGES; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(tfull0 + 8 * s, 1); mbar_init(tempty0 + 8 * s, EPI_WARPS * 32); }
+    for (int s = 0; s < 2; ++s) { mbar_init(tfull0 + 8 * s, 1); mbar_init(tempty0 + 8 * s, 4 * 32); }
+    for (int s = 0; s < EPI_WARPS * NBUF; ++s) mbar_init(res0 + 8 * s, 1);
     fence_barrier_init();
   }
   if (warp == 1) tc_alloc(smem_u32(tmem_slot), L::TMEM_COLS);
@@ -97,7 +111,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
       int kbg = 0, i = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++i) {
         const int as = i & 1;
-        mbar_wait(tempty0 + 8 * as, ((i >> 1) & 1) ^ 1);  // epilogue has drained this accumulator buffer
+        mbar_wait(tempty0 + 8 * as, ((i >> 1) & 1) ^ 1);  // epilogue group `as` has drained this accumulator buffer
         tc_fence_after();
         const uint32_t tacc = tmem_base + as * BN;
         for (int kb = 0; kb < num_kb; ++kb, ++kbg) {
@@ -116,93 +130,183 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
     }
   } else {
     const int ew = warp - 2;                 // 0..7
+    const int grp = ew >> 2;                 // accumulator buffer (= tile parity) this warp's group drains
     const int q = warp & 3;                  // TMEM lane quarter this warp may read
-    const int hsel = ew >> 2;                // which half of the tile's columns
-    const bool active = (BN >= 32) || hsel == 0;
-    uint8_t* stg = smem + L::STG_OFF + ew * L::STG_BYTES;
-    const int et = threadIdx.x - 64;         // 0..255
-    constexpr int UPR = L::SUB / 8;          // 16-byte (8-column) units per staged row
-    constexpr int RPP = 32 / UPR;            // rows written per warp pass
-    constexpr int PASSES = 32 / RPP;
-    int i = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++i) {
-      const int as = i & 1;
-      const int n_t = tile % n_tiles, m_t = tile / n_tiles;
-      const TileRows tr = tile_rows(g, m_t, BM);
-      const int n0 = n_t * BN;
-      float* sc = s_sb + as * 2 * BN;
-      float* bi = sc + BN;
-      for (int c = et; c < BN; c += EPI_WARPS * 32) {
-        const int n = n0 + c;
-        sc[c] = (g.scale && n < g.N) ? g.scale[n] : 1.f;
-        bi[c] = (g.bias && n < g.N) ? g.bias[n] : 0.f;
-      }
-      epi_bar_sync();
-      const RowMap m = map_row(g, tr.row0 + q * 32 + lane, tr.row_end);
-      const int my_orow = m.valid ? m.orow : -1;
-      // phase-2 ownership: lane -> (row p*RPP + rsub, 8-column unit u) of every staged sub-block
-      const int u = lane % UPR, rsub = lane / UPR;
-      int orow[PASSES];
+    uint8_t* stg = smem + L::STG_OFF + ew * L::STG_WARP;
+    const uint32_t tfull = tfull0 + 8 * grp, tempty = tempty0 + 8 * grp;
+
+    if constexpr (MODE != MODE_LEGACY) {
+      // ------------------------------------------------------------ TMA epilogue (identity row mapping)
+      constexpr int CW = MODE == MODE_TMA_BF16 ? 64 : 32;  // columns per 128-byte chunk
+      constexpr int NCH = BN / CW;
+      static_assert(BN % CW == 0, "tile must hold whole chunks");
+      const bool has_res = g.residual != nullptr;
+      const uint32_t stg_u32 = smem_u32(stg), rbar0 = res0 + 8 * (ew * NBUF);
+      const int sw = lane & 7;
+      uint32_t nld = 0, ncs = 0;   // residual chunks requested / chunks consumed (warp-uniform)
+      int pf_i = grp, pf_c = 0;    // prefetch cursor: tile ordinal, chunk in tile
+      auto issue_prefetch = [&]() {
+        const int tile = blockIdx.x + pf_i * (int)gridDim.x;
+        if (tile >= total_tiles) return;
+        const int n0 = (tile % n_tiles) * BN, row = (tile / n_tiles) * BM + q * 32;
+        if (lane == 0) {
+          const uint32_t b = nld % NBUF;
+          mbar_expect_tx(rbar0 + 8 * b, STG_BUF);
+          tma_load_2d(stg_u32 + b * STG_BUF, &tmRes, n0 + pf_c * CW, row, rbar0 + 8 * b);
+        }
+        ++nld;
+        if (++pf_c == NCH || n0 + pf_c * CW >= g.N) { pf_c = 0; pf_i += 2; }
+      };
+      if (has_res)
+        for (int j = 0; j < NBUF - 1; ++j) issue_prefetch();
+      for (int i = grp;; i += 2) {
+        const int tile = blockIdx.x + i * (int)gridDim.x;
+        if (tile >= total_tiles) break;
+        const int n0 = (tile % n_tiles) * BN, row0 = (tile / n_tiles) * BM;
+        const RowMap m = map_row(g, (long long)row0 + q * 32 + lane, g.M);
+        const int nvc = min(NCH, (g.N - n0 + CW - 1) / CW);  // chunks with at least one real column
+        mbar_wait(tfull, (i >> 1) & 1);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + grp * BN;
+        for (int c = 0; c < nvc; ++c) {
+          float acc[CW];
 #pragma unroll
-      for (int p = 0; p < PASSES; ++p) orow[p] = __shfl_sync(0xffffffffu, my_orow, p * RPP + rsub);
-      // bf16 residual tiles are fetched before the accumulator is even ready, so their HBM latency hides behind the
-      // MMA of this tile and the drain of the previous one
-      constexpr bool PREFETCH = (BN <= 128);
-      constexpr int NSUB = L::HALF / L::SUB;
-      uint4 rpre[PREFETCH ? NSUB * PASSES : 1];
-      const bool res_bf16 = g.residual != nullptr && g.out_dtype == CROG_BF16;
-      if constexpr (PREFETCH) {
-        if (res_bf16 && active) {
+          for (int h = 0; h < CW / 32; ++h) {
+            uint32_t r[32];
+            tc_ld32(taddr + c * CW + h * 32, r);
+            tc_wait_ld();
 #pragma unroll
-          for (int sb = 0; sb < NSUB; ++sb) {
-            const int ncol = n0 + hsel * L::HALF + sb * L::SUB + u * 8;
+            for (int j = 0; j < 32; ++j) acc[h * 32 + j] = __uint_as_float(r[j]);
+          }
+          if (c == nvc - 1) {  // last read of this accumulator buffer: hand it back to the MMA warp
+            tc_fence_before();
+            mbar_arrive(tempty);
+          }
+          const int ncol = n0 + c * CW;
+          if (m.valid) {
 #pragma unroll
-            for (int p = 0; p < PASSES; ++p)
-              rpre[sb * PASSES + p] = (ncol < g.N && orow[p] >= 0)
-                  ? __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(g.residual) + (long long)orow[p] * g.res_ld + ncol))
-                  : make_uint4(0, 0, 0, 0);
+            for (int h = 0; h < CW / 32; ++h) {
+              if (ncol + h * 32 < g.N) {
+                float(&a32)[32] = *reinterpret_cast<float(*)[32]>(&acc[h * 32]);
+                epilogue_math<32>(g, m, ncol + h * 32, a32, g.scale ? g.scale + ncol + h * 32 : nullptr,
+                                  g.bias ? g.bias + ncol + h * 32 : nullptr);
+              }
+            }
+          }
+          const uint32_t b = ncs % NBUF;
+          uint8_t* srow = stg + b * STG_BUF + lane * 128;
+          if (has_res) {
+            mbar_wait(rbar0 + 8 * b, (ncs / NBUF) & 1);
+            if constexpr (MODE == MODE_TMA_BF16) {
+#pragma unroll
+              for (int u = 0; u < 8; ++u) {
+                const uint4 rr = *reinterpret_cast<const uint4*>(srow + ((u ^ sw) << 4));
+                const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&rr);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const float2 f = __bfloat1622float2(h2[j]);
+                  acc[u * 8 + 2 * j] += f.x; acc[u * 8 + 2 * j + 1] += f.y;
+                }
+              }
+            } else {
+#pragma unroll
+              for (int u = 0; u < 8; ++u) {
+                const float4 f = *reinterpret_cast<const float4*>(srow + ((u ^ sw) << 4));
+                acc[u * 4] += f.x; acc[u * 4 + 1] += f.y; acc[u * 4 + 2] += f.z; acc[u * 4 + 3] += f.w;
+              }
+            }
+            if (g.residual_relu) {
+#pragma unroll
+              for (int j = 0; j < CW; ++j) acc[j] = fmaxf(acc[j], 0.f);
+            }
+          } else {
+            // the store that last read this staging buffer (NBUF chunks ago) must have drained it
+            if (lane == 0) bulk_wait_read<NBUF - 1>();
+            __syncwarp();
+          }
+          if (!m.valid) {  // halo rows of a padded tensor hold zeros; rows >= M are clipped by the store
+#pragma unroll
+            for (int j = 0; j < CW; ++j) acc[j] = 0.f;
+          }
+          if constexpr (MODE == MODE_TMA_BF16) {
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+              uint4 pk;
+              __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&pk);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) h2[j] = __floats2bfloat162_rn(acc[u * 8 + 2 * j], acc[u * 8 + 2 * j + 1]);
+              *reinterpret_cast<uint4*>(srow + ((u ^ sw) << 4)) = pk;
+            }
+          } else {
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+              *reinterpret_cast<float4*>(srow + ((u ^ sw) << 4)) = make_float4(acc[u * 4], acc[u * 4 + 1], acc[u * 4 + 2], acc[u * 4 + 3]);
+          }
+          fence_proxy_async_smem();  // generic-proxy writes -> visible to the TMA engine (async proxy)
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(&tmOut, stg_u32 + b * STG_BUF, ncol, row0 + q * 32);
+            bulk_commit();
+          }
+          ++ncs;
+          if (has_res) {
+            // the next prefetch lands in the buffer of chunk ncs-2 (the previous one): its store must have drained it
+            if (lane == 0) bulk_wait_read<1>();
+            issue_prefetch();
           }
         }
       }
-      mbar_wait(tfull0 + 8 * as, (i >> 1) & 1);
-      tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * BN + hsel * L::HALF;
+      if (lane == 0) bulk_wait_all();
+    } else {
+      // ------------------------------------------------------------ legacy epilogue (row remapping)
+      constexpr int SUB = L::SUB;
+      constexpr int NSUB = BN / SUB;
+      constexpr int UPR = SUB / 8;             // 16-byte (8-column) units per staged row
+      constexpr int RPP = 32 / UPR;            // rows written per warp pass
+      constexpr int PASSES = 32 / RPP;
+      const int u = lane % UPR, rsub = lane / UPR;
+      for (int i = grp;; i += 2) {
+        const int tile = blockIdx.x + i * (int)gridDim.x;
+        if (tile >= total_tiles) break;
+        const int n_t = tile % n_tiles, m_t = tile / n_tiles;
+        const TileRows tr = tile_rows(g, m_t, BM);
+        const int n0 = n_t * BN;
+        const RowMap m = map_row(g, tr.row0 + q * 32 + lane, tr.row_end);
+        const int my_orow = m.valid ? m.orow : -1;
+        int orow[PASSES];
 #pragma unroll
-      for (int sbi = 0; sbi < NSUB; ++sbi) {
-        const int sub = sbi * L::SUB;
-        const int cbase = hsel * L::HALF + sub;  // column of the tile where this staged block starts
-        if (active) {
+        for (int p = 0; p < PASSES; ++p) orow[p] = __shfl_sync(0xffffffffu, my_orow, p * RPP + rsub);
+        const int nvs = min(NSUB, (g.N - n0 + SUB - 1) / SUB);
+        mbar_wait(tfull, (i >> 1) & 1);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + grp * BN;
+        for (int sbi = 0; sbi < nvs; ++sbi) {
+          const int cbase = sbi * SUB;
           // ---- phase 1: accumulator -> registers -> epilogue math -> fp32 staging (thread = row)
-          if constexpr (L::SUB >= 32) {
+          float acc[SUB];
+          if constexpr (SUB == 32) {
             uint32_t r[32];
-            tc_ld32(taddr + sub, r);
+            tc_ld32(taddr + cbase, r);
             tc_wait_ld();
-            float acc[32];
 #pragma unroll
             for (int j = 0; j < 32; ++j) acc[j] = __uint_as_float(r[j]);
-            if (m.valid && n0 + cbase < g.N) epilogue_math<32>(g, m, n0 + cbase, acc, sc + cbase, bi + cbase);
-            float4* dst = reinterpret_cast<float4*>(stg + lane * L::PITCH);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) dst[j] = make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
           } else {
             uint32_t r[16];
-            tc_ld16(taddr + sub, r);
+            tc_ld16(taddr + cbase, r);
             tc_wait_ld();
-            float acc[16];
 #pragma unroll
             for (int j = 0; j < 16; ++j) acc[j] = __uint_as_float(r[j]);
-            if (m.valid) epilogue_math<16>(g, m, n0 + cbase, acc, sc + cbase, bi + cbase);
-            float4* dst = reinterpret_cast<float4*>(stg + lane * L::PITCH);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) dst[j] = make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
           }
-        }
-        if (sbi == NSUB - 1) {  // last read of this accumulator buffer: hand it back to the MMA warp
-          tc_fence_before();
-          mbar_arrive(tempty0 + 8 * as);
-        }
-        __syncwarp();
-        if (active) {
+          if (sbi == nvs - 1) {
+            tc_fence_before();
+            mbar_arrive(tempty);
+          }
+          if (m.valid)
+            epilogue_math<SUB>(g, m, n0 + cbase, acc, g.scale ? g.scale + n0 + cbase : nullptr, g.bias ? g.bias + n0 + cbase : nullptr);
+          float4* dst = reinterpret_cast<float4*>(stg + lane * L::PITCH);
+#pragma unroll
+          for (int j = 0; j < SUB / 4; ++j) dst[j] = make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
+          __syncwarp();
           // ---- phase 2: staging -> (+residual) -> global, row-contiguous 16-byte accesses
           const int ncol = n0 + cbase + u * 8;
           const bool colok = ncol < g.N;
@@ -217,13 +321,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
             if (g.out_dtype == CROG_BF16) {
               uint4 rr[PASSES];
 #pragma unroll
-              for (int p = 0; p < PASSES; ++p) {
-                if constexpr (PREFETCH) rr[p] = rpre[sbi * PASSES + p];
-                else
-                  rr[p] = (colok && orow[p] >= 0)
-                              ? __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(g.residual) + (long long)orow[p] * g.res_ld + ncol))
-                              : make_uint4(0, 0, 0, 0);
-              }
+              for (int p = 0; p < PASSES; ++p)
+                rr[p] = (colok && orow[p] >= 0)
+                            ? __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(g.residual) + (long long)orow[p] * g.res_ld + ncol))
+                            : make_uint4(0, 0, 0, 0);
 #pragma unroll
               for (int p = 0; p < PASSES; ++p) {
                 const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&rr[p]);
@@ -263,8 +364,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
             if (g.out_dtype == CROG_BF16) store8(reinterpret_cast<bf16*>(g.out) + (long long)orow[p] * g.out_ld + ncol, v[p]);
             else store8(reinterpret_cast<float*>(g.out) + (long long)orow[p] * g.out_ld + ncol, v[p]);
           }
+          __syncwarp();  // staging is reused by the next sub-block / tile
         }
-        __syncwarp();  // staging is reused by the next sub-block / tile
       }
     }
   }
@@ -279,34 +380,54 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
 // ---------------------------------------------------------------- host side
 int g_num_sms = 0;
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, int NBUF, int MODE>
 int launch(const CrogGemm* g, cudaStream_t stream) {
-  using L = Cfg<BN, STAGES>;
+  using L = Cfg<BN, STAGES, NBUF>;
   static_assert(L::TOTAL <= 227 * 1024, "shared memory budget");
   static bool attr_set = false;  // per-process; device attribute is re-set cheaply if another device is used
   static int attr_dev = -1;
   int dev = 0;
   CROG_CUDA_OK(cudaGetDevice(&dev));
   if (!attr_set || attr_dev != dev) {
-    CROG_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+    CROG_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES, NBUF, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
     CROG_CUDA_OK(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
     attr_set = true; attr_dev = dev;
   }
-  CUtensorMap tmA, tmB;
+  CUtensorMap tmA, tmB, tmOut, tmRes;
   const long long Ktot = (long long)g->taps * g->cin;
-  int rc = crog_encode_2d_bf16(&tmA, g->a, (uint64_t)g->cin, (uint64_t)g->a_rows, (uint64_t)g->a_ld, BM);
+  int rc = crog_encode_2d(&tmA, g->a, CROG_BF16, (uint64_t)g->cin, (uint64_t)g->a_rows, (uint64_t)g->a_ld, BM);
   if (rc) return rc;
   uint64_t wrows = (uint64_t)g->N;
   if (g->w_sample_stride > 0) wrows = (uint64_t)(g->w_sample_stride / Ktot) * (uint64_t)(g->M / g->sample_rows);
-  rc = crog_encode_2d_bf16(&tmB, g->w, (uint64_t)Ktot, wrows, (uint64_t)Ktot, BN);
+  rc = crog_encode_2d(&tmB, g->w, CROG_BF16, (uint64_t)Ktot, wrows, (uint64_t)Ktot, BN);
   if (rc) return rc;
+  if (MODE != MODE_LEGACY) {
+    rc = crog_encode_2d(&tmOut, g->out, g->out_dtype, (uint64_t)g->N, (uint64_t)g->M, (uint64_t)g->out_ld, 32);
+    if (rc) return rc;
+    tmRes = tmOut;
+    if (g->residual) {
+      rc = crog_encode_2d(&tmRes, g->residual, g->out_dtype, (uint64_t)g->N, (uint64_t)g->M, (uint64_t)g->res_ld, 32);
+      if (rc) return rc;
+    }
+  } else {
+    tmOut = tmA; tmRes = tmA;  // unused
+  }
   const int n_tiles = (g->N + BN - 1) / BN;
   const int total = num_m_tiles(*g, BM) * n_tiles;
   if (total == 0) return CROG_OK;
   const int grid = total < g_num_sms ? total : g_num_sms;
-  gemm_tc_kernel<BN, STAGES><<<grid, NUM_THREADS, L::TOTAL, stream>>>(tmA, tmB, *g, n_tiles, total);
+  gemm_tc_kernel<BN, STAGES, NBUF, MODE><<<grid, NUM_THREADS, L::TOTAL, stream>>>(tmA, tmB, tmOut, tmRes, *g, n_tiles, total);
   CROG_LAUNCH_OK("gemm_tc");
   return CROG_OK;
+}
+
+template <int MODE>
+int dispatch(const CrogGemm* g, cudaStream_t stream) {
+  if (g->N <= 64) return launch<64, 5, 3, MODE>(g, stream);
+  // 128 x 256 tiles cut the L2 -> smem operand traffic per FLOP by 25 % ((BM+BN)/(BM*BN)); worth it when the
+  // contraction is long enough to be tensor/L2 bound rather than epilogue bound
+  if (g->N % 256 == 0 && (long long)g->taps * g->cin >= 1024) return launch<256, 3, 2, MODE>(g, stream);
+  return launch<128, 4, 3, MODE>(g, stream);
 }
 
 }  // namespace
@@ -321,15 +442,17 @@ int crog_gemm_tc(const CrogGemm* g, cudaStream_t stream) {
   if (g->w_sample_stride > 0)
     CROG_REQUIRE(g->w_sample_stride % ((long long)g->taps * g->cin) == 0 && g->sample_rows > 0, CROG_E_BADSHAPE,
                  "gemm_tc: per-sample weights need whole rows");
-  if (g->N <= 16) return launch<16, 8>(g, stream);
-  if (g->N <= 64) return launch<64, 6>(g, stream);
-  // 128 x 256 tiles cut the L2 -> smem operand traffic per FLOP by 25 % ((BM+BN)/(BM*BN)); worth it when the
-  // contraction is long enough to be tensor/L2 bound rather than epilogue bound
-  if (g->N % 256 == 0 && (long long)g->taps * g->cin >= 1024) return launch<256, 3>(g, stream);
-  return launch<128, 5>(g, stream);
+  // TMA epilogue: output row == enumerated row (so the tile is one box of the output matrix), shared weights
+  const bool identity = (g->H == 0) || (g->in_padded == g->out_padded);
+  const int esz = g->out_dtype == CROG_BF16 ? 2 : 4;
+  const bool tma_ok = identity && g->w_sample_stride == 0 && g->N > 16 && ((long long)g->out_ld * esz) % 16 == 0 &&
+                      (!g->residual || ((long long)g->res_ld * esz) % 16 == 0) && !getenv("CROG_GEMM_LEGACY_EPILOGUE");
+  if (tma_ok) return g->out_dtype == CROG_BF16 ? dispatch<MODE_TMA_BF16>(g, stream) : dispatch<MODE_TMA_F32>(g, stream);
+  if (g->N <= 16) return launch<16, 8, 2, MODE_LEGACY>(g, stream);
+  return dispatch<MODE_LEGACY>(g, stream);
 }
 
-int crog_encode_2d_bf16(CUtensorMap* tm, const void* base, uint64_t cols, uint64_t rows, uint64_t ld_elems, uint32_t box_rows) {
+int crog_encode_2d(CUtensorMap* tm, const void* base, int dtype, uint64_t cols, uint64_t rows, uint64_t ld_elems, uint32_t box_rows) {
   static CrogEncodeTiledFn enc = nullptr;
   if (!enc) {
     void* p = nullptr;
@@ -339,12 +462,13 @@ int crog_encode_2d_bf16(CUtensorMap* tm, const void* base, uint64_t cols, uint64
       enc = reinterpret_cast<CrogEncodeTiledFn>(p);
   }
   CROG_REQUIRE(enc != nullptr, CROG_E_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  const bool f32 = dtype == CROG_F32;
   cuuint64_t dims[2] = {cols, rows};
-  cuuint64_t strides[1] = {ld_elems * 2};
-  cuuint32_t box[2] = {64u, box_rows};
+  cuuint64_t strides[1] = {ld_elems * (f32 ? 4u : 2u)};
+  cuuint32_t box[2] = {f32 ? 32u : 64u, box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+  CUresult r = enc(tm, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims,
+                   strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   CROG_REQUIRE(r == CUDA_SUCCESS, CROG_E_CUDA, "cuTensorMapEncodeTiled failed (%d): cols=%llu rows=%llu ld=%llu", (int)r,
                (unsigned long long)cols, (unsigned long long)rows, (unsigned long long)ld_elems);

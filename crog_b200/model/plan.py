@@ -275,12 +275,16 @@ class ForwardPlan:
         self.keep.update(c3=c3, c4=c4, c5=c5)
         t_begin = len(self.ops)
         wordfeat, state32, state_a = self._text()
+        # everything that only depends on the sentence state rides on the text branch too: the FPN text gate
+        # (layers.py:376) and the projector's text-generated kernel folded with vis.4 (layers.py:91-93)
+        self._text_gate(state_a)
+        self._dynamic_weights(state32)
         self.text_range = (t_begin, len(self.ops))  # independent of the image tower: may run on a forked stream
-        fq = self._neck(c3, c4, c5, state_a)
+        fq = self._neck(c3, c4, c5)
         if cfg.use_contrastive:
             fq = self._decoder(fq, wordfeat)
             self.keep["fq_dec"] = fq
-        self._projector(fq, state32)
+        self._projector(fq)
 
     def _bottleneck(self, p: str, x: Act, inpl: int, planes: int, stride: int) -> Act:
         sd, RELU = self.sd, L.ACT_RELU
@@ -392,14 +396,20 @@ class ForwardPlan:
         self.gemm(name, a, self.wt(_conv_w(wsrc)), wsrc.shape[0], out, taps=taps, scale=self.f32(sc), bias=self.f32(bi),
                   act=L.ACT_RELU, **kw)
 
-    def _neck(self, c3: Act, c4: Act, c5: Act, state_a: Act) -> Act:
+    def _text_gate(self, state_a: Act):
+        """layers.py:376: state' = ReLU(BN1d(W . state)), the per-(sample, channel) gate of the FPN."""
+        sd = self.sd
+        fo = list(self.cfg.fpn_out)
+        sc, bi = _bn_fold(sd, "neck.txt_proj.1")
+        self.gate = self.new(0, 0, fo[2], dtype=torch.float32, rows=self.B)
+        self.gemm("neck.txt_proj", state_a, self.wt(sd["neck.txt_proj.0.weight"]), fo[2], self.gate, scale=self.f32(sc),
+                  bias=self.f32(bi), act=L.ACT_RELU)
+
+    def _neck(self, c3: Act, c4: Act, c5: Act) -> Act:
         """layers.py:371-398."""
         sd, B = self.sd, self.B
         fo = list(self.cfg.fpn_out)
-        sc, bi = _bn_fold(sd, "neck.txt_proj.1")
-        gate = self.new(0, 0, fo[2], dtype=torch.float32, rows=B)
-        self.gemm("neck.txt_proj", state_a, self.wt(sd["neck.txt_proj.0.weight"]), fo[2], gate, scale=self.f32(sc),
-                  bias=self.f32(bi), act=L.ACT_RELU)
+        gate = self.gate
         s2, b2 = _bn_fold(sd, "neck.norm_layer.0")
         f5 = self.new(c5.H, c5.W, fo[2], padded=True)
         self._cbr("neck.f1_v_proj", "neck.f1_v_proj", c5, f5, 1, gate=gate.t, scale2=self.f32(s2), bias2=self.f32(b2))
@@ -492,13 +502,29 @@ class ForwardPlan:
         self.layernorm("decoder.norm", vis, "decoder.norm", out)
         return out
 
-    def _projector(self, fq: Act, state32: Act):
-        """layers.py:64-132 (MultiTaskProjector) / :152-173 (Projector).  vis.4 (1x1, 256->256*NH) is folded
-        into the text-generated 3x3 kernel, so the heads are one per-sample 3x3 convolution."""
+    def _dynamic_weights(self, state32: Act):
+        """layers.py:91-93 folded with vis.4 (layers.py:58,70-77): per-sample [ZR, CP] kernel of the head convolution."""
         sd, B, lib = self.sd, self.B, self.lib
         Cc = sd["proj.vis.3.0.weight"].shape[0]
         NH = sd["proj.vis.4.weight"].shape[0] // Cc
         ZR, CP = ((9 * NH + 15) // 16) * 16, Cc + 64  # Z columns (9 taps x NH heads, padded), feature channels + ones chunk
+        wfold = torch.zeros((B * ZR, CP), device=self.dev, dtype=self.adt)
+        scratch = torch.zeros((B, 9 * Cc + 1), device=self.dev, dtype=torch.float32)
+        tw, tb = self.f32(sd["proj.txt.weight"]), self.f32(sd["proj.txt.bias"])
+        vw = self.f32(sd["proj.vis.4.weight"].reshape(NH * Cc, Cc))
+        vb = self.f32(sd["proj.vis.4.bias"])
+        a = (state32.ptr, L.F32, tw.data_ptr(), tb.data_ptr(), vw.data_ptr(), vb.data_ptr(), scratch.data_ptr(),
+             wfold.data_ptr(), self.acode, B, state32.C, Cc, NH, ZR, CP)
+        self._hold.extend([wfold, scratch])
+        self._add("proj.dynw_fold", lambda s: L.check(lib.crog_dynw_fold(*a, s)), launches=2)
+        self.wfold, self.NH, self._proj_dims = wfold, NH, (Cc, ZR, CP)
+
+    def _projector(self, fq: Act):
+        """layers.py:64-132 (MultiTaskProjector) / :152-173 (Projector).  vis.4 (1x1, 256->256*NH) is folded
+        into the text-generated 3x3 kernel, so the heads are one per-sample 3x3 convolution."""
+        sd, B, lib = self.sd, self.B, self.lib
+        NH, wfold = self.NH, self.wfold
+        Cc, ZR, CP = self._proj_dims
         H1, W1 = fq.H * 2, fq.W * 2
         u1 = self.new(H1, W1, fq.C, padded=True)
         self.resample("proj.up1", fq, u1, L.RS_BILINEAR2)
@@ -510,22 +536,12 @@ class ForwardPlan:
         feat = self.new(H2, W2, CP, padded=True)
         feat.t.view(B, H2 + 2, W2 + 2, CP)[:, 1:-1, 1:-1, Cc] = 1.0  # constant-one channel carrying the biases
         self._cbr("proj.vis.3", "proj.vis.3", u2, feat.cols(0, Cc), 9)
-        wfold = torch.zeros((B * ZR, CP), device=self.dev, dtype=self.adt)
-        scratch = torch.zeros((B, 9 * Cc + 1), device=self.dev, dtype=torch.float32)
-        tw, tb = self.f32(sd["proj.txt.weight"]), self.f32(sd["proj.txt.bias"])
-        vw = self.f32(sd["proj.vis.4.weight"].reshape(NH * Cc, Cc))
-        vb = self.f32(sd["proj.vis.4.bias"])
-        a = (state32.ptr, L.F32, tw.data_ptr(), tb.data_ptr(), vw.data_ptr(), vb.data_ptr(), scratch.data_ptr(),
-             wfold.data_ptr(), self.acode, B, state32.C, Cc, NH, ZR, CP)
-        self._hold.extend([wfold, scratch])
-        self._add("proj.dynw_fold", lambda s: L.check(lib.crog_dynw_fold(*a, s)), launches=2)
         # per-sample 1x1 GEMM: Z[p, h*9+tap] = feat[p, :] . wfold[b, h*9+tap, :]  (features are read once, not nine times)
         z = self.new(H2, W2, ZR, padded=True, dtype=torch.float32)
         self.gemm("proj.dynconv", feat, wfold, ZR, z, taps=1, w_sample_stride=ZR * CP, cin=CP, alg_n=9 * NH, alg_cin=Cc)
         self.out = torch.zeros((NH, B, 1, H2, W2), device=self.dev, dtype=torch.float32)
         a2 = (z.ptr, z.ld, self.out.data_ptr(), B, H2, W2, NH)
         self._add("proj.gather", lambda s: L.check(lib.crog_dynconv_gather(*a2, s)))
-        self.NH = NH
 
     # ------------------------------------------------------------------ execution
     def run(self, stream: Optional[int] = None, fork_text: bool = True):
