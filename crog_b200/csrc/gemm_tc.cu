@@ -33,29 +33,37 @@ constexpr int NUM_THREADS = 64 + EPI_WARPS * 32;
 constexpr int STG_BUF = 4096;  // one staging tile: 32 rows x 128 bytes
 enum { MODE_LEGACY = 0, MODE_TMA_BF16 = 1, MODE_TMA_F32 = 2 };
 
-template <int BN, int STAGES, int NBUF>
+// CONV3 (3x3 convolutions with one 64-channel chunk and N <= BN): the whole weight matrix (9 taps x BN x 64) stays
+// resident in shared memory, and a stage holds BM + 2 activation rows of one ky band, so the three kx taps are three
+// row-shifted views (descriptor start + kx * 128 B) of ONE TMA box: operand traffic from L2 drops from 9 x (A + B) to
+// 3 x A per tile.
+template <int BN, int STAGES, int NBUF, bool CONV3>
 struct Cfg {
-  static constexpr int A_BYTES = BM * BK * 2;
+  static constexpr int A_ROWS = CONV3 ? BM + 2 : BM;
+  static constexpr int A_TX = A_ROWS * BK * 2;                 // bytes one A box delivers
+  static constexpr int A_BYTES = ((A_TX + 1023) / 1024) * 1024;
   static constexpr int B_BYTES = BN * BK * 2;
-  static constexpr int STAGE_BYTES = A_BYTES + ((B_BYTES + 1023) / 1024) * 1024;
+  static constexpr int STAGE_BYTES = CONV3 ? A_BYTES : A_BYTES + ((B_BYTES + 1023) / 1024) * 1024;
+  static constexpr int BRES_BYTES = CONV3 ? 9 * B_BYTES : 0;   // resident weights
   static constexpr int SUB = BN > 32 ? 32 : BN;               // legacy: columns staged at a time
   static constexpr int PITCH = SUB * 4 + 16;                  // legacy staging row pitch (bytes): 16B-phase conflict free
   static constexpr int STG_WARP = NBUF * STG_BUF;             // per epilogue warp (>= 32 * PITCH = 4608)
-  static constexpr int STG_OFF = STAGES * STAGE_BYTES;
+  static constexpr int BRES_OFF = STAGES * STAGE_BYTES;
+  static constexpr int STG_OFF = BRES_OFF + BRES_BYTES;
   static constexpr int BAR_OFF = STG_OFF + EPI_WARPS * STG_WARP;
-  static constexpr int NBARS = 2 * STAGES + 4 + EPI_WARPS * NBUF;  // full[S], empty[S], tfull[2], tempty[2], res[8][NBUF]
+  static constexpr int NBARS = 2 * STAGES + 5 + EPI_WARPS * NBUF;  // full[S], empty[S], tfull[2], tempty[2], bres, res[8][NBUF]
   static constexpr int TOTAL = BAR_OFF + NBARS * 8 + 16 + 1024;   // + tmem slot + alignment slack
   static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
   static_assert(NBUF >= 2 && STG_WARP >= 32 * PITCH, "staging too small");
 };
 
-template <int BN, int STAGES, int NBUF, int MODE>
+template <int BN, int STAGES, int NBUF, int MODE, bool CONV3>
 __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                    const __grid_constant__ CUtensorMap tmB,
                                                                    const __grid_constant__ CUtensorMap tmOut,
                                                                    const __grid_constant__ CUtensorMap tmRes,
                                                                    const CrogGemm g, int n_tiles, int total_tiles) {
-  using L = Cfg<BN, STAGES, NBUF>;
+  using L = Cfg<BN, STAGES, NBUF, CONV3>;
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment for SWIZZLE_128B tiles; plain pointer arithmetic keeps the shared address space so the
   // epilogue's staging accesses compile to LDS / STS instead of generic loads
@@ -65,9 +73,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int kchunks = g.cin / BK;
-  const int num_kb = g.taps * kchunks;
+  const int num_kb = CONV3 ? 3 : g.taps * kchunks;  // CONV3: one k-block per ky band
   const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + STAGES), tfull0 = smem_u32(bars + 2 * STAGES),
-                 tempty0 = smem_u32(bars + 2 * STAGES + 2), res0 = smem_u32(bars + 2 * STAGES + 4);
+                 tempty0 = smem_u32(bars + 2 * STAGES + 2), bres = smem_u32(bars + 2 * STAGES + 4),
+                 res0 = smem_u32(bars + 2 * STAGES + 5);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -79,6 +88,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
     for (int s = 0; s < STAGES; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(tfull0 + 8 * s, 1); mbar_init(tempty0 + 8 * s, 4 * 32); }
     for (int s = 0; s < EPI_WARPS * NBUF; ++s) mbar_init(res0 + 8 * s, 1);
+    mbar_init(bres, 1);
     fence_barrier_init();
   }
   if (warp == 1) tc_alloc(smem_u32(tmem_slot), L::TMEM_COLS);
@@ -90,6 +100,19 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
   if (warp == 0) {
     if (lane == 0) {
       int kbg = 0;  // k-blocks issued so far (ring position)
+      if constexpr (CONV3) {
+        mbar_expect_tx(bres, L::BRES_BYTES);
+        for (int t = 0; t < 9; ++t) tma_load_2d(smem_u32(smem + L::BRES_OFF + t * L::B_BYTES), &tmB, t * BK, 0, bres);
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+          const long long row0 = (long long)tile * BM;  // n_tiles == 1
+          for (int ky = 0; ky < 3; ++ky, ++kbg) {
+            const int s = kbg % STAGES, it = kbg / STAGES;
+            mbar_wait(empty0 + 8 * s, (it & 1) ^ 1);
+            mbar_expect_tx(full0 + 8 * s, L::A_TX);
+            tma_load_2d(smem_u32(smem + s * L::STAGE_BYTES), &tmA, 0, (int)(row0 + (ky - 1) * (g.W + 2) - 1), full0 + 8 * s);
+          }
+        }
+      } else
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int n_t = tile % n_tiles, m_t = tile / n_tiles;
         const TileRows tr = tile_rows(g, m_t, BM);
@@ -109,11 +132,32 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc(BM, BN);
       int kbg = 0, i = 0;
+      if constexpr (CONV3) mbar_wait(bres, 0);
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++i) {
         const int as = i & 1;
         mbar_wait(tempty0 + 8 * as, ((i >> 1) & 1) ^ 1);  // epilogue group `as` has drained this accumulator buffer
         tc_fence_after();
         const uint32_t tacc = tmem_base + as * BN;
+        if constexpr (CONV3) {
+          for (int ky = 0; ky < 3; ++ky, ++kbg) {
+            const int s = kbg % STAGES, it = kbg / STAGES;
+            mbar_wait(full0 + 8 * s, it & 1);
+            tc_fence_after();
+            const uint32_t sa = smem_u32(smem + s * L::STAGE_BYTES);
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) {
+              // rows [kx, kx + 128) of the band: the SWIZZLE_128B XOR is a function of the absolute shared address
+              // (descriptor base_offset = 0), so a start address moved by whole 128-byte rows still reads the
+              // pattern TMA wrote (verified on B200: tests/test_gpu_kernels.py::test_conv3x3_padded)
+              const uint64_t da = make_sdesc(sa + kx * 128);
+              const uint64_t db = make_sdesc(smem_u32(smem + L::BRES_OFF + (ky * 3 + kx) * L::B_BYTES));
+#pragma unroll
+              for (int k = 0; k < BK / UMMA_K; ++k)
+                tc_mma_bf16(tacc, da + (uint64_t)(k * UMMA_K * 2 / 16), db + (uint64_t)(k * UMMA_K * 2 / 16), idesc, (ky | kx | k) != 0);
+            }
+            tc_commit(empty0 + 8 * s);
+          }
+        } else
         for (int kb = 0; kb < num_kb; ++kb, ++kbg) {
           const int s = kbg % STAGES, it = kbg / STAGES;
           mbar_wait(full0 + 8 * s, it & 1);
@@ -380,22 +424,22 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
 // ---------------------------------------------------------------- host side
 int g_num_sms = 0;
 
-template <int BN, int STAGES, int NBUF, int MODE>
+template <int BN, int STAGES, int NBUF, int MODE, bool CONV3 = false>
 int launch(const CrogGemm* g, cudaStream_t stream) {
-  using L = Cfg<BN, STAGES, NBUF>;
+  using L = Cfg<BN, STAGES, NBUF, CONV3>;
   static_assert(L::TOTAL <= 227 * 1024, "shared memory budget");
   static bool attr_set = false;  // per-process; device attribute is re-set cheaply if another device is used
   static int attr_dev = -1;
   int dev = 0;
   CROG_CUDA_OK(cudaGetDevice(&dev));
   if (!attr_set || attr_dev != dev) {
-    CROG_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES, NBUF, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+    CROG_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES, NBUF, MODE, CONV3>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
     CROG_CUDA_OK(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
     attr_set = true; attr_dev = dev;
   }
   CUtensorMap tmA, tmB, tmOut, tmRes;
   const long long Ktot = (long long)g->taps * g->cin;
-  int rc = crog_encode_2d(&tmA, g->a, CROG_BF16, (uint64_t)g->cin, (uint64_t)g->a_rows, (uint64_t)g->a_ld, BM);
+  int rc = crog_encode_2d(&tmA, g->a, CROG_BF16, (uint64_t)g->cin, (uint64_t)g->a_rows, (uint64_t)g->a_ld, L::A_ROWS);
   if (rc) return rc;
   uint64_t wrows = (uint64_t)g->N;
   if (g->w_sample_stride > 0) wrows = (uint64_t)(g->w_sample_stride / Ktot) * (uint64_t)(g->M / g->sample_rows);
@@ -416,13 +460,15 @@ int launch(const CrogGemm* g, cudaStream_t stream) {
   const int total = num_m_tiles(*g, BM) * n_tiles;
   if (total == 0) return CROG_OK;
   const int grid = total < g_num_sms ? total : g_num_sms;
-  gemm_tc_kernel<BN, STAGES, NBUF, MODE><<<grid, NUM_THREADS, L::TOTAL, stream>>>(tmA, tmB, tmOut, tmRes, *g, n_tiles, total);
+  gemm_tc_kernel<BN, STAGES, NBUF, MODE, CONV3><<<grid, NUM_THREADS, L::TOTAL, stream>>>(tmA, tmB, tmOut, tmRes, *g, n_tiles, total);
   CROG_LAUNCH_OK("gemm_tc");
   return CROG_OK;
 }
 
 template <int MODE>
 int dispatch(const CrogGemm* g, cudaStream_t stream) {
+  if (g->N <= 64 && g->taps == 9 && g->cin == BK && g->w_sample_stride == 0 && !getenv("CROG_GEMM_NO_CONV3"))
+    return launch<64, 5, 2, MODE, true>(g, stream);
   if (g->N <= 64) return launch<64, 5, 3, MODE>(g, stream);
   // 128 x 256 tiles cut the L2 -> smem operand traffic per FLOP by 25 % ((BM+BN)/(BM*BN)); worth it when the
   // contraction is long enough to be tensor/L2 bound rather than epilogue bound

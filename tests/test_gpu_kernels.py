@@ -45,7 +45,8 @@ def test_plain_gemm(name, dt, impl, tol, M, N, K):
 
 
 @pytest.mark.parametrize("name,dt,impl,tol", IMPLS)
-@pytest.mark.parametrize("B,H,W,Cin,Cout", [(2, 13, 13, 64, 64), (1, 26, 26, 128, 192), (3, 9, 20, 64, 128)])
+@pytest.mark.parametrize("B,H,W,Cin,Cout", [(2, 13, 13, 64, 64), (1, 26, 26, 128, 192), (3, 9, 20, 64, 128), (1, 5, 200, 64, 64),
+                                            (2, 30, 30, 64, 32)])
 def test_conv3x3_padded(name, dt, impl, tol, B, H, W, Cin, Cout):
     x, w = _rand(B, Cin, H, W, seed=4), _rand(Cout, Cin, 3, 3, seed=5, scale=(9 * Cin) ** -0.5)
     sc, bi = torch.rand(Cout, device=DEV) + 0.5, _rand(Cout, seed=6)
