@@ -13,9 +13,9 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 SO_PATH = os.path.join(_HERE, "lib", "libcrog_b200.so")
 
 F32, BF16 = 0, 1
-ACT_NONE, ACT_RELU, ACT_QUICKGELU = 0, 1, 2
+ACT_NONE, ACT_RELU, ACT_QUICKGELU, ACT_TANH = 0, 1, 2, 3
 IMPL_AUTO, IMPL_SIMT, IMPL_TCGEN05 = 0, 1, 2
-RS_COPY, RS_AVGPOOL2, RS_BILINEAR2 = 0, 1, 2
+RS_COPY, RS_AVGPOOL2, RS_BILINEAR2, RS_SUBSAMPLE2, RS_BILINEAR2_AC = 0, 1, 2, 3, 4
 
 
 class CrogError(RuntimeError):
@@ -31,6 +31,7 @@ class CrogGemm(C.Structure):
         ("addmat_rows", C.c_int32), ("act", C.c_int32), ("gate", C.c_void_p), ("scale2", C.c_void_p),
         ("bias2", C.c_void_p), ("residual", C.c_void_p), ("res_ld", C.c_int32), ("residual_relu", C.c_int32),
         ("out", C.c_void_p), ("out_ld", C.c_int32), ("out_dtype", C.c_int32), ("impl", C.c_int32),
+        ("out_sample_rows", C.c_int32),
     ]
 
 
@@ -56,6 +57,15 @@ SIGNATURES = {
     "crog_detect_grasps": (C.c_int, [_P, _P, _P, _P, _I, _I, _I, _I, _F, _P, _P, _P, _P, _P]),
     "crog_angle_map": (C.c_int, [_P, _P, _P, _L, _P]),
     "crog_jaccard": (C.c_int, [_P, _P, _I, _P, _P, _I, _I, _P, _P, _P, _P, _I, _P]),
+    "crog_stem7_patches": (C.c_int, [_P, _P, _I, _I, _I, _I, _I, _P, _I, _P]),
+    "crog_maxpool3s2": (C.c_int, [_P, _I, _I, _P, _I, _I, _I, _I, _I, _I, _I, _P]),
+    "crog_patches3": (C.c_int, [_P, _I, _P, _I, _I, _I, _I, _I, _I, _P]),
+    "crog_ssg_heads": (C.c_int, [_P, _I, _L, _I, _I, _P, _P, _P]),
+    "crog_ssg_nms_workspace_bytes": (C.c_int64, [_I, _I]),
+    "crog_ssg_fast_nms": (C.c_int, [_P, _P, _P, _I, _I, _F, _I, _I, _F, _P, _P, _P, _P, _P, _P]),
+    "crog_ssg_detect": (C.c_int, [_P, _P, _P, _I, _I, _F, _F, _I, _I, _F, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "crog_ssg_masks": (C.c_int, [_P, _I, _I, _I, _P, _P, _P, _P, _P, _I, _P, _P, _I, _I, _I, _P]),
+    "crog_gaussian": (C.c_int, [_P, _P, _P, _I, _I, _I, _P, _I, _P, _I, _I, _P]),
 }
 
 _lib = None

@@ -16,7 +16,7 @@ void crog_set_error(const char* fmt, ...) {
 }
 
 extern "C" const char* crog_last_error(void) { return g_err; }
-extern "C" int crog_abi_version(void) { return 1; }
+extern "C" int crog_abi_version(void) { return 2; }
 
 extern "C" int crog_check_device(void) {
   int dev = 0;

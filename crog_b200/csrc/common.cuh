@@ -111,7 +111,8 @@ __device__ __forceinline__ RowMap map_row(const CrogGemm& g, long long r64, long
     y = rem / g.W; x = rem - y * g.W;
   }
   m.sp = y * g.W + x;
-  m.orow = g.out_padded ? ((m.b * (g.H + 2) + y + 1) * (g.W + 2) + x + 1) : ((m.b * g.H + y) * g.W + x);
+  if (g.out_padded) m.orow = (m.b * (g.H + 2) + y + 1) * (g.W + 2) + x + 1;
+  else m.orow = m.b * (g.out_sample_rows > 0 ? g.out_sample_rows : g.H * g.W) + m.sp;
   return m;
 }
 
@@ -167,6 +168,9 @@ __device__ __forceinline__ void epilogue_math(const CrogGemm& g, const RowMap& m
   } else if (g.act == CROG_ACT_QUICKGELU) {
 #pragma unroll
     for (int j = 0; j < CNT; ++j) acc[j] = quickgelu(acc[j]);
+  } else if (g.act == CROG_ACT_TANH) {
+#pragma unroll
+    for (int j = 0; j < CNT; ++j) acc[j] = tanhf(acc[j]);
   }
   if (g.gate) {
     const float* gt = g.gate + (long long)m.b * g.N + n0;

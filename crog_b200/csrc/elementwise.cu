@@ -341,11 +341,15 @@ inline int grid_for(long long total, int block) {
 
 }  // namespace
 
+int crog_resample2(const void* in, int in_ld, int in_padded, void* out, int out_ld, int out_padded, int B, int H, int W, int C, int mode,
+                   int dtype, cudaStream_t s);
+
 extern "C" int crog_resample(const void* in, int32_t in_ld, int32_t in_padded, void* out, int32_t out_ld, int32_t out_padded,
                              int32_t B, int32_t H, int32_t W, int32_t C, int32_t mode, int32_t dtype, void* stream) {
   CROG_REQUIRE(C % 8 == 0 && in_ld % 8 == 0 && out_ld % 8 == 0, CROG_E_BADSHAPE, "resample: channels must be multiples of 8");
   CROG_REQUIRE(aligned16(in) && aligned16(out), CROG_E_BADALIGN, "resample: pointers must be 16B aligned");
-  CROG_REQUIRE(mode >= 0 && mode <= 2, CROG_E_BADSHAPE, "resample: bad mode %d", mode);
+  CROG_REQUIRE(mode >= 0 && mode <= 4, CROG_E_BADSHAPE, "resample: bad mode %d", mode);
+  if (mode >= 3) return crog_resample2(in, in_ld, in_padded, out, out_ld, out_padded, B, H, W, C, mode, dtype, (cudaStream_t)stream);
   if (mode == 1) CROG_REQUIRE(H % 2 == 0 && W % 2 == 0, CROG_E_BADSHAPE, "avgpool2 needs even H,W");
   const int OH = mode == 1 ? H / 2 : (mode == 2 ? 2 * H : H), OW = mode == 1 ? W / 2 : (mode == 2 ? 2 * W : W);
   if ((long long)B * OH * OW * C == 0) return CROG_OK;

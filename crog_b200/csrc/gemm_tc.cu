@@ -491,7 +491,7 @@ int crog_gemm_tc(const CrogGemm* g, cudaStream_t stream) {
   // TMA epilogue: output row == enumerated row (so the tile is one box of the output matrix), shared weights
   const bool identity = (g->H == 0) || (g->in_padded == g->out_padded);
   const int esz = g->out_dtype == CROG_BF16 ? 2 : 4;
-  const bool tma_ok = identity && g->w_sample_stride == 0 && g->N > 16 && ((long long)g->out_ld * esz) % 16 == 0 &&
+  const bool tma_ok = identity && g->w_sample_stride == 0 && g->out_sample_rows == 0 && g->N > 16 && ((long long)g->out_ld * esz) % 16 == 0 &&
                       (!g->residual || ((long long)g->res_ld * esz) % 16 == 0) && !getenv("CROG_GEMM_LEGACY_EPILOGUE");
   if (tma_ok) return g->out_dtype == CROG_BF16 ? dispatch<MODE_TMA_BF16>(g, stream) : dispatch<MODE_TMA_F32>(g, stream);
   if (g->N <= 16) return launch<16, 8, 2, MODE_LEGACY>(g, stream);

@@ -1,0 +1,549 @@
+// SSG (config 4) kernels: the layout / gather kernels the torchvision-style ResNet-50 + FPN needs on top of the
+// implicit-GEMM (strided convolutions as gathers, 3x3/2 max-pool), the head finalisation, and the device side of
+// ssg_post_processing (utils/grasp_eval.py:100-221 of the reference): score filter + box decode, Fast NMS
+// (:55-93), prototype assembly + crop (utils/box_utils.py:150-171), bilinear resize to the original image,
+// and the 17-tap Gaussian with float64 accumulation (skimage.filters.gaussian -> scipy.ndimage).
+#include <math.h>
+
+#include "common.cuh"
+
+namespace {
+
+__device__ __forceinline__ long long prow(int b, int y, int x, int H, int W, int padded) {
+  return padded ? ((long long)(b * (H + 2) + y + 1) * (W + 2) + x + 1) : ((long long)(b * H + y) * W + x);
+}
+
+// ------------------------------------------------------------------ stem: 7x7 / stride 2 / pad 3 patches -> [rows, Kp]
+// K index = (ky*7 + kx)*cin + c (matches the [Cout, ky, kx, Cin] weight packing), zero padded to Kp.
+// One thread per (output pixel, 8-wide K group), K fastest so every warp store is a contiguous run of 16-byte vectors.
+template <typename T>
+__global__ void __launch_bounds__(256) stem7_patches_kernel(const float* __restrict__ rgb, const float* __restrict__ depth, int B,
+                                                            int H, int W, int cin, int Kp, T* __restrict__ out) {
+  const int OH = (H + 6 - 7) / 2 + 1, OW = (W + 6 - 7) / 2 + 1;
+  const int groups = Kp / 8;
+  const long long total = (long long)B * OH * OW * groups;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int gk = (int)(i % groups);
+    const long long pix = i / groups;
+    const int ox = (int)(pix % OW), oy = (int)((pix / OW) % OH), b = (int)(pix / ((long long)OW * OH));
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int k = gk * 8 + j;
+      float val = 0.f;
+      if (k < 49 * cin) {
+        const int c = k % cin, t = k / cin, ky = t / 7, kx = t % 7;
+        const int iy = 2 * oy + ky - 3, ix = 2 * ox + kx - 3;
+        if (iy >= 0 && iy < H && ix >= 0 && ix < W)
+          val = c < 3 ? __ldg(rgb + ((long long)(b * 3 + c) * H + iy) * W + ix) : __ldg(depth + ((long long)b * H + iy) * W + ix);
+      }
+      v[j] = val;
+    }
+    store8(out + pix * Kp + gk * 8, v);
+  }
+}
+
+// ------------------------------------------------------------------ nn.MaxPool2d(3, 2, 1) on NHWC (ssg.py:67,101)
+template <typename T>
+__global__ void __launch_bounds__(256) maxpool3s2_kernel(const T* __restrict__ in, int in_ld, int in_padded, T* __restrict__ out,
+                                                         int out_ld, int out_padded, int B, int H, int W, int C) {
+  const int OH = (H - 1) / 2 + 1, OW = (W - 1) / 2 + 1, cgs = C / 8;
+  const int b = blockIdx.x / OH, oy = blockIdx.x % OH;
+  T* op = out + prow(b, oy, 0, OH, OW, out_padded) * out_ld;
+  for (int i = threadIdx.x; i < OW * cgs; i += 256) {
+    const int ox = i / cgs, cg = i - ox * cgs;
+    float m[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) m[j] = -INFINITY;
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+      const int iy = 2 * oy + ky - 1;
+      if (iy < 0 || iy >= H) continue;
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        const int ix = 2 * ox + kx - 1;
+        if (ix < 0 || ix >= W) continue;
+        float v[8];
+        load8(in + prow(b, iy, ix, H, W, in_padded) * in_ld + cg * 8, v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) m[j] = fmaxf(m[j], v[j]);
+      }
+    }
+    store8(op + (long long)ox * out_ld + cg * 8, m);
+  }
+}
+
+// ------------------------------------------------------------------ 3x3 / stride s / pad 1 patches of a zero-haloed NHWC tensor
+// out[(b, oy, ox), tap*C + c] = in_padded[b, s*oy + ky, s*ox + kx, c]   (padded coordinates, so pad = 1 is the halo)
+template <typename T>
+__global__ void __launch_bounds__(256) patches3_kernel(const T* __restrict__ in, int in_ld, T* __restrict__ out, int B, int H, int W,
+                                                       int C, int stride) {
+  const int OH = (H - 1) / stride + 1, OW = (W - 1) / stride + 1, cgs = C / 8;
+  const int b = blockIdx.x / OH, oy = blockIdx.x % OH;
+  const int n = OW * 9 * cgs;
+  T* op = out + (long long)(b * OH + oy) * OW * 9 * C;
+  for (int i = threadIdx.x; i < n; i += 256) {
+    const int cg = i % cgs, t = (i / cgs) % 9, ox = i / (9 * cgs);
+    const int ky = t / 3, kx = t % 3;
+    const long long r = (long long)(b * (H + 2) + stride * oy + ky) * (W + 2) + stride * ox + kx;
+    float f[8];
+    load8(in + r * in_ld + cg * 8, f);
+    store8(op + ((long long)ox * 9 + t) * C + cg * 8, f);
+  }
+}
+
+// ------------------------------------------------------------------ extra resample modes: x[::2, ::2] and bilinear x2 align_corners=True
+template <typename T, int MODE>  // 3 = subsample2, 4 = bilinear x2 (align_corners=True, ssg.py:159)
+__global__ void __launch_bounds__(256) resample2_kernel(const T* __restrict__ in, int in_ld, int in_padded, T* __restrict__ out,
+                                                        int out_ld, int out_padded, int B, int H, int W, int C) {
+  const int OH = MODE == 3 ? (H - 1) / 2 + 1 : 2 * H, OW = MODE == 3 ? (W - 1) / 2 + 1 : 2 * W, cgs = C / 8;
+  const int b = blockIdx.x / OH, oy = blockIdx.x % OH;
+  T* op = out + prow(b, oy, 0, OH, OW, out_padded) * out_ld;
+  if (MODE == 3) {
+    for (int i = threadIdx.x; i < OW * cgs; i += 256) {
+      const int ox = i / cgs, cg = i - ox * cgs;
+      float v[8];
+      load8(in + prow(b, 2 * oy, 2 * ox, H, W, in_padded) * in_ld + cg * 8, v);
+      store8(op + (long long)ox * out_ld + cg * 8, v);
+    }
+  } else {
+    // PyTorch: scale = (in - 1) / (out - 1); src = scale * dst; lambda1 = src - floor(src)
+    const float sh = OH > 1 ? (float)(H - 1) / (float)(OH - 1) : 0.f, sw = OW > 1 ? (float)(W - 1) / (float)(OW - 1) : 0.f;
+    const float sy = sh * oy;
+    const int y0 = (int)sy, y1 = min(y0 + 1, H - 1);
+    const float ly = sy - y0, hy = 1.f - ly;
+    for (int i = threadIdx.x; i < OW * cgs; i += 256) {
+      const int ox = i / cgs, cg = i - ox * cgs;
+      const float sx = sw * ox;
+      const int x0 = (int)sx, x1 = min(x0 + 1, W - 1);
+      const float lx = sx - x0, hx = 1.f - lx;
+      float v[8], a[8], c[8], d[8];
+      load8(in + prow(b, y0, x0, H, W, in_padded) * in_ld + cg * 8, v);
+      load8(in + prow(b, y0, x1, H, W, in_padded) * in_ld + cg * 8, a);
+      load8(in + prow(b, y1, x0, H, W, in_padded) * in_ld + cg * 8, c);
+      load8(in + prow(b, y1, x1, H, W, in_padded) * in_ld + cg * 8, d);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = hy * (hx * v[j] + lx * a[j]) + ly * (hx * c[j] + lx * d[j]);
+      store8(op + (long long)ox * out_ld + cg * 8, v);
+    }
+  }
+}
+
+// ------------------------------------------------------------------ head finalisation: softmax over classes + box slice
+// in: [rows, ld] fp32 with columns [na*nc class logits | na*4 box deltas | pad]; one warp per (row, anchor).
+__global__ void __launch_bounds__(256) ssg_heads_kernel(const float* __restrict__ in, int ld, long long rows, int na, int nc,
+                                                        float* __restrict__ cls, float* __restrict__ box) {
+  const int lane = threadIdx.x & 31;
+  const long long w = blockIdx.x * (long long)(blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (w >= rows * na) return;
+  const long long r = w / na;
+  const int a = (int)(w % na);
+  const float* src = in + r * ld + a * nc;
+  float mx = -INFINITY;
+  for (int k = lane; k < nc; k += 32) mx = fmaxf(mx, src[k]);
+  mx = warp_max(mx);
+  float s = 0.f;
+  for (int k = lane; k < nc; k += 32) s += expf(src[k] - mx);
+  s = warp_sum(s);
+  for (int k = lane; k < nc; k += 32) cls[w * nc + k] = expf(src[k] - mx) / s;
+  if (lane < 4) box[w * 4 + lane] = in[r * ld + na * nc + a * 4 + lane];
+}
+
+// ------------------------------------------------------------------ post-processing: score filter + box decode
+// grasp_eval.py:113-137: keep = max_{c>=1} cls[n, c] > thr; centre-form decode with variances (0.1, 0.2) -> point form,
+// clipped to [0, 1].  Every float op is a separately rounded fp32 op in the reference's order.
+__global__ void ssg_decode_kernel(const float* __restrict__ cls, const float* __restrict__ box, const float* __restrict__ anchors,
+                                  int N, int nc, float thr, int* __restrict__ keep, float* __restrict__ boxes) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  float mx = -INFINITY;
+  for (int c = 1; c < nc; ++c) mx = fmaxf(mx, cls[(long long)n * nc + c]);
+  keep[n] = mx > thr;
+  const float ax = anchors[n * 4], ay = anchors[n * 4 + 1], aw = anchors[n * 4 + 2], ah = anchors[n * 4 + 3];
+  const float bx = box[n * 4], by = box[n * 4 + 1], bw = box[n * 4 + 2], bh = box[n * 4 + 3];
+  const float cx = __fadd_rn(ax, __fmul_rn(__fmul_rn(bx, 0.1f), aw)), cy = __fadd_rn(ay, __fmul_rn(__fmul_rn(by, 0.1f), ah));
+  const float w = __fmul_rn(aw, expf(__fmul_rn(bw, 0.2f))), h = __fmul_rn(ah, expf(__fmul_rn(bh, 0.2f)));
+  const float x1 = __fsub_rn(cx, __fdiv_rn(w, 2.f)), y1 = __fsub_rn(cy, __fdiv_rn(h, 2.f));
+  const float x2 = __fadd_rn(w, x1), y2 = __fadd_rn(h, y1);
+  boxes[n * 4] = fminf(fmaxf(x1, 0.f), 1.f); boxes[n * 4 + 1] = fminf(fmaxf(y1, 0.f), 1.f);
+  boxes[n * 4 + 2] = fminf(fmaxf(x2, 0.f), 1.f); boxes[n * 4 + 3] = fminf(fmaxf(y2, 0.f), 1.f);
+}
+
+// ------------------------------------------------------------------ Fast NMS (grasp_eval.py:55-93)
+constexpr int NMS_T = 1024;       // threads per class CTA
+constexpr int NMS_CAP = 24576;    // kept anchors held in shared memory (192 KB of 64-bit keys)
+constexpr int NMS_SEL = 256;      // >= top_k
+
+__device__ __forceinline__ unsigned long long score_key(float s, int idx) {
+  // scores are softmax outputs (>= 0): the IEEE bit pattern orders them; ties -> lower index first (stable sort)
+  return ((unsigned long long)__float_as_uint(s) << 32) | (unsigned long long)(0xffffffffu - (uint32_t)idx);
+}
+
+// in-place bitonic sort, descending, n a power of two, all threads of the CTA participate
+__device__ void bitonic_desc(unsigned long long* a, int n) {
+  for (int k = 2; k <= n; k <<= 1)
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      __syncthreads();
+      for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const int l = i ^ j;
+        if (l > i) {
+          const unsigned long long x = a[i], y = a[l];
+          const bool up = (i & k) == 0;  // descending runs first
+          if (up ? (x < y) : (x > y)) { a[i] = y; a[l] = x; }
+        }
+      }
+    }
+  __syncthreads();
+}
+
+__device__ __forceinline__ float box_iou1(const float4 a, const float4 b) {
+  // utils/box_utils.py:28-36, separately rounded fp32 ops
+  const float iw = fmaxf(__fsub_rn(fminf(a.z, b.z), fmaxf(a.x, b.x)), 0.f), ih = fmaxf(__fsub_rn(fminf(a.w, b.w), fmaxf(a.y, b.y)), 0.f);
+  const float ia = __fmul_rn(iw, ih);
+  const float aa = __fmul_rn(__fsub_rn(a.z, a.x), __fsub_rn(a.w, a.y)), ab = __fmul_rn(__fsub_rn(b.z, b.x), __fsub_rn(b.w, b.y));
+  return __fdiv_rn(ia, __fsub_rn(__fadd_rn(aa, ab), ia));
+}
+
+// One CTA per foreground class: exact top_k of the kept anchors by (score desc, index asc) with a 64-bit radix select in
+// shared memory, a bitonic sort of the selected keys, then the upper-triangular IoU column maximum.
+__global__ void __launch_bounds__(NMS_T) ssg_nms_class_kernel(const float* __restrict__ cls, const int* __restrict__ keep,
+                                                              const float* __restrict__ boxes, int N, int nc, int top_k, float iou_thr,
+                                                              unsigned long long* __restrict__ cand, int* __restrict__ cand_keep,
+                                                              int* __restrict__ cand_n) {
+  extern __shared__ unsigned long long s_keys[];  // [NMS_CAP]
+  __shared__ unsigned long long s_sel[NMS_SEL];
+  __shared__ float4 s_box[NMS_SEL];
+  __shared__ int s_hist[256];
+  __shared__ int s_cnt, s_nsel;
+  __shared__ unsigned long long s_prefix;
+  __shared__ int s_remaining;
+  const int c = blockIdx.x + 1;  // class (0 = background is excluded)
+  if (threadIdx.x == 0) { s_cnt = 0; s_nsel = 0; }
+  __syncthreads();
+  for (int n = threadIdx.x; n < N; n += NMS_T)
+    if (keep[n]) {
+      const int p = atomicAdd(&s_cnt, 1);
+      if (p < NMS_CAP) s_keys[p] = score_key(cls[(long long)n * nc + c], n);
+    }
+  __syncthreads();
+  const int n = min(s_cnt, NMS_CAP);
+  unsigned long long T = 0ull;  // keys >= T are selected
+  if (n > top_k) {
+    if (threadIdx.x == 0) { s_prefix = 0ull; s_remaining = top_k; }
+    for (int pass = 7; pass >= 0; --pass) {
+      for (int i = threadIdx.x; i < 256; i += NMS_T) s_hist[i] = 0;
+      __syncthreads();
+      const unsigned long long prefix = s_prefix;
+      const unsigned long long himask = pass == 7 ? 0ull : (~0ull << (8 * (pass + 1)));
+      for (int i = threadIdx.x; i < n; i += NMS_T) {
+        const unsigned long long k = s_keys[i];
+        if ((k & himask) == prefix) atomicAdd(&s_hist[(int)((k >> (8 * pass)) & 0xff)], 1);
+      }
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        int rem = s_remaining, b = 255;
+        for (; b > 0; --b) {
+          if (s_hist[b] >= rem) break;
+          rem -= s_hist[b];
+        }
+        s_remaining = rem;  // rank of the wanted key inside bin b
+        s_prefix = prefix | ((unsigned long long)b << (8 * pass));
+      }
+      __syncthreads();
+    }
+    T = s_prefix;
+  }
+  for (int i = threadIdx.x; i < NMS_SEL; i += NMS_T) s_sel[i] = 0ull;
+  __syncthreads();
+  for (int i = threadIdx.x; i < n; i += NMS_T) {
+    const unsigned long long k = s_keys[i];
+    if (k >= T && k != 0ull) { const int p = atomicAdd(&s_nsel, 1); if (p < NMS_SEL) s_sel[p] = k; }
+  }
+  __syncthreads();
+  const int nsel = min(s_nsel, top_k);
+  bitonic_desc(s_sel, NMS_SEL);
+  for (int i = threadIdx.x; i < nsel; i += NMS_T) {
+    const int a = (int)(0xffffffffu - (uint32_t)(s_sel[i] & 0xffffffffull));
+    s_box[i] = *reinterpret_cast<const float4*>(boxes + (long long)a * 4);
+  }
+  __syncthreads();
+  for (int j = threadIdx.x; j < nsel; j += NMS_T) {
+    float m = 0.f;  // triu_(diagonal=1) leaves zeros on and below the diagonal, so the column maximum starts at 0
+    bool isnan_ = false;
+    const float4 bj = s_box[j];
+    for (int i = 0; i < j; ++i) {
+      const float v = box_iou1(s_box[i], bj);
+      if (v != v) isnan_ = true;  // torch.max propagates NaN (0/0 for degenerate boxes); NaN <= thr is False
+      m = fmaxf(m, v);
+    }
+    cand[(long long)blockIdx.x * top_k + j] = s_sel[j];
+    cand_keep[(long long)blockIdx.x * top_k + j] = (!isnan_ && m <= iou_thr) ? 1 : 0;
+  }
+  if (threadIdx.x == 0) cand_n[blockIdx.x] = nsel;
+}
+
+// One CTA: flatten the kept candidates class-major (the order boolean indexing gives), stable sort by score, keep
+// max_det, then the score > thr2 filter of grasp_eval.py:142-150 (kept only if at least one detection passes).
+constexpr int MRG_CAP = 8192;
+__global__ void __launch_bounds__(1024) ssg_nms_merge_kernel(const unsigned long long* __restrict__ cand, const int* __restrict__ cand_keep,
+                                                             const int* __restrict__ cand_n, int ncls, int top_k, int max_det, float thr2,
+                                                             int* __restrict__ det_n, int* __restrict__ det_anchor, int* __restrict__ det_class,
+                                                             float* __restrict__ det_score) {
+  extern __shared__ unsigned long long s_k[];  // [MRG_CAP]
+  __shared__ int s_pass;
+  for (int i = threadIdx.x; i < MRG_CAP; i += blockDim.x) {
+    unsigned long long k = 0ull;
+    if (i < ncls * top_k) {
+      const int c = i / top_k, j = i % top_k;
+      if (j < cand_n[c] && cand_keep[i]) k = (cand[i] & 0xffffffff00000000ull) | (unsigned long long)(0xffffffffu - (uint32_t)i);
+    }
+    s_k[i] = k;
+  }
+  if (threadIdx.x == 0) s_pass = 0;
+  bitonic_desc(s_k, MRG_CAP);
+  int total = 0;
+  for (int i = threadIdx.x; i < max_det; i += blockDim.x)
+    if (s_k[i] != 0ull && __uint_as_float((uint32_t)(s_k[i] >> 32)) > thr2) atomicAdd(&s_pass, 1);
+  __syncthreads();
+  // count of non-empty entries among the first max_det
+  __shared__ int s_tot;
+  if (threadIdx.x == 0) s_tot = 0;
+  __syncthreads();
+  for (int i = threadIdx.x; i < max_det; i += blockDim.x) if (s_k[i] != 0ull) atomicAdd(&s_tot, 1);
+  __syncthreads();
+  total = s_pass > 0 ? s_pass : s_tot;  // sorted descending, so the passing detections are a prefix
+  for (int i = threadIdx.x; i < max_det; i += blockDim.x) {
+    if (i < total) {
+      const int flat = (int)(0xffffffffu - (uint32_t)(s_k[i] & 0xffffffffull));
+      det_anchor[i] = (int)(0xffffffffu - (uint32_t)(cand[flat] & 0xffffffffull));
+      det_class[i] = flat / top_k;  // 0-based foreground class (the reference adds 1 afterwards)
+      det_score[i] = __uint_as_float((uint32_t)(s_k[i] >> 32));
+    } else {
+      det_anchor[i] = -1; det_class[i] = -1; det_score[i] = 0.f;
+    }
+  }
+  if (threadIdx.x == 0) *det_n = total;
+}
+
+// ------------------------------------------------------------------ prototype assembly + crop (grasp_eval.py:171-181)
+// out[d][k][y][x] = crop(act_k(protos[y, x, :] . coef_k(d)))  with k = 0 ins, 1 qua, 2 sin, 3 cos, 4 wid; sigmoid on 0, 1, 4.
+__global__ void __launch_bounds__(256) ssg_lowres_kernel(const float* __restrict__ protos, int h, int w, int np_,
+                                                         const float* __restrict__ coef, const float* __restrict__ gcoef,
+                                                         const float* __restrict__ boxes, const int* __restrict__ det_anchor,
+                                                         const int* __restrict__ det_n, float* __restrict__ out) {
+  extern __shared__ float s_c[];  // [5][np]
+  const int d = blockIdx.y;
+  if (d >= *det_n) return;
+  const int a = det_anchor[d];
+  for (int i = threadIdx.x; i < 5 * np_; i += blockDim.x) {
+    const int k = i / np_, j = i % np_;
+    s_c[i] = k == 0 ? coef[(long long)a * np_ + j] : gcoef[((long long)a * 4 + (k - 1)) * np_ + j];
+  }
+  __syncthreads();
+  // sanitize_coordinates (box_utils.py:120-135) with padding = 1
+  const float bx1 = boxes[a * 4], by1 = boxes[a * 4 + 1], bx2 = boxes[a * 4 + 2], by2 = boxes[a * 4 + 3];
+  const float xa = __fmul_rn(bx1, (float)w), xb = __fmul_rn(bx2, (float)w), ya = __fmul_rn(by1, (float)h), yb = __fmul_rn(by2, (float)h);
+  const float x1 = fmaxf(__fsub_rn(fminf(xa, xb), 1.f), 0.f), x2 = fminf(__fadd_rn(fmaxf(xa, xb), 1.f), (float)w);
+  const float y1 = fmaxf(__fsub_rn(fminf(ya, yb), 1.f), 0.f), y2 = fminf(__fadd_rn(fmaxf(ya, yb), 1.f), (float)h);
+  const int npix = h * w;
+  for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < npix; p += gridDim.x * blockDim.x) {
+    const int y = p / w, x = p % w;
+    const bool inside = (float)x >= x1 && (float)x < x2 && (float)y >= y1 && (float)y < y2;
+    float acc[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+    if (inside) {
+      const float* pr = protos + (long long)p * np_;
+      for (int j = 0; j < np_; j += 4) {
+        const float4 q = *reinterpret_cast<const float4*>(pr + j);
+#pragma unroll
+        for (int k = 0; k < 5; ++k) {
+          acc[k] = fmaf(q.x, s_c[k * np_ + j], acc[k]); acc[k] = fmaf(q.y, s_c[k * np_ + j + 1], acc[k]);
+          acc[k] = fmaf(q.z, s_c[k * np_ + j + 2], acc[k]); acc[k] = fmaf(q.w, s_c[k * np_ + j + 3], acc[k]);
+        }
+      }
+      acc[0] = 1.f / (1.f + expf(-acc[0])); acc[1] = 1.f / (1.f + expf(-acc[1])); acc[4] = 1.f / (1.f + expf(-acc[4]));
+    }
+#pragma unroll
+    for (int k = 0; k < 5; ++k) out[((long long)d * 5 + k) * npix + p] = acc[k];
+  }
+}
+
+// ------------------------------------------------------------------ F.interpolate(size=(S,S), bilinear, align_corners=False) + [:oh, :ow] crop
+// planes [P][h][w] -> [P][oh][ow]; planes whose bit is set in bin_mask (by plane % planes_per_det) are thresholded > 0.5.
+__global__ void __launch_bounds__(256) bilinear_crop_kernel(const float* __restrict__ in, int h, int w, float* __restrict__ out, int oh,
+                                                            int ow, int S, const int* __restrict__ n_planes, int planes_per_det,
+                                                            uint32_t bin_mask) {
+  const int pl = blockIdx.z;
+  if (n_planes && pl >= *n_planes * planes_per_det) return;
+  const int ox = blockIdx.x * blockDim.x + threadIdx.x, oy = blockIdx.y;
+  if (ox >= ow) return;
+  const float sc_h = (float)h / (float)S, sc_w = (float)w / (float)S;
+  const float sy = fmaxf(__fsub_rn(__fmul_rn(sc_h, (float)oy + 0.5f), 0.5f), 0.f), sx = fmaxf(__fsub_rn(__fmul_rn(sc_w, (float)ox + 0.5f), 0.5f), 0.f);
+  const int y0 = (int)sy, x0 = (int)sx, y1 = y0 + (y0 < h - 1), x1 = x0 + (x0 < w - 1);
+  const float ly = sy - y0, lx = sx - x0, hy = 1.f - ly, hx = 1.f - lx;
+  const float* src = in + (long long)pl * h * w;
+  const float v = hy * (hx * __ldg(src + y0 * w + x0) + lx * __ldg(src + y0 * w + x1)) + ly * (hx * __ldg(src + y1 * w + x0) + lx * __ldg(src + y1 * w + x1));
+  const int d = pl / planes_per_det, k = pl % planes_per_det;
+  const bool bin = (bin_mask >> k) & 1u;
+  // output is map-major: [planes_per_det][gridDim.z / planes_per_det detections][oh][ow], so each map type is one contiguous batch
+  out[(((long long)k * (gridDim.z / planes_per_det) + d) * oh + oy) * ow + ox] = bin ? (v > 0.5f ? 1.f : 0.f) : v;
+}
+
+// ------------------------------------------------------------------ Gaussian (sigma = 2 -> 17 taps), float64 accumulation, float32 per pass
+struct GaussW { double w[33]; int r; };
+
+// scipy correlate1d order for a symmetric kernel: centre tap first, then pairs from the outermost inwards; each product and
+// sum is a separately rounded float64 operation (no FMA), the pass result is rounded to float32 once.
+template <int AXIS>
+__global__ void __launch_bounds__(256) gaussian_pass_kernel(const float* __restrict__ in, float* __restrict__ out, int H, int W,
+                                                            const int* __restrict__ n_planes, int plane_stride_sel, int plane_sel, GaussW g) {
+  // planes processed: pl = blockIdx.z * plane_stride_sel + plane_sel (lets the caller smooth only the quality planes)
+  const int pz = blockIdx.z;
+  if (n_planes && pz >= *n_planes) return;
+  const long long base = ((long long)pz * plane_stride_sel + plane_sel) * H * W;
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+  if (x >= W) return;
+  const float* src = in + base;
+  const int r = g.r;
+  auto at = [&](int o) -> double {
+    if (AXIS == 0) { const int yy = min(max(y + o, 0), H - 1); return (double)__ldg(src + (long long)yy * W + x); }
+    const int xx = min(max(x + o, 0), W - 1);
+    return (double)__ldg(src + (long long)y * W + xx);
+  };
+  double acc = __dmul_rn(at(0), g.w[r]);
+  for (int j = -r; j < 0; ++j) acc = __dadd_rn(acc, __dmul_rn(__dadd_rn(at(j), at(-j)), g.w[j + r]));
+  out[base + (long long)y * W + x] = (float)acc;
+}
+
+}  // namespace
+
+// ====================================================================== C ABI
+extern "C" int crog_stem7_patches(const float* rgb, const float* depth, int32_t B, int32_t H, int32_t W, int32_t cin, int32_t Kp,
+                                  void* out, int32_t out_dtype, void* stream) {
+  CROG_REQUIRE((cin == 3 || cin == 4) && Kp % 8 == 0 && Kp >= 49 * cin, CROG_E_BADSHAPE, "stem7_patches: cin %d Kp %d", cin, Kp);
+  CROG_REQUIRE(cin == 3 || depth != nullptr, CROG_E_BADSHAPE, "stem7_patches: depth plane missing");
+  const long long total = (long long)B * ((H - 1) / 2 + 1) * ((W - 1) / 2 + 1) * (Kp / 8);
+  if (total == 0) return CROG_OK;
+  long long g = (total + 255) / 256;
+  if (g > 148 * 64) g = 148 * 64;
+  if (out_dtype == CROG_F32) stem7_patches_kernel<float><<<(int)g, 256, 0, (cudaStream_t)stream>>>(rgb, depth, B, H, W, cin, Kp, (float*)out);
+  else stem7_patches_kernel<bf16><<<(int)g, 256, 0, (cudaStream_t)stream>>>(rgb, depth, B, H, W, cin, Kp, (bf16*)out);
+  CROG_LAUNCH_OK("stem7_patches");
+  return CROG_OK;
+}
+
+extern "C" int crog_maxpool3s2(const void* in, int32_t in_ld, int32_t in_padded, void* out, int32_t out_ld, int32_t out_padded,
+                               int32_t B, int32_t H, int32_t W, int32_t C, int32_t dtype, void* stream) {
+  CROG_REQUIRE(C % 8 == 0 && in_ld % 8 == 0 && out_ld % 8 == 0 && aligned16(in) && aligned16(out), CROG_E_BADSHAPE, "maxpool3s2: bad shape");
+  if (B * H * W == 0) return CROG_OK;
+  const int g = B * ((H - 1) / 2 + 1);
+  if (dtype == CROG_F32) maxpool3s2_kernel<float><<<g, 256, 0, (cudaStream_t)stream>>>((const float*)in, in_ld, in_padded, (float*)out, out_ld, out_padded, B, H, W, C);
+  else maxpool3s2_kernel<bf16><<<g, 256, 0, (cudaStream_t)stream>>>((const bf16*)in, in_ld, in_padded, (bf16*)out, out_ld, out_padded, B, H, W, C);
+  CROG_LAUNCH_OK("maxpool3s2");
+  return CROG_OK;
+}
+
+extern "C" int crog_patches3(const void* in, int32_t in_ld, void* out, int32_t B, int32_t H, int32_t W, int32_t C, int32_t stride,
+                             int32_t dtype, void* stream) {
+  CROG_REQUIRE(C % 8 == 0 && in_ld % 8 == 0 && (stride == 1 || stride == 2) && aligned16(in) && aligned16(out), CROG_E_BADSHAPE, "patches3: bad shape");
+  if (B * H * W == 0) return CROG_OK;
+  const int g = B * ((H - 1) / stride + 1);
+  if (dtype == CROG_F32) patches3_kernel<float><<<g, 256, 0, (cudaStream_t)stream>>>((const float*)in, in_ld, (float*)out, B, H, W, C, stride);
+  else patches3_kernel<bf16><<<g, 256, 0, (cudaStream_t)stream>>>((const bf16*)in, in_ld, (bf16*)out, B, H, W, C, stride);
+  CROG_LAUNCH_OK("patches3");
+  return CROG_OK;
+}
+
+int crog_resample2(const void* in, int in_ld, int in_padded, void* out, int out_ld, int out_padded, int B, int H, int W, int C, int mode,
+                   int dtype, cudaStream_t s) {
+  const int OH = mode == 3 ? (H - 1) / 2 + 1 : 2 * H;
+  const int g = B * OH;
+  if (g == 0) return CROG_OK;
+#define RS2(T, M) resample2_kernel<T, M><<<g, 256, 0, s>>>((const T*)in, in_ld, in_padded, (T*)out, out_ld, out_padded, B, H, W, C)
+  if (dtype == CROG_F32) { if (mode == 3) RS2(float, 3); else RS2(float, 4); }
+  else { if (mode == 3) RS2(bf16, 3); else RS2(bf16, 4); }
+#undef RS2
+  CROG_LAUNCH_OK("resample2");
+  return CROG_OK;
+}
+
+extern "C" int crog_ssg_heads(const float* in, int32_t ld, int64_t rows, int32_t na, int32_t nc, float* cls, float* box, void* stream) {
+  CROG_REQUIRE(ld >= na * (nc + 4), CROG_E_BADSHAPE, "ssg_heads: ld %d too small", ld);
+  if (rows == 0) return CROG_OK;
+  const long long warps = rows * na;
+  ssg_heads_kernel<<<(int)((warps + 7) / 8), 256, 0, (cudaStream_t)stream>>>(in, ld, rows, na, nc, cls, box);
+  CROG_LAUNCH_OK("ssg_heads");
+  return CROG_OK;
+}
+
+extern "C" int64_t crog_ssg_nms_workspace_bytes(int32_t num_classes, int32_t top_k) {
+  const int64_t n = (int64_t)(num_classes - 1) * top_k;
+  return n * 8 + n * 4 + (int64_t)(num_classes - 1) * 4 + 256;
+}
+
+extern "C" int crog_ssg_fast_nms(const float* cls, const int32_t* keep, const float* boxes, int32_t N, int32_t num_classes, float iou_thr,
+                                 int32_t top_k, int32_t max_det, float score_thr2, int32_t* det_n, int32_t* det_anchor, int32_t* det_class,
+                                 float* det_score, void* workspace, void* stream) {
+  CROG_REQUIRE(N >= 0 && num_classes >= 2 && top_k >= 1 && top_k <= NMS_SEL && max_det >= 1 && max_det <= 1024, CROG_E_BADSHAPE,
+               "ssg_fast_nms: N %d classes %d top_k %d max_det %d", N, num_classes, top_k, max_det);
+  CROG_REQUIRE(N <= NMS_CAP && (num_classes - 1) * top_k <= MRG_CAP, CROG_E_BADSHAPE, "ssg_fast_nms: at most %d anchors and %d candidates", NMS_CAP, MRG_CAP);
+  CROG_REQUIRE(aligned16(boxes) && aligned16(workspace), CROG_E_BADALIGN, "ssg_fast_nms: 16B alignment");
+  cudaStream_t s = (cudaStream_t)stream;
+  const int ncls = num_classes - 1;
+  unsigned long long* cand = (unsigned long long*)workspace;
+  int* cand_keep = (int*)(cand + (size_t)ncls * top_k);
+  int* cand_n = cand_keep + (size_t)ncls * top_k;
+  static bool attr = false;
+  if (!attr) {
+    CROG_CUDA_OK(cudaFuncSetAttribute(ssg_nms_class_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, NMS_CAP * 8));
+    CROG_CUDA_OK(cudaFuncSetAttribute(ssg_nms_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MRG_CAP * 8));
+    attr = true;
+  }
+  ssg_nms_class_kernel<<<ncls, NMS_T, NMS_CAP * 8, s>>>(cls, keep, boxes, N, num_classes, top_k, iou_thr, cand, cand_keep, cand_n);
+  CROG_LAUNCH_OK("ssg_nms_class");
+  ssg_nms_merge_kernel<<<1, 1024, MRG_CAP * 8, s>>>(cand, cand_keep, cand_n, ncls, top_k, max_det, score_thr2, det_n, det_anchor, det_class, det_score);
+  CROG_LAUNCH_OK("ssg_nms_merge");
+  return CROG_OK;
+}
+
+extern "C" int crog_ssg_detect(const float* cls, const float* box, const float* anchors, int32_t N, int32_t num_classes, float score_thr,
+                               float iou_thr, int32_t top_k, int32_t max_det, float score_thr2, int32_t* keep, float* boxes,
+                               int32_t* det_n, int32_t* det_anchor, int32_t* det_class, float* det_score, void* workspace, void* stream) {
+  CROG_REQUIRE(N >= 1, CROG_E_BADSHAPE, "ssg_detect: N %d", N);
+  ssg_decode_kernel<<<(N + 255) / 256, 256, 0, (cudaStream_t)stream>>>(cls, box, anchors, N, num_classes, score_thr, keep, boxes);
+  CROG_LAUNCH_OK("ssg_decode");
+  return crog_ssg_fast_nms(cls, keep, boxes, N, num_classes, iou_thr, top_k, max_det, score_thr2, det_n, det_anchor, det_class, det_score,
+                           workspace, stream);
+}
+
+extern "C" int crog_ssg_masks(const float* protos, int32_t h, int32_t w, int32_t num_protos, const float* coef, const float* gcoef,
+                              const float* boxes, const int32_t* det_anchor, const int32_t* det_n, int32_t max_det, float* lowres,
+                              float* out, int32_t out_h, int32_t out_w, int32_t resize_to, void* stream) {
+  CROG_REQUIRE(num_protos % 4 == 0 && num_protos <= 256 && aligned16(protos), CROG_E_BADSHAPE, "ssg_masks: num_protos %d", num_protos);
+  CROG_REQUIRE(out_h <= resize_to && out_w <= resize_to && max_det * 5 <= 65535, CROG_E_BADSHAPE, "ssg_masks: bad output extent");
+  cudaStream_t s = (cudaStream_t)stream;
+  dim3 g1((h * w + 255) / 256, max_det);
+  ssg_lowres_kernel<<<g1, 256, 5 * num_protos * sizeof(float), s>>>(protos, h, w, num_protos, coef, gcoef, boxes, det_anchor, det_n, lowres);
+  CROG_LAUNCH_OK("ssg_lowres");
+  dim3 g2((out_w + 255) / 256, out_h, max_det * 5);
+  bilinear_crop_kernel<<<g2, 256, 0, s>>>(lowres, h, w, out, out_h, out_w, resize_to, det_n, 5, 1u);
+  CROG_LAUNCH_OK("ssg_resize");
+  return CROG_OK;
+}
+
+extern "C" int crog_gaussian(const float* in, float* tmp, float* out, int32_t P, int32_t H, int32_t W, const double* weights_host,
+                             int32_t radius, const int32_t* n_planes, int32_t plane_stride, int32_t plane_sel, void* stream) {
+  const int r = radius;
+  CROG_REQUIRE(weights_host != nullptr && r >= 1 && r <= 16, CROG_E_BADSHAPE, "gaussian: radius %d unsupported (1..16)", r);
+  CROG_REQUIRE(P <= 65535 && H <= 65535, CROG_E_BADSHAPE, "gaussian: too many planes");
+  if (P * H * W == 0) return CROG_OK;
+  GaussW g;
+  g.r = r;
+  for (int i = 0; i <= 2 * r; ++i) g.w[i] = weights_host[i];
+  cudaStream_t s = (cudaStream_t)stream;
+  dim3 grid((W + 255) / 256, H, P);
+  gaussian_pass_kernel<0><<<grid, 256, 0, s>>>(in, tmp, H, W, n_planes, plane_stride, plane_sel, g);
+  CROG_LAUNCH_OK("gaussian_rows");
+  gaussian_pass_kernel<1><<<grid, 256, 0, s>>>(tmp, out, H, W, n_planes, plane_stride, plane_sel, g);
+  CROG_LAUNCH_OK("gaussian_cols");
+  return CROG_OK;
+}

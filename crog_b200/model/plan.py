@@ -173,7 +173,7 @@ class ForwardPlan:
     def gemm(self, name: str, a: Act, w: torch.Tensor, N: int, out: Act, taps: int = 1, scale=None, bias=None,
              act: int = L.ACT_NONE, residual: Optional[Act] = None, residual_relu: bool = False, addmat=None,
              gate=None, scale2=None, bias2=None, w_sample_stride: int = 0, cin: Optional[int] = None,
-             alg_n: Optional[int] = None, alg_cin: Optional[int] = None):
+             alg_n: Optional[int] = None, alg_cin: Optional[int] = None, out_sample_rows: int = 0, out_row0: int = 0):
         g = L.CrogGemm()
         cin = cin if cin is not None else a.C
         assert w.shape[-1] == taps * cin, (name, tuple(w.shape), taps, cin)
@@ -192,9 +192,10 @@ class ForwardPlan:
         if residual is not None:
             assert residual.t.dtype == out.t.dtype and residual.padded == out.padded
             g.residual, g.res_ld, g.residual_relu = residual.ptr, residual.ld, int(residual_relu)
-        g.out, g.out_ld, g.out_dtype = out.ptr, out.ld, L.dtype_code(out.t.dtype)
+        g.out, g.out_ld, g.out_dtype = out.ptr + out_row0 * out.ld * out.t.element_size(), out.ld, L.dtype_code(out.t.dtype)
         g.impl = self.impl
-        if a.H > 0:
+        g.out_sample_rows = out_sample_rows
+        if a.H > 0 and out_sample_rows == 0:
             assert out.H == a.H and out.W == a.W, name
         self._hold.extend([g, w, scale, bias, addmat, gate, scale2, bias2])
         lib = self.lib

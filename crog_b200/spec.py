@@ -161,3 +161,51 @@ def crog_tensor_specs(cfg) -> List[TensorSpec]:
     add(TensorSpec("proj.vis.4.bias", (c * heads,), "bias", fan_in=c))
     ext(_linear("proj.txt", c * 9 + 1, cfg.word_dim))
     return out
+
+
+# ====================================================================== SSG (config 4)
+def ssg_tensor_specs(cfg) -> List[TensorSpec]:
+    """All tensors of the reference ``SSG(cfg).state_dict()`` (model/ssg.py:53-245): torchvision-style
+    ResNet (7x7 stem on 3 or 4 channels, stride in the 3x3 conv), FPN with biased convs and no BN,
+    ProtoNet, the shared PredictionModule and ``semantic_seg_conv`` (created because the module is
+    built in training mode, ssg.py:237-238; unused at inference but part of every checkpoint)."""
+    out: List[TensorSpec] = []
+    add, ext = out.append, out.extend
+
+    def convb(name: str, cout: int, cin: int, k: int):
+        add(_conv(name + ".weight", cout, cin, k))
+        add(TensorSpec(name + ".bias", (cout,), "bias", fan_in=cin * k * k))
+
+    cin0 = 4 if cfg.with_depth else 3
+    add(_conv("backbone.conv1.weight", 64, cin0, 7)); ext(_bn("backbone.bn1", 64))
+    inplanes = 64
+    for li, nblocks in enumerate(cfg.resnet_layers):
+        planes = 64 * 2 ** li
+        for bi in range(nblocks):
+            p = f"backbone.layers.{li}.{bi}"
+            add(_conv(p + ".conv1.weight", planes, inplanes, 1)); ext(_bn(p + ".bn1", planes))
+            add(_conv(p + ".conv2.weight", planes, planes, 3)); ext(_bn(p + ".bn2", planes))
+            add(_conv(p + ".conv3.weight", planes * 4, planes, 1)); ext(_bn(p + ".bn3", planes * 4))
+            if bi == 0:
+                add(_conv(p + ".downsample.0.weight", planes * 4, inplanes, 1))
+                ext(_bn(p + ".downsample.1", planes * 4))
+            inplanes = planes * 4
+    for i, c in enumerate(cfg.fpn_in_channels):
+        convb(f"fpn.lat_layers.{i}", 256, c, 1)
+    for i in range(len(cfg.fpn_in_channels)):
+        convb(f"fpn.pred_layers.{i}.0", 256, 256, 3)
+    for i in range(2):
+        convb(f"fpn.downsample_layers.{i}.0", 256, 256, 3)
+    for i in (0, 2, 4):
+        convb(f"proto_net.proto1.{i}", 256, 256, 3)
+    convb("proto_net.proto2.0", 256, 256, 3)
+    convb("proto_net.proto2.2", cfg.num_protos, 256, 1)
+    na = len(cfg.aspect_ratios)
+    convb("prediction_layers.upfeature.0", 256, 256, 3)
+    convb("prediction_layers.bbox_layer", na * 4, 256, 3)
+    convb("prediction_layers.conf_layer", na * cfg.num_classes, 256, 3)
+    convb("prediction_layers.coef_layer.0", na * cfg.num_protos, 256, 3)
+    if cfg.with_grasp_masks:
+        convb("prediction_layers.grasp_coef_layer.0", na * cfg.num_protos * 4, 256, 3)
+    convb("semantic_seg_conv", cfg.num_classes, 256, 1)
+    return out

@@ -184,3 +184,88 @@ def make_tail_maps(n: int, kind: str = "blobs", seed: int = 7, size: int = 416
         c[i] = np.cos(2 * phi) + rng.normal(0, 0.05, phi.shape).astype(np.float32)
         w[i] = (0.5 + 0.5 * np.sin(rng.uniform(0.005, 0.03) * xx + rng.uniform(0.005, 0.03) * yy)).astype(np.float32)
     return q, s, c, w
+
+
+# ====================================================================== SSG (config 4)
+def ssg_cfg(**over) -> SimpleNamespace:
+    """Model / post-processing keys of config/OCID-Grasp/ssg_r50.yaml:6-31,52-57."""
+    cfg = SimpleNamespace(
+        backbone="resnet", resnet_layers=[3, 4, 6, 3], path_to_pretrained_resnet=None, resume=None, with_depth=True,
+        fpn_in_channels=[512, 1024, 2048], num_protos=32, num_classes=32, aspect_ratios=[1, 0.5, 2],
+        anchor_strides=[8, 16, 32, 64, 128], with_grasp_masks=True, img_size=544,
+        nms_score_thre=0.05, nms_iou_thre=0.5, top_k=200, max_detections=100)
+    for k, v in over.items():
+        setattr(cfg, k, v)
+    return cfg
+
+
+def make_ssg_state_dict(cfg, seed: int = 0, mode: str = "perturbed") -> Dict[str, torch.Tensor]:
+    """mode="init": the reference's xavier-uniform convs, zero biases, identity BN (ssg.py:241-245).
+    mode="perturbed": He-scaled convs, random biases and BN affine / statistics (every term exercised)."""
+    from .spec import ssg_tensor_specs
+
+    assert mode in ("init", "perturbed")
+    g = torch.Generator().manual_seed(seed)
+    sd: Dict[str, torch.Tensor] = {}
+    for s in ssg_tensor_specs(cfg):
+        if s.role == "conv":
+            if mode == "init":
+                co, ci, kh, kw = s.shape
+                bound = math.sqrt(6.0 / (ci * kh * kw + co * kh * kw))
+                t = (torch.rand(s.shape, generator=g) * 2 - 1) * bound
+            else:
+                gain = 1.0 if ("prediction_layers" in s.name and "upfeature" not in s.name) or "proto2.2" in s.name else 2.0
+                t = torch.randn(s.shape, generator=g) * math.sqrt(gain / s.fan_in)
+        elif s.role == "bias":
+            t = torch.zeros(s.shape) if mode == "init" else torch.randn(s.shape, generator=g) * 0.05
+        elif s.role == "bn_w":
+            if mode == "init":
+                t = torch.ones(s.shape)
+            elif s.name.endswith("bn3.weight"):
+                t = torch.rand(s.shape, generator=g) * 0.4 + 0.1
+            else:
+                t = torch.rand(s.shape, generator=g) + 0.5
+        elif s.role in ("bn_b", "bn_mean"):
+            t = torch.zeros(s.shape) if mode == "init" else torch.randn(s.shape, generator=g) * 0.1
+        elif s.role == "bn_var":
+            t = torch.ones(s.shape) if mode == "init" else torch.rand(s.shape, generator=g) + 0.5
+        elif s.role == "bn_count":
+            t = torch.zeros((), dtype=torch.int64)
+        else:  # pragma: no cover
+            raise KeyError(s.role)
+        sd[s.name] = t.contiguous()
+    return sd
+
+
+def make_ssg_inputs(batch: int, size: int = 544, seed: int = 5) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Config-4 inputs: rgb ~ U(0,1) B x 3 x S x S, depth ~ U(0,1) B x 1 x S x S."""
+    g = torch.Generator().manual_seed(seed)
+    return torch.rand((batch, 3, size, size), generator=g), torch.rand((batch, 1, size, size), generator=g)
+
+
+def make_ssg_output_dict(cfg, n_confident: int = 8, seed: int = 6, proto_hw: int = 136) -> Dict[str, torch.Tensor]:
+    """A synthetic single-image ``output_dict`` with ``n_confident`` confident, well separated detections (random-init
+    scores never pass 0.3, so post-processing is exercised on injected detections)."""
+    from .model.ssg_anchors import make_all_anchors
+
+    g = torch.Generator().manual_seed(seed)
+    anchors = torch.tensor(make_all_anchors(cfg), dtype=torch.float32).view(-1, 4)
+    N, nc, npz = anchors.shape[0], cfg.num_classes, cfg.num_protos
+    logits = torch.randn((N, nc), generator=g) * 0.5
+    logits[:, 0] += 6.0  # background dominates
+    box = torch.randn((N, 4), generator=g) * 0.3
+    coef = torch.tanh(torch.randn((N, npz), generator=g))
+    gcoef = torch.tanh(torch.randn((N, 4, npz), generator=g))
+    # confident anchors on the stride-16/32 levels, spread over the image, plus near-duplicates for NMS to remove
+    lvl0 = 3 * (proto_hw // 2) ** 2
+    picks = lvl0 + torch.randperm(3 * (proto_hw // 4) ** 2, generator=g)[:n_confident]
+    for j, a in enumerate(picks.tolist()):
+        cls = 1 + (j * 7) % (nc - 1)
+        logits[a, cls] += 9.0 + 0.1 * j
+        if a + 3 < N:  # neighbouring cell, same ratio: overlaps heavily -> suppressed by Fast NMS
+            logits[a + 3, cls] += 8.0
+            box[a + 3] = box[a]
+    protos = torch.relu(torch.randn((proto_hw, proto_hw, npz), generator=g))
+    # make the quality channel of the confident instances peaky enough to pass threshold_abs = 0.4 after smoothing
+    return {"anchors": anchors.view(-1).tolist(), "protos": protos.unsqueeze(0), "cls_pred": torch.softmax(logits, -1).unsqueeze(0),
+            "box_pred": box.unsqueeze(0), "ins_coef_pred": coef.unsqueeze(0), "grasp_coef_pred": gcoef.unsqueeze(0)}

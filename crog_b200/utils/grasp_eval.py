@@ -153,3 +153,182 @@ def calculate_jacquard_index(grasp_preds, grasp_targets, iou_threshold=0.25):
         grasp_targets[:, 2] = edited[:, 2]
         grasp_targets[:, 3] = edited[:, 3]
     return int(flags[0, 1].item())
+
+
+# ======================================================================= SSG post-processing (BASELINE config 4)
+_anchor_cache = {}
+
+
+def _anchors_dev(anchors, dev) -> torch.Tensor:
+    if torch.is_tensor(anchors):
+        return anchors.to(dev, torch.float32).reshape(-1, 4).contiguous()
+    key = (id(anchors), len(anchors), dev.index)
+    t = _anchor_cache.get(key)
+    if t is None:
+        t = torch.tensor(anchors, dtype=torch.float32, device=dev).reshape(-1, 4).contiguous()
+        if len(_anchor_cache) > 8:
+            _anchor_cache.clear()
+        _anchor_cache[key] = t
+    return t
+
+
+def gaussian_taps(sigma: float, truncate: float = 4.0) -> np.ndarray:
+    """The float64 taps scipy.ndimage.gaussian_filter builds (``_gaussian_kernel1d``), which is what
+    skimage.filters.gaussian(sigma, preserve_range=True) of utils/grasp_eval.py:198 runs with."""
+    r = int(truncate * float(sigma) + 0.5)
+    x = np.arange(-r, r + 1)
+    w = np.exp(-0.5 / (sigma * sigma) * x ** 2)
+    return np.ascontiguousarray(w / w.sum(), dtype=np.float64)
+
+
+def gaussian_batched(maps: torch.Tensor, sigma: float = 2.0, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """[P, H, W] float32 CUDA maps -> Gaussian-smoothed maps with scipy/skimage semantics (edge-replicate, separable,
+    float64 accumulation, float32 result per pass)."""
+    lib = L.lib()
+    assert maps.is_cuda and maps.dtype == torch.float32 and maps.dim() == 3 and maps.is_contiguous()
+    taps = gaussian_taps(sigma)
+    P, H, W = maps.shape
+    tmp = torch.empty_like(maps)
+    out = torch.empty_like(maps) if out is None else out
+    with torch.cuda.device(maps.device):
+        L.check(lib.crog_gaussian(maps.data_ptr(), tmp.data_ptr(), out.data_ptr(), P, H, W, taps.ctypes.data, (len(taps) - 1) // 2,
+                                  None, 1, 0, L.stream_ptr()))
+    return out
+
+
+def _ssg_detect(cfg, cls: torch.Tensor, box: torch.Tensor, anchors: torch.Tensor, score_thr2: float = 0.3):
+    """grasp_eval.py:113-150 on the device for one image: returns (boxes [N,4], det_n, det_anchor, det_class, det_score)."""
+    lib = L.lib()
+    N, nc = cls.shape
+    dev = cls.device
+    md = int(cfg.max_detections)
+    keep = torch.empty((N,), dtype=torch.int32, device=dev)
+    boxes = torch.empty((N, 4), dtype=torch.float32, device=dev)
+    det_n = torch.zeros((1,), dtype=torch.int32, device=dev)
+    det_anchor = torch.empty((md,), dtype=torch.int32, device=dev)
+    det_class = torch.empty((md,), dtype=torch.int32, device=dev)
+    det_score = torch.empty((md,), dtype=torch.float32, device=dev)
+    ws = torch.empty((int(L.load().crog_ssg_nms_workspace_bytes(nc, int(cfg.top_k))),), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        L.check(lib.crog_ssg_detect(cls.data_ptr(), box.data_ptr(), anchors.data_ptr(), N, nc, float(cfg.nms_score_thre),
+                                    float(cfg.nms_iou_thre), int(cfg.top_k), md, float(score_thr2), keep.data_ptr(), boxes.data_ptr(),
+                                    det_n.data_ptr(), det_anchor.data_ptr(), det_class.data_ptr(), det_score.data_ptr(),
+                                    ws.data_ptr(), L.stream_ptr()))
+    return boxes, det_n, det_anchor, det_class, det_score, keep
+
+
+def fast_nms(cfg, box_pred_kept, cls_pred_kept, ins_coef_pred_kept, grasp_coef_pred_kept):
+    """utils/grasp_eval.py:55-93 with the reference's signature: ``box_pred_kept`` [n,4] decoded boxes, ``cls_pred_kept``
+    [num_fg_classes, n] scores -> (class_ids, scores, boxes, coefs, grasp_coefs) of the surviving detections, best first.
+    Ties in either sort go to the lower index (the reference leaves them to torch.sort)."""
+    lib = L.lib()
+    dev = _dev()
+    box = torch.as_tensor(box_pred_kept).to(dev, torch.float32).contiguous()
+    sc = torch.as_tensor(cls_pred_kept).to(dev, torch.float32)
+    coef, gco = torch.as_tensor(ins_coef_pred_kept).to(dev), torch.as_tensor(grasp_coef_pred_kept).to(dev)
+    ncf, n = sc.shape
+    md = int(cfg.max_detections)
+    cls_full = torch.cat([torch.zeros((1, n), device=dev), sc]).t().contiguous()  # [n, 1 + fg classes]; column 0 is ignored
+    keep = torch.ones((max(n, 1),), dtype=torch.int32, device=dev)
+    det_n = torch.zeros((1,), dtype=torch.int32, device=dev)
+    det_anchor = torch.empty((md,), dtype=torch.int32, device=dev)
+    det_class = torch.empty((md,), dtype=torch.int32, device=dev)
+    det_score = torch.empty((md,), dtype=torch.float32, device=dev)
+    ws = torch.empty((int(L.load().crog_ssg_nms_workspace_bytes(ncf + 1, int(cfg.top_k))),), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        L.check(lib.crog_ssg_fast_nms(cls_full.data_ptr(), keep.data_ptr(), box.data_ptr(), n, ncf + 1, float(cfg.nms_iou_thre),
+                                      int(cfg.top_k), md, float("inf"), det_n.data_ptr(), det_anchor.data_ptr(), det_class.data_ptr(),
+                                      det_score.data_ptr(), ws.data_ptr(), L.stream_ptr()))
+    k = int(det_n.item())
+    idx = det_anchor[:k].long()
+    return det_class[:k].long(), det_score[:k], box[idx], coef[idx], gco[idx]
+
+
+def ssg_masks_device(cfg, output_b, boxes, det_anchor, n: int, ori_size):
+    """grasp_eval.py:171-198 for one image with ``n`` detections, on the device: returns ``hr`` [5, n, ori_h, ori_w] float32
+    (instance mask (0/1), quality — already Gaussian-smoothed —, sin, cos, width)."""
+    lib = L.lib()
+    protos, coef, gco = output_b
+    ori_h, ori_w = int(ori_size[0]), int(ori_size[1])
+    S = max(ori_h, ori_w)
+    h, w, npz = protos.shape
+    dev = protos.device
+    lowres = torch.empty((n, 5, h, w), dtype=torch.float32, device=dev)
+    hr = torch.empty((5, n, ori_h, ori_w), dtype=torch.float32, device=dev)
+    if n == 0:
+        return hr
+    taps = gaussian_taps(2.0)
+    tmp = torch.empty((n, ori_h, ori_w), dtype=torch.float32, device=dev)
+    n_dev = torch.full((1,), n, dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        L.check(lib.crog_ssg_masks(protos.data_ptr(), h, w, npz, coef.data_ptr(), gco.data_ptr(), boxes.data_ptr(),
+                                   det_anchor.data_ptr(), n_dev.data_ptr(), n, lowres.data_ptr(), hr.data_ptr(), ori_h, ori_w, S,
+                                   L.stream_ptr()))
+        q = hr[1]
+        L.check(lib.crog_gaussian(q.data_ptr(), tmp.data_ptr(), q.data_ptr(), n, ori_h, ori_w, taps.ctypes.data, (len(taps) - 1) // 2,
+                                  None, 1, 0, L.stream_ptr()))
+    return hr
+
+
+@torch.no_grad()
+def ssg_post_processing(cfg, output_dict, data_dict):
+    """utils/grasp_eval.py:100-221 (batch size 1, like the reference): score filter, box decode, Fast NMS, prototype
+    assembly + crop, bilinear resize to the original image, Gaussian smoothing of the quality maps and grasp decode —
+    all on the B200; the returned dict has the reference's keys and host types."""
+    dev = _dev()
+    ori_h, ori_w = data_dict["ori_size"]
+    f = lambda k: torch.as_tensor(output_dict[k]).to(dev, torch.float32).squeeze(0).contiguous()
+    protos, cls, box, coef, gco = f("protos"), f("cls_pred"), f("box_pred"), f("ins_coef_pred"), f("grasp_coef_pred")
+    if cls.dim() != 2:
+        raise L.CrogError("ssg_post_processing handles one image per call (batch size 1), like the reference")
+    anchors = _anchors_dev(output_dict["anchors"], dev)
+    boxes, det_n, det_anchor, det_class, det_score, _ = _ssg_detect(cfg, cls, box, anchors)
+    n = int(det_n.item())  # dynamic output shapes, as in the reference
+    hr = ssg_masks_device(cfg, (protos, coef, gco), boxes, det_anchor, n, (ori_h, ori_w))
+    ins, qua, sin, cos, wid = hr[0], hr[1], hr[2], hr[3], hr[4]
+    top1, top5 = [], []
+    ang = torch.empty_like(sin)
+    if n > 0:
+        ang = angle_map(sin, cos)
+        _, npk, grasps = detect_grasps_batched(qua, sin, cos, wid, 5)
+        npk_h, g_h = npk.cpu().tolist(), grasps.cpu().tolist()
+        for i in range(n):
+            rows = [[r[0], r[1], r[2], 20, r[4]] for r in g_h[i][:npk_h[i]]]
+            top5.append(rows)
+            top1.append(rows[:1])  # the greedy peak order does not depend on K: top-1 is the first of top-5
+    idx = det_anchor[:n].long()
+    return {
+        "cls": (det_class[:n].long() + 1).cpu().numpy(),
+        "bboxes": boxes[idx].cpu().numpy() * np.array([ori_w, ori_w, ori_w, ori_w]),
+        "ins_masks": ins.cpu().numpy(),
+        "grasps_top1": top1,
+        "grasps_top5": top5,
+        "grasp_masks": (qua.cpu().numpy(), ang.cpu().numpy(), wid.cpu().numpy()),
+    }
+
+
+@torch.no_grad()
+def ssg_post_processing_batched(cfg, output_dict, ori_size=(480, 640)):
+    """Device-resident batched form used by the engine / benchmark: the per-image stages of ssg_post_processing for every
+    sample of a batch with ONE host synchronisation (the detection counts), nothing else leaving HBM.
+    Returns a list of per-sample dicts of CUDA tensors: n, cls, boxes, hr [5,n,H,W], n_peaks [n], grasps [n,5,5]."""
+    protos, cls, box = output_dict["protos"], output_dict["cls_pred"], output_dict["box_pred"]
+    coef, gco = output_dict["ins_coef_pred"], output_dict["grasp_coef_pred"]
+    dev = protos.device
+    anchors = _anchors_dev(output_dict["anchors"], dev)
+    B = protos.shape[0]
+    dets = [_ssg_detect(cfg, cls[b], box[b], anchors) for b in range(B)]
+    counts = torch.cat([d[1] for d in dets]).cpu().tolist()  # the one sync
+    out = []
+    for b in range(B):
+        boxes, _, det_anchor, det_class, det_score, _ = dets[b]
+        n = counts[b]
+        hr = ssg_masks_device(cfg, (protos[b], coef[b], gco[b]), boxes, det_anchor, n, ori_size)
+        if n > 0:
+            _, npk, grasps = detect_grasps_batched(hr[1], hr[2], hr[3], hr[4], 5)
+        else:
+            npk = torch.zeros((0,), dtype=torch.int32, device=dev)
+            grasps = torch.zeros((0, 5, 5), dtype=torch.float64, device=dev)
+        out.append({"n": n, "cls": det_class[:n] + 1, "boxes": boxes[det_anchor[:n].long()], "scores": det_score[:n], "hr": hr,
+                    "n_peaks": npk, "grasps": grasps})
+    return out

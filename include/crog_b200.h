@@ -32,7 +32,7 @@ enum {
   CROG_E_CUDA = -4,
 };
 enum { CROG_F32 = 0, CROG_BF16 = 1 };
-enum { CROG_ACT_NONE = 0, CROG_ACT_RELU = 1, CROG_ACT_QUICKGELU = 2 };
+enum { CROG_ACT_NONE = 0, CROG_ACT_RELU = 1, CROG_ACT_QUICKGELU = 2, CROG_ACT_TANH = 3 };
 enum { CROG_IMPL_AUTO = 0, CROG_IMPL_SIMT = 1, CROG_IMPL_TCGEN05 = 2 };
 
 const char* crog_last_error(void);
@@ -87,13 +87,18 @@ typedef struct CrogGemm {
   int32_t out_ld;
   int32_t out_dtype;      /* CROG_F32 | CROG_BF16 */
   int32_t impl;           /* CROG_IMPL_* */
+  int32_t out_sample_rows;/* compact output: rows per sample in the OUTPUT matrix (0: H*W). Lets several feature
+                             levels of one sample land back to back in one [B, sum_l H_l*W_l, N] tensor (torch.cat of
+                             model/ssg.py:266-269): pass `out` already offset to the level's first row. */
 } CrogGemm;
 int crog_gemm(const CrogGemm* g, void* stream);
 
 /* ------------------------------------------------------------------ layout / resampling
  * replaces: nn.AvgPool2d(2) (clip.py:23,35,184; layers.py:386), F.interpolate(scale_factor=2,
  * mode='bilinear') (layers.py:54,56,382,393), torch.cat along channels (writes a channel
- * slice: pass out already offset, out_ld = full width).  mode: 0 copy, 1 avgpool2, 2 bilinear x2. */
+ * slice: pass out already offset, out_ld = full width).  mode: 0 copy, 1 avgpool2, 2 bilinear x2 (align_corners=False),
+ * 3 x[::2, ::2] (the input side of a stride-2 1x1 convolution, model/ssg.py:80-81), 4 bilinear x2 with
+ * align_corners=True (nn.Upsample of model/ssg.py:159). */
 int crog_resample(const void* in, int32_t in_ld, int32_t in_padded, void* out, int32_t out_ld,
                   int32_t out_padded, int32_t B, int32_t H, int32_t W, int32_t C, int32_t mode,
                   int32_t dtype, void* stream);
@@ -172,6 +177,52 @@ int crog_angle_map(const float* sin_m, const float* cos_m, float* out, int64_t n
 int crog_jaccard(const double* grasps, const int32_t* n_peaks, int32_t K, double* gt, const int32_t* gt_count,
                  int32_t Mmax, int32_t B, int32_t* inter, int32_t* uni, int32_t* j_flags, int64_t* counters,
                  int32_t edit_gt, void* stream);
+
+/* ------------------------------------------------------------------ SSG (BASELINE config 4): model/ssg.py, grasp_eval.py:55-221
+ * 7x7 / stride 2 / pad 3 stem (model/ssg.py:65,217-222) as a patch gather: out [B*OH*OW, Kp] of out_dtype, column
+ * (ky*7+kx)*cin + c, zero padded to Kp; rgb [B,3,H,W] and depth [B,1,H,W] fp32 NCHW (depth may be NULL when cin == 3).
+ * The convolution itself is then crog_gemm on the patch matrix. */
+int crog_stem7_patches(const float* rgb, const float* depth, int32_t B, int32_t H, int32_t W, int32_t cin, int32_t Kp,
+                       void* out, int32_t out_dtype, void* stream);
+/* nn.MaxPool2d(kernel_size=3, stride=2, padding=1) on NHWC rows (model/ssg.py:67,101). */
+int crog_maxpool3s2(const void* in, int32_t in_ld, int32_t in_padded, void* out, int32_t out_ld, int32_t out_padded,
+                    int32_t B, int32_t H, int32_t W, int32_t C, int32_t dtype, void* stream);
+/* 3x3 / stride s / pad 1 patches of a zero-haloed NHWC tensor -> compact [B*OH*OW, 9*C] (tap-major), the A operand of
+ * the stride-2 3x3 convolutions (model/ssg.py:22,180-183). */
+int crog_patches3(const void* in, int32_t in_ld, void* out, int32_t B, int32_t H, int32_t W, int32_t C, int32_t stride,
+                  int32_t dtype, void* stream);
+/* Head finalisation (model/ssg.py:136-139,272-275): in fp32 [rows, ld] with columns [na*nc logits | na*4 box deltas];
+ * cls[rows*na, nc] = softmax over classes, box[rows*na, 4] = the deltas. */
+int crog_ssg_heads(const float* in, int32_t ld, int64_t rows, int32_t na, int32_t nc, float* cls, float* box, void* stream);
+
+/* Detection stage of ssg_post_processing for ONE image (grasp_eval.py:113-150 + fast_nms :55-93):
+ * keep[n] = max_{c>=1} cls[n,c] > score_thr; boxes[N,4] = decoded point-form boxes clipped to [0,1] (all anchors);
+ * per foreground class the top_k kept anchors by score (ties: lower anchor index), upper-triangular IoU suppression
+ * at iou_thr, then the max_det best survivors over all classes, and finally the score > score_thr2 filter (applied
+ * only if at least one detection passes, as in the reference).  Outputs (device): det_n, det_anchor[max_det],
+ * det_class[max_det] (0-based foreground class; the reference reports class + 1), det_score[max_det]. */
+int64_t crog_ssg_nms_workspace_bytes(int32_t num_classes, int32_t top_k);
+/* fast_nms alone (grasp_eval.py:55-93) on already decoded boxes: cls [N, num_classes] (column 0 = background, ignored),
+ * keep [N] (0/1 per anchor), boxes [N,4]; det_anchor indexes the N rows. */
+int crog_ssg_fast_nms(const float* cls, const int32_t* keep, const float* boxes, int32_t N, int32_t num_classes, float iou_thr,
+                      int32_t top_k, int32_t max_det, float score_thr2, int32_t* det_n, int32_t* det_anchor, int32_t* det_class,
+                      float* det_score, void* workspace, void* stream);
+int crog_ssg_detect(const float* cls, const float* box, const float* anchors, int32_t N, int32_t num_classes, float score_thr,
+                    float iou_thr, int32_t top_k, int32_t max_det, float score_thr2, int32_t* keep, float* boxes,
+                    int32_t* det_n, int32_t* det_anchor, int32_t* det_class, float* det_score, void* workspace, void* stream);
+/* Mask stage (grasp_eval.py:171-194): lowres[d][k] = crop(act_k(protos . coef_k(d))) for k = ins, qua, sin, cos, wid
+ * (sigmoid on ins / qua / wid), [max_det, 5, h, w]; out[k][d] = bilinear resize to resize_to^2 (align_corners=False)
+ * cropped to [out_h, out_w], map-major [5, max_det, out_h, out_w]; the instance plane is thresholded (> 0.5 -> 1.0).
+ * Only the first *det_n detections are written. */
+int crog_ssg_masks(const float* protos, int32_t h, int32_t w, int32_t num_protos, const float* coef, const float* gcoef,
+                   const float* boxes, const int32_t* det_anchor, const int32_t* det_n, int32_t max_det, float* lowres,
+                   float* out, int32_t out_h, int32_t out_w, int32_t resize_to, void* stream);
+/* skimage.filters.gaussian(map, sigma, preserve_range=True) of grasp_eval.py:198 = scipy.ndimage.gaussian_filter(mode='nearest'):
+ * separable (rows first), float64 accumulation in scipy's tap order, float32 result per pass.  weights_host: the 2*radius+1
+ * normalised float64 taps (HOST pointer; computed by the caller exactly as scipy does).  Planes smoothed:
+ * p * plane_stride + plane_sel for p < min(P, *n_planes) (n_planes may be NULL); tmp and out use the same layout; out may alias in. */
+int crog_gaussian(const float* in, float* tmp, float* out, int32_t P, int32_t H, int32_t W, const double* weights_host,
+                  int32_t radius, const int32_t* n_planes, int32_t plane_stride, int32_t plane_sel, void* stream);
 
 #ifdef __cplusplus
 }

@@ -29,7 +29,7 @@ def _rand(*shape, seed=0, scale=1.0):
 
 def test_library_and_device():
     lib = L.lib()
-    assert lib.crog_abi_version() == 1
+    assert lib.crog_abi_version() == 2
     assert lib.crog_check_device() == 0
 
 
