@@ -13,7 +13,7 @@ CSRC = os.path.join(PKG, "csrc")
 OUT_DIR = os.path.join(PKG, "lib")
 OBJ_DIR = os.path.join(OUT_DIR, "obj")
 SO_PATH = os.path.join(OUT_DIR, "libcrog_b200.so")
-SOURCES = ["api.cu", "gemm_simt.cu", "gemm_tc.cu", "elementwise.cu", "attention.cu", "attention_tc.cu", "tail.cu", "ssg.cu"]
+SOURCES = ["api.cu", "gemm_simt.cu", "gemm_tc.cu", "elementwise.cu", "attention.cu", "attention_tc.cu", "tail.cu", "ssg.cu", "warp.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--use_fast_math=false",
          "-Xcompiler", "-fPIC", "-Xptxas", "-v"]

@@ -1,5 +1,6 @@
 // C-ABI plumbing: error reporting, device check, GEMM dispatch, dtype cast.
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -16,6 +17,17 @@ void crog_set_error(const char* fmt, ...) {
 }
 
 extern "C" const char* crog_last_error(void) { return g_err; }
+
+bool crog_pdl_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    // measured on B200 (profiles/README.md, r1 log): with the forward replayed as a CUDA graph the programmatic edges
+    // cost 3 % (15.13 -> 15.65 ms/step), so the attribute is opt-in
+    const char* e = getenv("CROG_PDL");
+    on = (e && e[0] == '1') ? 1 : 0;
+  }
+  return on != 0;
+}
 extern "C" int crog_abi_version(void) { return 2; }
 
 extern "C" int crog_check_device(void) {
@@ -55,6 +67,8 @@ extern "C" int crog_gemm(const CrogGemm* g, void* stream) {
 namespace {
 template <typename TI, typename TO>
 __global__ void cast_kernel(const TI* __restrict__ in, TO* __restrict__ out, long long n) {
+  pdl_launch();
+  pdl_wait();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     out[i] = from_f<TO>(to_f(in[i]));
 }
@@ -65,10 +79,10 @@ extern "C" int crog_cast(const void* in, int32_t in_dtype, void* out, int32_t ou
   long long g = (n + 255) / 256;
   if (g > 148 * 16) g = 148 * 16;
   cudaStream_t s = (cudaStream_t)stream;
-  if (in_dtype == CROG_F32 && out_dtype == CROG_BF16) cast_kernel<float, bf16><<<(int)g, 256, 0, s>>>((const float*)in, (bf16*)out, n);
-  else if (in_dtype == CROG_BF16 && out_dtype == CROG_F32) cast_kernel<bf16, float><<<(int)g, 256, 0, s>>>((const bf16*)in, (float*)out, n);
-  else if (in_dtype == CROG_F32) cast_kernel<float, float><<<(int)g, 256, 0, s>>>((const float*)in, (float*)out, n);
-  else cast_kernel<bf16, bf16><<<(int)g, 256, 0, s>>>((const bf16*)in, (bf16*)out, n);
+  if (in_dtype == CROG_F32 && out_dtype == CROG_BF16) crog_launch(cast_kernel<float, bf16>, dim3((unsigned)g), dim3(256), 0, s, (const float*)in, (bf16*)out, (long long)n);
+  else if (in_dtype == CROG_BF16 && out_dtype == CROG_F32) crog_launch(cast_kernel<bf16, float>, dim3((unsigned)g), dim3(256), 0, s, (const bf16*)in, (float*)out, (long long)n);
+  else if (in_dtype == CROG_F32) crog_launch(cast_kernel<float, float>, dim3((unsigned)g), dim3(256), 0, s, (const float*)in, (float*)out, (long long)n);
+  else crog_launch(cast_kernel<bf16, bf16>, dim3((unsigned)g), dim3(256), 0, s, (const bf16*)in, (bf16*)out, (long long)n);
   CROG_LAUNCH_OK("cast");
   return CROG_OK;
 }

@@ -17,6 +17,8 @@ __global__ void __launch_bounds__(QB) attention_kernel(const T* __restrict__ q, 
   __shared__ float Ks[KT][HD];
   __shared__ float Vs[KT][HD];
   __shared__ int s_masked[KT];
+  pdl_launch();
+  pdl_wait();
   const int b = blockIdx.z, h = blockIdx.y;
   const int qi = blockIdx.x * QB + threadIdx.x;
   const bool qvalid = qi < Tq;
@@ -131,9 +133,9 @@ extern "C" int crog_attention(const void* q, int32_t ldq, const void* k, int32_t
     return crog_attention_tc(q, ldq, k, ldk, v, ldv, o, ldo, B, heads, Tq, Tk, scale, s);
   dim3 grid((Tq + QB - 1) / QB, heads, B);
   if (dtype == CROG_F32)
-    attention_kernel<float><<<grid, QB, 0, s>>>((const float*)q, ldq, (const float*)k, ldk, (const float*)v, ldv, (float*)o, ldo, Tq, Tk, scale, causal, pad_word);
+    crog_launch(attention_kernel<float>, grid, dim3(QB), 0, s, (const float*)q, ldq, (const float*)k, ldk, (const float*)v, ldv, (float*)o, ldo, Tq, Tk, scale, causal, pad_word);
   else
-    attention_kernel<bf16><<<grid, QB, 0, s>>>((const bf16*)q, ldq, (const bf16*)k, ldk, (const bf16*)v, ldv, (bf16*)o, ldo, Tq, Tk, scale, causal, pad_word);
+    crog_launch(attention_kernel<bf16>, grid, dim3(QB), 0, s, (const bf16*)q, ldq, (const bf16*)k, ldk, (const bf16*)v, ldv, (bf16*)o, ldo, Tq, Tk, scale, causal, pad_word);
   CROG_LAUNCH_OK("attention");
   return CROG_OK;
 }

@@ -31,6 +31,7 @@ __global__ void __launch_bounds__(192, 2) attention_tc_kernel(const __grid_const
   const uint32_t b_qfull = smem_u32(bars + 0), b_kfull = smem_u32(bars + 1), b_vfull = smem_u32(bars + 2),
                  b_kempty = smem_u32(bars + 3), b_vempty = smem_u32(bars + 4), b_sfull = smem_u32(bars + 5),
                  b_pfull = smem_u32(bars + 6), b_ofull = smem_u32(bars + 7);
+  pdl_launch();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * QT, h = blockIdx.y, b = blockIdx.z;
   const int ntiles = (Tk + KT - 1) / KT;
@@ -46,6 +47,7 @@ __global__ void __launch_bounds__(192, 2) attention_tc_kernel(const __grid_const
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+  pdl_wait();
   const uint32_t sQ = smem_u32(smem + SM_Q), sK = smem_u32(smem + SM_K), sV = smem_u32(smem + SM_V), sP = smem_u32(smem + SM_P);
 
   if (warp == 0) {
@@ -189,7 +191,7 @@ int crog_attention_tc(const void* q, int ldq, const void* k, int ldk, const void
   rc = crog_encode_2d_bf16(&tmV, v, (uint64_t)heads * HD, (uint64_t)B * Tk, (uint64_t)ldv, KT);
   if (rc) return rc;
   dim3 grid((Tq + QT - 1) / QT, heads, B);
-  attention_tc_kernel<<<grid, 192, SM_TOTAL, stream>>>(tmQ, tmK, tmV, (bf16*)o, ldo, Tq, Tk, scale * 1.4426950408889634f);
+  crog_launch(attention_tc_kernel, grid, dim3(192), SM_TOTAL, stream, tmQ, tmK, tmV, (bf16*)o, ldo, Tq, Tk, scale * 1.4426950408889634f);
   CROG_LAUNCH_OK("attention_tc");
   return CROG_OK;
 }

@@ -33,6 +33,27 @@ void crog_set_error(const char* fmt, ...);
 
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
+// ---------------------------------------------------------------- programmatic dependent launch (PDL)
+// With CROG_PDL=1 every kernel of the forward is launched with programmatic stream serialization (off by default: it
+// measured slower under graph replay): it may become resident while its predecessor drains, runs its prologue (barrier init, TMEM allocation, descriptor prefetch, index math) and then
+// blocks in pdl_wait() until the predecessor grid has completed and its writes are visible.  pdl_launch() at the top
+// of a kernel lets ITS successor do the same.  Under stream capture these become programmatic graph edges.
+// Rule: no global-memory access that depends on (or is depended on by) an earlier kernel before pdl_wait().
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+bool crog_pdl_enabled();  // CROG_PDL=1 turns the launch attribute on (without it the device-side instructions are no-ops)
+template <typename... KA, typename... A>
+static inline cudaError_t crog_launch(void (*kernel)(KA...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, A&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = crog_pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KA>(args)...);
+}
+
 // ---------------------------------------------------------------- 8-wide vector access
 __device__ __forceinline__ void load8(const float* p, float (&v)[8]) {
   float4 a = *reinterpret_cast<const float4*>(p);

@@ -15,6 +15,8 @@ __device__ __forceinline__ long long pix_row(int b, int y, int x, int H, int W, 
 template <typename T, int MODE>
 __global__ void __launch_bounds__(256) resample_kernel(const T* __restrict__ in, int in_ld, int in_padded, T* __restrict__ out,
                                                        int out_ld, int out_padded, int B, int H, int W, int C) {
+  pdl_launch();
+  pdl_wait();
   const int OH = MODE == 1 ? H / 2 : (MODE == 2 ? 2 * H : H);
   const int OW = MODE == 1 ? W / 2 : (MODE == 2 ? 2 * W : W);
   const int cgs = C / 8;
@@ -74,12 +76,14 @@ __global__ void stem_conv1_kernel(const float* __restrict__ img, int B, int Hin,
                                   const float* __restrict__ scale, const float* __restrict__ bias, int cout,
                                   T* __restrict__ out, int out_ld) {
   extern __shared__ __align__(16) float sw[];  // [27][cout] + scale + bias
+  pdl_launch();  // the weights below are constants of the plan: staging them overlaps the predecessor's tail
   for (int i = threadIdx.x; i < 27 * cout; i += blockDim.x) {
     const int co = i % cout, k = i / cout;
     sw[i] = w[co * 27 + k];
   }
   for (int i = threadIdx.x; i < cout; i += blockDim.x) { sw[27 * cout + i] = scale[i]; sw[28 * cout + i] = bias[i]; }
   __syncthreads();
+  pdl_wait();
   const int OH = Hin / 2, OW = Win / 2;
   const long long total = (long long)B * OH * OW;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -123,6 +127,8 @@ template <typename TI, typename TO, int CH>  // D = CH * 256
 __global__ void layernorm_kernel(const TI* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
                                  const float* __restrict__ residual, TO* __restrict__ out, long long rows, float eps) {
   constexpr int D = CH * 256;
+  pdl_launch();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const long long row = blockIdx.x * (long long)(blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -160,6 +166,8 @@ __global__ void layernorm_kernel(const TI* __restrict__ x, const float* __restri
 // ------------------------------------------------------------------ text embedding / EOT gather
 __global__ void embed_kernel(const int64_t* __restrict__ word, const float* __restrict__ emb, const float* __restrict__ pos,
                              float* __restrict__ out, int B, int L, int D) {
+  pdl_launch();
+  pdl_wait();
   const int row = blockIdx.x, l = row % L;
   const long long id = word[row];
   for (int c = threadIdx.x * 4; c < D; c += blockDim.x * 4) {
@@ -171,6 +179,8 @@ __global__ void embed_kernel(const int64_t* __restrict__ word, const float* __re
 
 template <typename TI, typename TO>
 __global__ void gather_eot_kernel(const int64_t* __restrict__ word, const TI* __restrict__ x, TO* __restrict__ out, int L, int D) {
+  pdl_launch();
+  pdl_wait();
   const int b = blockIdx.x;
   __shared__ int s_arg;
   if (threadIdx.x == 0) {
@@ -187,6 +197,8 @@ __global__ void gather_eot_kernel(const int64_t* __restrict__ word, const TI* __
 template <typename T>
 __global__ void txt_linear_kernel(const T* __restrict__ state, const float* __restrict__ w, const float* __restrict__ bias,
                                   float* __restrict__ out, int B, int K, int O) {
+  pdl_launch();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const long long wid = blockIdx.x * (long long)(blockDim.x >> 5) + (threadIdx.x >> 5);
   if (wid >= (long long)B * O) return;
@@ -200,6 +212,8 @@ __global__ void txt_linear_kernel(const T* __restrict__ state, const float* __re
 template <typename T>
 __global__ void dynw_fold_kernel(const float* __restrict__ t, const float* __restrict__ vw, const float* __restrict__ vb,
                                  T* __restrict__ wfold, int B, int C, int NH, int rows_per_sample, int Cpad) {
+  pdl_launch();
+  pdl_wait();
   // one block per (b, h, tap); threads over j.  Output row of sample b: h*9 + tap.
   const int tap = blockIdx.x % 9, h = (blockIdx.x / 9) % NH, b = blockIdx.x / (9 * NH);
   const int O = 9 * C + 1;
@@ -222,6 +236,8 @@ __global__ void dynw_fold_kernel(const float* __restrict__ t, const float* __res
 // out[h][b, y, x] = sum_tap Z[padded_row(b, y+ky-1, x+kx-1), h*9 + tap]: the nine shifted reads of the per-tap partial
 // products that the per-sample 1x1 GEMM left in the zero-haloed Z matrix.
 __global__ void dynconv_gather_kernel(const float* __restrict__ z, int ldz, float* __restrict__ out, int B, int H, int W, int NH) {
+  pdl_launch();
+  pdl_wait();
   const long long total = (long long)B * H * W;
   const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (i >= total) return;
@@ -355,7 +371,7 @@ extern "C" int crog_resample(const void* in, int32_t in_ld, int32_t in_padded, v
   if ((long long)B * OH * OW * C == 0) return CROG_OK;
   const int g = B * OH;
   cudaStream_t s = (cudaStream_t)stream;
-#define RS(T, M) resample_kernel<T, M><<<g, 256, 0, s>>>((const T*)in, in_ld, in_padded, (T*)out, out_ld, out_padded, B, H, W, C)
+#define RS(T, M) crog_launch(resample_kernel<T, M>, dim3(g), dim3(256), 0, s, (const T*)in, in_ld, in_padded, (T*)out, out_ld, out_padded, B, H, W, C)
   if (dtype == CROG_F32) { if (mode == 0) RS(float, 0); else if (mode == 1) RS(float, 1); else RS(float, 2); }
   else { if (mode == 0) RS(bf16, 0); else if (mode == 1) RS(bf16, 1); else RS(bf16, 2); }
 #undef RS
@@ -371,9 +387,9 @@ extern "C" int crog_stem_conv1(const float* img, int32_t B, int32_t Hin, int32_t
   const int g = grid_for(total, 128);
   const size_t sm = (size_t)(29 * cout) * sizeof(float);
   if (out_dtype == CROG_F32)
-    stem_conv1_kernel<float><<<g, 128, sm, (cudaStream_t)stream>>>(img, B, Hin, Win, w, scale, bias, cout, (float*)out, out_ld);
+    crog_launch(stem_conv1_kernel<float>, dim3(g), dim3(128), sm, (cudaStream_t)stream, img, B, Hin, Win, w, scale, bias, cout, (float*)out, out_ld);
   else
-    stem_conv1_kernel<bf16><<<g, 128, sm, (cudaStream_t)stream>>>(img, B, Hin, Win, w, scale, bias, cout, (bf16*)out, out_ld);
+    crog_launch(stem_conv1_kernel<bf16>, dim3(g), dim3(128), sm, (cudaStream_t)stream, img, B, Hin, Win, w, scale, bias, cout, (bf16*)out, out_ld);
   CROG_LAUNCH_OK("stem_conv1");
   return CROG_OK;
 }
@@ -385,7 +401,7 @@ extern "C" int crog_layernorm(const void* x, int32_t x_dtype, const float* gamma
   const int wpb = 8;
   const int g = (int)((rows + wpb - 1) / wpb);
   cudaStream_t s = (cudaStream_t)stream;
-#define LN(TI, TO, CH) layernorm_kernel<TI, TO, CH><<<g, wpb * 32, 0, s>>>((const TI*)x, gamma, beta, residual, (TO*)out, rows, eps)
+#define LN(TI, TO, CH) crog_launch(layernorm_kernel<TI, TO, CH>, dim3(g), dim3(wpb * 32), 0, s, (const TI*)x, gamma, beta, residual, (TO*)out, (long long)rows, eps)
 #define LN_D(TI, TO) do { if (D == 256) LN(TI, TO, 1); else if (D == 512) LN(TI, TO, 2); else if (D == 1024) LN(TI, TO, 4); else LN(TI, TO, 8); } while (0)
   if (x_dtype == CROG_F32 && out_dtype == CROG_F32) LN_D(float, float);
   else if (x_dtype == CROG_F32) LN_D(float, bf16);
@@ -401,7 +417,7 @@ extern "C" int crog_embed_tokens(const int64_t* word, const float* emb, const fl
                                  int32_t D, void* stream) {
   CROG_REQUIRE(D % 4 == 0, CROG_E_BADSHAPE, "embed: D %% 4");
   if (B * L == 0) return CROG_OK;
-  embed_kernel<<<B * L, 128, 0, (cudaStream_t)stream>>>(word, emb, pos, out, B, L, D);
+  crog_launch(embed_kernel, dim3(B * L), dim3(128), 0, (cudaStream_t)stream, word, emb, pos, out, B, L, D);
   CROG_LAUNCH_OK("embed");
   return CROG_OK;
 }
@@ -410,10 +426,10 @@ extern "C" int crog_gather_eot(const int64_t* word, const void* x, int32_t x_dty
                                int32_t L, int32_t D, void* stream) {
   if (B == 0) return CROG_OK;
   cudaStream_t s = (cudaStream_t)stream;
-  if (x_dtype == CROG_F32 && out_dtype == CROG_F32) gather_eot_kernel<float, float><<<B, 128, 0, s>>>(word, (const float*)x, (float*)out, L, D);
-  else if (x_dtype == CROG_F32) gather_eot_kernel<float, bf16><<<B, 128, 0, s>>>(word, (const float*)x, (bf16*)out, L, D);
-  else if (out_dtype == CROG_F32) gather_eot_kernel<bf16, float><<<B, 128, 0, s>>>(word, (const bf16*)x, (float*)out, L, D);
-  else gather_eot_kernel<bf16, bf16><<<B, 128, 0, s>>>(word, (const bf16*)x, (bf16*)out, L, D);
+  if (x_dtype == CROG_F32 && out_dtype == CROG_F32) crog_launch(gather_eot_kernel<float, float>, dim3(B), dim3(128), 0, s, word, (const float*)x, (float*)out, L, D);
+  else if (x_dtype == CROG_F32) crog_launch(gather_eot_kernel<float, bf16>, dim3(B), dim3(128), 0, s, word, (const float*)x, (bf16*)out, L, D);
+  else if (out_dtype == CROG_F32) crog_launch(gather_eot_kernel<bf16, float>, dim3(B), dim3(128), 0, s, word, (const bf16*)x, (float*)out, L, D);
+  else crog_launch(gather_eot_kernel<bf16, bf16>, dim3(B), dim3(128), 0, s, word, (const bf16*)x, (bf16*)out, L, D);
   CROG_LAUNCH_OK("gather_eot");
   return CROG_OK;
 }
@@ -427,12 +443,12 @@ extern "C" int crog_dynw_fold(const void* state, int32_t state_dtype, const floa
   const int O = 9 * C + 1;
   const long long warps = (long long)B * O;
   const int g1 = (int)((warps + 7) / 8);
-  if (state_dtype == CROG_F32) txt_linear_kernel<float><<<g1, 256, 0, s>>>((const float*)state, txt_w, txt_b, scratch, B, word_dim, O);
-  else txt_linear_kernel<bf16><<<g1, 256, 0, s>>>((const bf16*)state, txt_w, txt_b, scratch, B, word_dim, O);
+  if (state_dtype == CROG_F32) crog_launch(txt_linear_kernel<float>, dim3(g1), dim3(256), 0, s, (const float*)state, txt_w, txt_b, scratch, B, word_dim, O);
+  else crog_launch(txt_linear_kernel<bf16>, dim3(g1), dim3(256), 0, s, (const bf16*)state, txt_w, txt_b, scratch, B, word_dim, O);
   CROG_LAUNCH_OK("txt_linear");
   const int g2 = B * NH * 9;
-  if (dtype == CROG_F32) dynw_fold_kernel<float><<<g2, 128, C * sizeof(float), s>>>(scratch, v_w, v_b, (float*)wfold, B, C, NH, NH_pad, Cpad);
-  else dynw_fold_kernel<bf16><<<g2, 128, C * sizeof(float), s>>>(scratch, v_w, v_b, (bf16*)wfold, B, C, NH, NH_pad, Cpad);
+  if (dtype == CROG_F32) crog_launch(dynw_fold_kernel<float>, dim3(g2), dim3(128), C * sizeof(float), s, scratch, v_w, v_b, (float*)wfold, B, C, NH, NH_pad, Cpad);
+  else crog_launch(dynw_fold_kernel<bf16>, dim3(g2), dim3(128), C * sizeof(float), s, scratch, v_w, v_b, (bf16*)wfold, B, C, NH, NH_pad, Cpad);
   CROG_LAUNCH_OK("dynw_fold");
   return CROG_OK;
 }
@@ -440,7 +456,7 @@ extern "C" int crog_dynw_fold(const void* state, int32_t state_dtype, const floa
 extern "C" int crog_dynconv_gather(const float* z, int32_t ldz, float* out, int32_t B, int32_t H, int32_t W, int32_t NH, void* stream) {
   const long long total = (long long)B * H * W;
   if (total == 0) return CROG_OK;
-  dynconv_gather_kernel<<<(int)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(z, ldz, out, B, H, W, NH);
+  crog_launch(dynconv_gather_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, (cudaStream_t)stream, z, ldz, out, B, H, W, NH);
   CROG_LAUNCH_OK("dynconv_gather");
   return CROG_OK;
 }

@@ -71,6 +71,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::BAR_OFF);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L::BAR_OFF + L::NBARS * 8);
 
+  pdl_launch();  // the successor may start its prologue as soon as this grid is resident
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int kchunks = g.cin / BK;
   const int num_kb = CONV3 ? 3 : g.taps * kchunks;  // CONV3: one k-block per ky band
@@ -96,6 +97,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();  // everything above overlapped the predecessor's tail; its outputs are visible from here on
 
   if (warp == 0) {
     if (lane == 0) {
@@ -460,7 +462,7 @@ int launch(const CrogGemm* g, cudaStream_t stream) {
   const int total = num_m_tiles(*g, BM) * n_tiles;
   if (total == 0) return CROG_OK;
   const int grid = total < g_num_sms ? total : g_num_sms;
-  gemm_tc_kernel<BN, STAGES, NBUF, MODE, CONV3><<<grid, NUM_THREADS, L::TOTAL, stream>>>(tmA, tmB, tmOut, tmRes, *g, n_tiles, total);
+  crog_launch(gemm_tc_kernel<BN, STAGES, NBUF, MODE, CONV3>, dim3(grid), dim3(NUM_THREADS), L::TOTAL, stream, tmA, tmB, tmOut, tmRes, *g, n_tiles, total);
   CROG_LAUNCH_OK("gemm_tc");
   return CROG_OK;
 }

@@ -1,7 +1,9 @@
 """Device-resident restatement of the per-batch evaluation body of the reference engine,
-``engine/crog_engine.py:386-556`` (``inference_with_grasp``), for the synthetic-benchmark
-contract of SURVEY.md §8(d): maps are decoded at the network resolution (identity
-``ori_size``; the inverse letterbox warp is row f-1 of the scope table and not built yet).
+``engine/crog_engine.py:386-556`` (``inference_with_grasp``).  ``GraspEvaluator.step`` is the
+synthetic-benchmark contract of SURVEY.md §8(d) (maps decoded at the network resolution, identity
+``ori_size``); ``GraspEvaluator.step_original`` is the real pipeline, with the OpenCV-exact inverse
+letterbox warp to the original image size (row f-1) between the glue and the decode, plus the
+mask-IoU / Pr@K bookkeeping.
 
     model(img, word) -> sigmoid(mask, qua, wid) + bicubic x4 (align_corners=True)   [crog_engine.py:446-474]
                      -> detect_grasps(K=1 and K=5) per sample                      [:519-522]
@@ -20,6 +22,7 @@ import torch
 
 from . import _lib as L
 from .utils import grasp_eval as GE
+from .utils import warp as WP
 
 SIGMOID_PLANES = 0b10011  # mask, qua, wid get a sigmoid; sin, cos stay raw (crog_engine.py:446-448)
 
@@ -46,6 +49,41 @@ class GraspEvaluator:
         self.K = num_grasps
         dev = device or next(model.parameters()).device
         self.counters = torch.zeros(4, dtype=torch.int64, device=dev)
+        self.iou_list = []  # per-batch device tensors of mask IoU (crog_engine.py:518-519)
+
+    @torch.no_grad()
+    def step_original(self, img: torch.Tensor, word: torch.Tensor, gt: torch.Tensor, gt_count: torch.Tensor, inverse_mats,
+                      ori_size: Tuple[int, int], mask_target: Optional[torch.Tensor] = None, mask_thr: float = 0.35):
+        """crog_engine.py:429-527 for a batch whose images share one original size ``ori_size = (h, w)``:
+        ``inverse_mats`` are the dataset's ``inverse`` matrices (2x3, one or B of them), ``mask_target`` the
+        letterboxed GT masks [B,S,S] (optional).  All five maps are warped back with cv2.warpAffine semantics
+        (INTER_CUBIC, borderValue 0), the mask is thresholded at 0.35 for IoU, the other four are decoded.
+        Returns a dict: post [5,B,S,S], maps [5,B,h,w], iou [B] | None, peaks, n_peaks, grasps, j_flags."""
+        maps, _ = self.model(img, word)
+        post = postprocess(maps, (img.shape[-2], img.shape[-1]))
+        h, w = int(ori_size[0]), int(ori_size[1])
+        inv = WP.warp_affine_cubic(post, inverse_mats, (w, h), 0.0)
+        iou = None
+        if mask_target is not None:
+            tgt = WP.warp_affine_cubic(mask_target.reshape(mask_target.shape[0], mask_target.shape[-2], mask_target.shape[-1]),
+                                       inverse_mats, (w, h), 0.0)
+            iou, _ = WP.mask_iou(inv[0], tgt, mask_thr)
+            self.iou_list.append(iou)
+        peaks, n, grasps = GE.detect_grasps_batched(inv[1], inv[2], inv[3], inv[4], self.K)
+        flags = GE.jacquard_batched(grasps, n, gt, gt_count, counters=self.counters)
+        return {"post": post, "maps": inv, "iou": iou, "peaks": peaks, "n_peaks": n, "grasps": grasps, "j_flags": flags}
+
+    def summary(self):
+        """crog_engine.py:535-556: mean mask IoU, Pr@50..90 and J@1 / J@K over everything seen so far (this rank)."""
+        j1, jk = self.j_index()
+        out = {"J@1": j1, f"J@{self.K}": jk, "n": 0, "IoU": float("nan"), "Pr": {}}
+        if self.iou_list:
+            iou = torch.cat(self.iou_list)
+            out["n"], out["IoU"] = int(iou.numel()), float(iou.mean().item())
+            for t in range(5, 10):
+                thr = torch.arange(0.5, 1.0, 0.1)[t - 5].item()  # the reference's float32 thresholds (crog_engine.py:541)
+                out["Pr"][f"Pr@{t * 10}"] = float((iou > thr).float().mean().item())
+        return out
 
     @torch.no_grad()
     def step(self, img: torch.Tensor, word: torch.Tensor, gt: torch.Tensor, gt_count: torch.Tensor):

@@ -224,6 +224,23 @@ int crog_ssg_masks(const float* protos, int32_t h, int32_t w, int32_t num_protos
 int crog_gaussian(const float* in, float* tmp, float* out, int32_t P, int32_t H, int32_t W, const double* weights_host,
                   int32_t radius, const int32_t* n_planes, int32_t plane_stride, int32_t plane_sel, void* stream);
 
+/* ------------------------------------------------------------------ letterbox warps around the model (OpenCV-exact)
+ * cv2.warpAffine(src, M, (w,h), flags=cv2.INTER_CUBIC, borderValue=border_value) of engine/crog_engine.py:387-391,
+ * 499-517 (the inverse letterbox of the prediction / target maps), batched: src [NP][B][Hs][Ws] fp32 -> dst
+ * [NP][B][h][w] fp32.  minv [B,6] float64 = the ALREADY INVERTED 2x3 matrices (dst pixel -> src pixel; OpenCV inverts
+ * M itself when WARP_INVERSE_MAP is not passed - the host does that in float64, crog_b200/utils/warp.py).
+ * Bit-exact with OpenCV: 1/32-pixel fixed-point coordinates, float32 weight products and summation order. */
+int crog_warp_affine_cubic_f32(const float* src, int32_t NP, int32_t B, int32_t Hs, int32_t Ws, const double* minv,
+                               float* dst, int32_t h, int32_t w, float border_value, void* stream);
+/* utils/dataset.py:843-866: cv2.warpAffine(img_u8, mat, input_size, INTER_CUBIC, borderValue=border_rgb) then
+ * .float().div_(255.).sub_(mean).div_(std): img [B][Ho][Wo][3] uint8 RGB -> out [B][3][Sh][Sw] fp32.  minv as above;
+ * border_rgb (3 doubles), mean, std_ (3 floats each) are HOST pointers.  Bit-exact (int16 fixed-point weights). */
+int crog_preprocess_u8(const uint8_t* img, int32_t B, int32_t Ho, int32_t Wo, const double* minv, float* out, int32_t Sh,
+                       int32_t Sw, const double* border_rgb, const float* mean, const float* std_, void* stream);
+/* engine/crog_engine.py:500-501,515-518: per sample pixel counts of (pred > thr) & (target != 0) and (pred > thr) |
+ * (target != 0): counts [B,2] int64 = {inter, union} (zeroed by the call). */
+int crog_mask_iou(const float* pred, const float* target, int32_t B, int64_t n, float thr, int64_t* counts, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

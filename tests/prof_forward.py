@@ -19,6 +19,8 @@ img, word = synth.make_inputs(B, 17)
 plan = model.plan_for(B, 416)
 plan.img.copy_(img.cuda()); plan.word.copy_(word.cuda())
 torch.cuda.synchronize()
+torch.cuda.profiler.start()
 plan.run()
 torch.cuda.synchronize()
+torch.cuda.profiler.stop()
 print("ok", plan.n_launches)
