@@ -28,8 +28,6 @@ namespace {
 constexpr int BM = 128;
 constexpr int BK = 64;  // bf16 elements = 128 bytes = one SWIZZLE_128B atom row
 constexpr int UMMA_K = 16;
-constexpr int EPI_WARPS = 8;
-constexpr int NUM_THREADS = 64 + EPI_WARPS * 32;
 constexpr int STG_BUF = 4096;  // one staging tile: 32 rows x 128 bytes
 enum { MODE_LEGACY = 0, MODE_TMA_BF16 = 1, MODE_TMA_F32 = 2 };
 
@@ -37,8 +35,12 @@ enum { MODE_LEGACY = 0, MODE_TMA_BF16 = 1, MODE_TMA_F32 = 2 };
 // resident in shared memory, and a stage holds BM + 2 activation rows of one ky band, so the three kx taps are three
 // row-shifted views (descriptor start + kx * 128 B) of ONE TMA box: operand traffic from L2 drops from 9 x (A + B) to
 // 3 x A per tile.
-template <int BN, int STAGES, int NBUF, bool CONV3>
+// EPI_WARPS = 8: two independent 4-warp epilogue groups (group g drains tiles g, g+2, ...), for short contractions
+// where the epilogue is the pace; EPI_WARPS = 4: one group drains every tile (alternating accumulator buffers), which
+// frees 32 KB of staging for one more operand stage when the contraction is long and the TMA feed is the pace.
+template <int BN, int STAGES, int NBUF, bool CONV3, int EPI_WARPS>
 struct Cfg {
+  static constexpr int NUM_THREADS = 64 + EPI_WARPS * 32;
   static constexpr int A_ROWS = CONV3 ? BM + 2 : BM;
   static constexpr int A_TX = A_ROWS * BK * 2;                 // bytes one A box delivers
   static constexpr int A_BYTES = ((A_TX + 1023) / 1024) * 1024;
@@ -57,13 +59,14 @@ struct Cfg {
   static_assert(NBUF >= 2 && STG_WARP >= 32 * PITCH, "staging too small");
 };
 
-template <int BN, int STAGES, int NBUF, int MODE, bool CONV3>
-__global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
+template <int BN, int STAGES, int NBUF, int MODE, bool CONV3, int EPI_WARPS>
+__global__ void __launch_bounds__(64 + EPI_WARPS * 32, 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                    const __grid_constant__ CUtensorMap tmB,
                                                                    const __grid_constant__ CUtensorMap tmOut,
                                                                    const __grid_constant__ CUtensorMap tmRes,
                                                                    const CrogGemm g, int n_tiles, int total_tiles) {
-  using L = Cfg<BN, STAGES, NBUF, CONV3>;
+  using L = Cfg<BN, STAGES, NBUF, CONV3, EPI_WARPS>;
+  constexpr int GROUPS = EPI_WARPS / 4;
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment for SWIZZLE_128B tiles; plain pointer arithmetic keeps the shared address space so the
   // epilogue's staging accesses compile to LDS / STS instead of generic loads
@@ -175,11 +178,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
       }
     }
   } else {
-    const int ew = warp - 2;                 // 0..7
-    const int grp = ew >> 2;                 // accumulator buffer (= tile parity) this warp's group drains
+    const int ew = warp - 2;                 // 0..EPI_WARPS-1
+    const int grp = ew >> 2;                 // this warp's group drains tiles grp, grp + GROUPS, ... (buffer = tile parity)
     const int q = warp & 3;                  // TMEM lane quarter this warp may read
     uint8_t* stg = smem + L::STG_OFF + ew * L::STG_WARP;
-    const uint32_t tfull = tfull0 + 8 * grp, tempty = tempty0 + 8 * grp;
 
     if constexpr (MODE != MODE_LEGACY) {
       // ------------------------------------------------------------ TMA epilogue (identity row mapping)
@@ -201,19 +203,21 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
           tma_load_2d(stg_u32 + b * STG_BUF, &tmRes, n0 + pf_c * CW, row, rbar0 + 8 * b);
         }
         ++nld;
-        if (++pf_c == NCH || n0 + pf_c * CW >= g.N) { pf_c = 0; pf_i += 2; }
+        if (++pf_c == NCH || n0 + pf_c * CW >= g.N) { pf_c = 0; pf_i += GROUPS; }
       };
       if (has_res)
         for (int j = 0; j < NBUF - 1; ++j) issue_prefetch();
-      for (int i = grp;; i += 2) {
+      for (int i = grp;; i += GROUPS) {
         const int tile = blockIdx.x + i * (int)gridDim.x;
         if (tile >= total_tiles) break;
+        const int buf = i & 1;
+        const uint32_t tfull = tfull0 + 8 * buf, tempty = tempty0 + 8 * buf;
         const int n0 = (tile % n_tiles) * BN, row0 = (tile / n_tiles) * BM;
         const RowMap m = map_row(g, (long long)row0 + q * 32 + lane, g.M);
         const int nvc = min(NCH, (g.N - n0 + CW - 1) / CW);  // chunks with at least one real column
         mbar_wait(tfull, (i >> 1) & 1);
         tc_fence_after();
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + grp * BN;
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN;
         for (int c = 0; c < nvc; ++c) {
           float acc[CW];
 #pragma unroll
@@ -311,9 +315,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
       constexpr int RPP = 32 / UPR;            // rows written per warp pass
       constexpr int PASSES = 32 / RPP;
       const int u = lane % UPR, rsub = lane / UPR;
-      for (int i = grp;; i += 2) {
+      for (int i = grp;; i += GROUPS) {
         const int tile = blockIdx.x + i * (int)gridDim.x;
         if (tile >= total_tiles) break;
+        const int buf = i & 1;
+        const uint32_t tfull = tfull0 + 8 * buf, tempty = tempty0 + 8 * buf;
         const int n_t = tile % n_tiles, m_t = tile / n_tiles;
         const TileRows tr = tile_rows(g, m_t, BM);
         const int n0 = n_t * BN;
@@ -325,7 +331,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
         const int nvs = min(NSUB, (g.N - n0 + SUB - 1) / SUB);
         mbar_wait(tfull, (i >> 1) & 1);
         tc_fence_after();
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + grp * BN;
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN;
         for (int sbi = 0; sbi < nvs; ++sbi) {
           const int cbase = sbi * SUB;
           // ---- phase 1: accumulator -> registers -> epilogue math -> fp32 staging (thread = row)
@@ -426,16 +432,16 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
 // ---------------------------------------------------------------- host side
 int g_num_sms = 0;
 
-template <int BN, int STAGES, int NBUF, int MODE, bool CONV3 = false>
+template <int BN, int STAGES, int NBUF, int MODE, bool CONV3 = false, int EPI_WARPS = 8>
 int launch(const CrogGemm* g, cudaStream_t stream) {
-  using L = Cfg<BN, STAGES, NBUF, CONV3>;
+  using L = Cfg<BN, STAGES, NBUF, CONV3, EPI_WARPS>;
   static_assert(L::TOTAL <= 227 * 1024, "shared memory budget");
   static bool attr_set = false;  // per-process; device attribute is re-set cheaply if another device is used
   static int attr_dev = -1;
   int dev = 0;
   CROG_CUDA_OK(cudaGetDevice(&dev));
   if (!attr_set || attr_dev != dev) {
-    CROG_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES, NBUF, MODE, CONV3>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+    CROG_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES, NBUF, MODE, CONV3, EPI_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
     CROG_CUDA_OK(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
     attr_set = true; attr_dev = dev;
   }
@@ -462,7 +468,7 @@ int launch(const CrogGemm* g, cudaStream_t stream) {
   const int total = num_m_tiles(*g, BM) * n_tiles;
   if (total == 0) return CROG_OK;
   const int grid = total < g_num_sms ? total : g_num_sms;
-  crog_launch(gemm_tc_kernel<BN, STAGES, NBUF, MODE, CONV3>, dim3(grid), dim3(NUM_THREADS), L::TOTAL, stream, tmA, tmB, tmOut, tmRes, *g, n_tiles, total);
+  crog_launch(gemm_tc_kernel<BN, STAGES, NBUF, MODE, CONV3, EPI_WARPS>, dim3(grid), dim3(L::NUM_THREADS), L::TOTAL, stream, tmA, tmB, tmOut, tmRes, *g, n_tiles, total);
   CROG_LAUNCH_OK("gemm_tc");
   return CROG_OK;
 }
@@ -474,7 +480,12 @@ int dispatch(const CrogGemm* g, cudaStream_t stream) {
   if (g->N <= 64) return launch<64, 5, 3, MODE>(g, stream);
   // 128 x 256 tiles cut the L2 -> smem operand traffic per FLOP by 25 % ((BM+BN)/(BM*BN)); worth it when the
   // contraction is long enough to be tensor/L2 bound rather than epilogue bound
-  if (g->N % 256 == 0 && (long long)g->taps * g->cin >= 1024) return launch<256, 3, 2, MODE>(g, stream);
+  if (g->N % 256 == 0 && (long long)g->taps * g->cin >= 1024) {
+    // long contractions: the TMA feed is the pace (96 B/clk/SM at full tensor rate), so a fourth 48 KB stage in flight
+    // is worth more than a second epilogue group
+    if (((long long)g->taps * g->cin >= 2048 || getenv("CROG_GEMM_4STAGE_ALL")) && !getenv("CROG_GEMM_3STAGE")) return launch<256, 4, 2, MODE, false, 4>(g, stream);
+    return launch<256, 3, 2, MODE>(g, stream);
+  }
   return launch<128, 4, 3, MODE>(g, stream);
 }
 

@@ -12,13 +12,15 @@
 //                         128 x 160-bit row masks in shared memory, popc(A&B) / popc(A|B), J flags,
 //                         counters accumulated with one atomicAdd per sample.
 #include <math.h>
+#include <stdlib.h>
 
-#include "common.cuh"
+#include "tc_common.cuh"
 #include "tail_geom.h"
 
 namespace {
 
-constexpr int BAND = 32;       // output rows per CTA band
+constexpr int BAND_SMALL = 32; // output rows per CTA band when few maps must fill the GPU
+constexpr int BAND_LARGE = 104; // ... and when there are plenty (4 halo rows per band: 3.8 % instead of 12.5 % re-read)
 constexpr int STRIP = 120;     // columns owned per warp (30 lanes x 4; lanes 0 and 31 carry the halo)
 constexpr int CAPW = 512;      // per-warp candidate list capacity
 constexpr int TSEL = 32;       // keys kept per warp segment
@@ -28,8 +30,8 @@ struct SegHeader {
   int count;
   int truncated;
   unsigned long long worst_kept;  // valid when truncated
-  float vmin, vmax;
-  int pad[2];
+  int nonconst;                   // some owned pixel differs from pixel (0,0): the map is not "trivial" (A.1 step 2)
+  int pad[3];
 };
 constexpr int SEG_BYTES = (int)sizeof(SegHeader) + TSEL * 8;
 
@@ -72,8 +74,8 @@ __device__ void warp_select_top(unsigned long long* list, int n, int keep, unsig
 // Lanes 1..30 of a warp own 4 columns each (a 120-column strip); lanes 0 and 31 load the 4 columns on either side and
 // only feed their neighbours through shuffles, so no lane needs extra halo loads.  Rows are software-pipelined five at a
 // time (the next five float4 loads are in flight while the current five are processed).
-__global__ void __launch_bounds__(256, 2) peak_scan_kernel(const float* __restrict__ q, int H, int W, float thr, int nwarps,
-                                                        uint8_t* __restrict__ ws) {
+__global__ void __launch_bounds__(256, 2) peak_scan_generic_kernel(const float* __restrict__ q, int H, int W, float thr, int nwarps,
+                                                                int BAND, uint8_t* __restrict__ ws) {
   extern __shared__ unsigned long long s_lists[];  // [warps][CAPW + TSEL]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp >= nwarps) return;
@@ -106,7 +108,8 @@ __global__ void __launch_bounds__(256, 2) peak_scan_kernel(const float* __restri
 #pragma unroll
   for (int u = 0; u < 5; ++u) { raw[u] = make_float4(NEG, NEG, NEG, NEG); hm[u] = raw[u]; cur[u] = load_row(y0 - 2 + u); }
   int count = 0, truncated = 0;
-  float vmin = INFINITY, vmax = -INFINITY;
+  const float p0 = __ldg(img);
+  int nonconst = 0;
 
   for (int rbase = y0 - 2; rbase < y1 + 2; rbase += 5) {
     float4 nxt[5];
@@ -120,10 +123,10 @@ __global__ void __launch_bounds__(256, 2) peak_scan_kernel(const float* __restri
       const float l2 = __shfl_up_sync(0xffffffffu, v.z, 1), l1 = __shfl_up_sync(0xffffffffu, v.w, 1);
       const float r1 = __shfl_down_sync(0xffffffffu, v.x, 1), r2 = __shfl_down_sync(0xffffffffu, v.y, 1);
       if (owner && r >= y0 && r < y1) {  // strip min/max over owned pixels (trivial-image test)
-        if (c0 < W) { vmin = fminf(vmin, v.x); vmax = fmaxf(vmax, v.x); }
-        if (c0 + 1 < W) { vmin = fminf(vmin, v.y); vmax = fmaxf(vmax, v.y); }
-        if (c0 + 2 < W) { vmin = fminf(vmin, v.z); vmax = fmaxf(vmax, v.z); }
-        if (c0 + 3 < W) { vmin = fminf(vmin, v.w); vmax = fmaxf(vmax, v.w); }
+        if (c0 < W) nonconst |= v.x != p0;
+        if (c0 + 1 < W) nonconst |= v.y != p0;
+        if (c0 + 2 < W) nonconst |= v.z != p0;
+        if (c0 + 3 < W) nonconst |= v.w != p0;
       }
       const float mxyz = max3(v.x, v.y, v.z), myzw = max3(v.y, v.z, v.w);
       raw[u] = v;
@@ -164,13 +167,168 @@ __global__ void __launch_bounds__(256, 2) peak_scan_kernel(const float* __restri
   }
   __syncwarp();
   if (count > TSEL) { warp_select_top(list, count, TSEL, top, lane); count = TSEL; truncated = 1; }
-  vmin = -warp_max(-vmin); vmax = warp_max(vmax);
+  nonconst = __any_sync(0xffffffffu, nonconst);
   uint8_t* seg = ws + ((long long)(b * nbands + band) * nwarps + warp) * SEG_BYTES;
   if (lane == 0) {
     SegHeader h;
     h.count = count; h.truncated = truncated;
     h.worst_kept = truncated ? list[TSEL - 1] : 0ull;
-    h.vmin = vmin; h.vmax = vmax; h.pad[0] = h.pad[1] = 0;
+    h.nonconst = nonconst; h.pad[0] = h.pad[1] = h.pad[2] = 0;
+    *reinterpret_cast<SegHeader*>(seg) = h;
+  }
+  unsigned long long* keys = reinterpret_cast<unsigned long long*>(seg + sizeof(SegHeader));
+  for (int i = lane; i < count; i += 32) keys[i] = list[i];
+}
+
+
+// Fast path (W % 4 == 0): bulk-copy staged.  A CTA owns a full-width band of rows, which is one contiguous byte
+// range of the map, so a dedicated producer warp streams it into a shared-memory ring with cp.async.bulk
+// (SCAN_R rows per stage, SCAN_NST stages, mbarrier complete_tx / empty handshakes) — ~100 KB in flight per SM
+// without spending registers on prefetch — and the consumer warps (one 120-column strip each) run the lean filter:
+//  * Emitted centres lie in rows [2, H-2) x columns [2, W-2), so no emitted 5x5 window ever leaves the map: the scan
+//    never visits out-of-range rows, and lanes whose columns are out of range read a clamped (valid) column.
+//  * A band visits rows [lo-2, hi+2) for its centre rows [lo, hi): four warm-up rows fill the register ring, every
+//    later row emits, so the steady-state row has no row-range test; the column tests are folded into per-lane
+//    thresholds (+inf for columns that may not emit).
+//  * Per lane-row (4 pixels): one LDS.128, four shuffles, six FMNMX3 for the horizontal maxima, eight for the
+//    vertical ones, eight compares, one vote.
+//  * The "trivial image" rule (A.1 step 2) costs nothing unless the map's four probe pixels are equal (TRACK).
+constexpr int SCAN_R = 5;    // rows per stage (= ring length, so ring slots are compile-time)
+constexpr int SCAN_NST = 4;  // stages
+
+__device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(bar) : "memory");
+}
+
+template <bool TRACK>
+__device__ __forceinline__ void scan_rows(const float* stage0, uint32_t full0, uint32_t empty0, int W, int row0, int nrows, int y0,
+                                          int y1, int ccol, int c0, bool owner, float tx, float ty, float tz, float tw, float p0,
+                                          int lane, unsigned long long* list, unsigned long long* top, int& count,
+                                          int& truncated, int& nonconst) {
+  const float NEG = -INFINITY;
+  float4 raw[5], hm[5];
+#pragma unroll
+  for (int u = 0; u < 5; ++u) { raw[u] = make_float4(NEG, NEG, NEG, NEG); hm[u] = raw[u]; }
+  const int nst = (nrows + SCAN_R - 1) / SCAN_R;
+  for (int k = 0; k < nst; ++k) {
+    const int s = k % SCAN_NST;
+    mbar_wait(full0 + 8 * s, (k / SCAN_NST) & 1);
+    const float* srow = stage0 + (long long)s * SCAN_R * W + ccol;
+#pragma unroll
+    for (int u = 0; u < SCAN_R; ++u) {
+      const int idx = k * SCAN_R + u;
+      if (idx >= nrows) break;  // warp-uniform
+      const float4 v = *reinterpret_cast<const float4*>(srow + u * W);
+      const float l2 = __shfl_up_sync(0xffffffffu, v.z, 1), l1 = __shfl_up_sync(0xffffffffu, v.w, 1);
+      const float r1 = __shfl_down_sync(0xffffffffu, v.x, 1), r2 = __shfl_down_sync(0xffffffffu, v.y, 1);
+      if (TRACK) {
+        const int r = row0 + idx;
+        if (owner && r >= y0 && r < y1) nonconst |= (v.x != p0) | (v.y != p0) | (v.z != p0) | (v.w != p0);
+      }
+      const float mxyz = max3(v.x, v.y, v.z), myzw = max3(v.y, v.z, v.w);
+      raw[u] = v;
+      hm[u] = make_float4(max3(mxyz, l2, l1), max3(mxyz, l1, v.w), max3(myzw, v.x, r1), max3(myzw, r1, r2));
+      if (idx >= 4) {  // warp-uniform; false only for the four warm-up rows
+        const float4 ctr = raw[(u + 3) % 5];  // centre row = this row - 2
+        // threshold first: the vertical maxima are only needed for strips that hold an above-threshold pixel
+        const bool a0 = ctr.x > tx, a1 = ctr.y > ty, a2 = ctr.z > tz, a3 = ctr.w > tw;
+        if (!__any_sync(0xffffffffu, a0 | a1 | a2 | a3)) continue;
+        const float vx = max3(max3(hm[0].x, hm[1].x, hm[2].x), hm[3].x, hm[4].x);
+        const float vy = max3(max3(hm[0].y, hm[1].y, hm[2].y), hm[3].y, hm[4].y);
+        const float vz = max3(max3(hm[0].z, hm[1].z, hm[2].z), hm[3].z, hm[4].z);
+        const float vw = max3(max3(hm[0].w, hm[1].w, hm[2].w), hm[3].w, hm[4].w);
+        const bool k0 = a0 && ctr.x == vx, k1 = a1 && ctr.y == vy;
+        const bool k2 = a2 && ctr.z == vz, k3 = a3 && ctr.w == vw;
+        if (__any_sync(0xffffffffu, k0 | k1 | k2 | k3)) {
+          if (count + 128 > CAPW) {  // make room: keep the best TSEL so far
+            __syncwarp();
+            warp_select_top(list, count, TSEL, top, lane);
+            count = TSEL; truncated = 1;
+          }
+          const uint32_t lt = (1u << lane) - 1u;
+          const bool kk[4] = {k0, k1, k2, k3};
+          const float cv[4] = {ctr.x, ctr.y, ctr.z, ctr.w};
+          const int rc = row0 + idx - 2;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint32_t m = __ballot_sync(0xffffffffu, kk[j]);
+            if (kk[j]) list[count + __popc(m & lt)] = make_key(cv[j], rc * W + c0 + j);
+            count += __popc(m);
+          }
+        }
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(empty0 + 8 * s);  // this warp is done reading the stage
+  }
+}
+
+// blockDim = (nwarps + 1) * 32: warps 0..nwarps-1 consume, warp nwarps produces.
+__global__ void __launch_bounds__(288) peak_scan_kernel(const float* __restrict__ q, int H, int W, float thr, int nwarps, int BAND,
+                                                        uint8_t* __restrict__ ws) {
+  extern __shared__ __align__(128) uint8_t s_raw[];
+  float* stage0 = reinterpret_cast<float*>(s_raw);                                            // [SCAN_NST][SCAN_R][W]
+  unsigned long long* s_lists = reinterpret_cast<unsigned long long*>(s_raw + (size_t)SCAN_NST * SCAN_R * W * 4);  // [warps][CAPW + TSEL]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_lists + (size_t)nwarps * (CAPW + TSEL));  // full[NST], empty[NST]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int band = blockIdx.x, b = blockIdx.y, nbands = gridDim.x;
+  const float* img = q + (long long)b * H * W;
+  const int y0 = band * BAND, y1 = min(y0 + BAND, H);
+  const int lo = max(y0, 2), hi = min(y1, H - 2);  // centre rows this band emits
+  const float p0 = __ldg(img);
+  const bool track = p0 == __ldg(img + 1) && p0 == __ldg(img + (H > 1 ? W : 0)) && p0 == __ldg(img + (long long)H * W - 1);  // CTA-uniform
+  // rows to visit: [lo-2, hi+2) when the band emits (those rows all exist and include the band's own rows at the
+  // top / bottom edge for the constant-map test); otherwise just the band's rows, and only when tracking
+  const bool emits = hi > lo;
+  const int row0 = emits ? lo - 2 : y0;
+  const int nrows = emits ? hi - lo + 4 : (track ? y1 - y0 : 0);
+  const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + SCAN_NST);
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < SCAN_NST; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, nwarps); }
+    fence_barrier_init();
+  }
+  __syncthreads();
+  if (warp == nwarps) {  // ---- producer
+    if (lane == 0) {
+      const int nst = (nrows + SCAN_R - 1) / SCAN_R;
+      for (int k = 0; k < nst; ++k) {
+        const int s = k % SCAN_NST;
+        if (k >= SCAN_NST) {  // back off between polls: the producer must not eat the consumers' issue slots
+          while (!mbar_try_wait(empty0 + 8 * s, ((k / SCAN_NST) - 1) & 1)) __nanosleep(200);
+        }
+        const int rows = min(SCAN_R, nrows - k * SCAN_R);
+        const uint32_t bytes = (uint32_t)rows * W * 4;
+        mbar_expect_tx(full0 + 8 * s, bytes);
+        bulk_load_1d(smem_u32(stage0 + (long long)s * SCAN_R * W), img + (long long)(row0 + k * SCAN_R) * W, bytes, full0 + 8 * s);
+      }
+    }
+    return;
+  }
+  // ---- consumers
+  unsigned long long* list = s_lists + warp * (CAPW + TSEL);
+  unsigned long long* top = list + CAPW;
+  const int c0 = warp * STRIP + (lane - 1) * 4;
+  const bool inrange = c0 >= 0 && c0 + 3 < W;  // W % 4 == 0: a lane's four columns are all in or all out
+  const bool owner = lane >= 1 && lane <= 30 && inrange;
+  // candidate columns must lie in [2, W-2): columns that may not emit get an unreachable threshold
+  const float INF = INFINITY;
+  const float tx = (owner && c0 >= 2 && emits) ? thr : INF, ty = (owner && c0 + 1 >= 2 && emits) ? thr : INF;
+  const float tz = (owner && c0 + 2 < W - 2 && emits) ? thr : INF, tw = (owner && c0 + 3 < W - 2 && emits) ? thr : INF;
+  const int ccol = min(max(c0, 0), W - 4);
+  int nonconst = track ? 0 : 1;
+  int count = 0, truncated = 0;
+  if (track) scan_rows<true>(stage0, full0, empty0, W, row0, nrows, y0, y1, ccol, c0, owner, tx, ty, tz, tw, p0, lane, list, top, count, truncated, nonconst);
+  else scan_rows<false>(stage0, full0, empty0, W, row0, nrows, y0, y1, ccol, c0, owner, tx, ty, tz, tw, p0, lane, list, top, count, truncated, nonconst);
+  __syncwarp();
+  if (count > TSEL) { warp_select_top(list, count, TSEL, top, lane); count = TSEL; truncated = 1; }
+  nonconst = __any_sync(0xffffffffu, nonconst);
+  uint8_t* seg = ws + ((long long)(b * nbands + band) * nwarps + warp) * SEG_BYTES;
+  if (lane == 0) {
+    SegHeader h;
+    h.count = count; h.truncated = truncated;
+    h.worst_kept = truncated ? list[TSEL - 1] : 0ull;
+    h.nonconst = nonconst; h.pad[0] = h.pad[1] = h.pad[2] = 0;
     *reinterpret_cast<SegHeader*>(seg) = h;
   }
   unsigned long long* keys = reinterpret_cast<unsigned long long*>(seg + sizeof(SegHeader));
@@ -197,15 +355,14 @@ __global__ void peak_select_kernel(const float* __restrict__ sin_m, const float*
   const uint8_t* base = ws + (long long)b * nseg * SEG_BYTES;
   // bound D: best "worst kept" key over truncated segments; min/max for the trivial-image rule
   unsigned long long D = 0ull;
-  float vmin = INFINITY, vmax = -INFINITY;
+  int nonconst = 0;
   for (int s = lane; s < nseg; s += 32) {
     const SegHeader* h = reinterpret_cast<const SegHeader*>(base + (long long)s * SEG_BYTES);
     if (h->truncated && h->worst_kept > D) D = h->worst_kept;
-    vmin = fminf(vmin, h->vmin); vmax = fmaxf(vmax, h->vmax);
+    nonconst |= h->nonconst;
   }
   D = warp_max_u64(D);
-  vmin = -warp_max(-vmin); vmax = warp_max(vmax);
-  const bool trivial = (vmin == vmax);
+  const bool trivial = !__any_sync(0xffffffffu, nonconst);
   int acc_r[MAXK], acc_c[MAXK];
   int nacc = 0, flag = 0;
   unsigned long long prev = ~0ull;
@@ -347,7 +504,7 @@ __device__ int slow_count(const TgRect* A, const TgRect* Bq, int* s_red) {
 // One CTA per sample.  Predicted rectangles are rasterised once into shared-memory row masks; then every warp takes
 // ground-truth rectangles round-robin (no CTA-wide barrier inside the loop): lane = scanline, row mask by exact integer
 // scanline arithmetic, popc(A & B) against the predictions that pass the angle gate, warp-shuffle reductions.
-__global__ void __launch_bounds__(JT) jaccard_kernel(const double* __restrict__ grasps, const int* __restrict__ n_peaks, int K,
+__global__ void __launch_bounds__(JT, 6) jaccard_kernel(const double* __restrict__ grasps, const int* __restrict__ n_peaks, int K,
                                                      double* __restrict__ gt, const int* __restrict__ gt_count, int Mmax,
                                                      int* __restrict__ inter_out, int* __restrict__ uni_out,
                                                      int* __restrict__ j_flags, long long* __restrict__ counters, int edit_gt) {
@@ -355,7 +512,12 @@ __global__ void __launch_bounds__(JT) jaccard_kernel(const double* __restrict__ 
   __shared__ TgRect s_pred[MAXK];
   __shared__ int s_parea[MAXK];
   __shared__ TgRect s_gt;
+  __shared__ TgRect s_gr[JT];      // phase-1 results: one ground-truth rectangle per thread
+  __shared__ uint32_t s_pass[JT];
+  __shared__ int s_list[JT];
+  __shared__ int s_nlist;
   __shared__ int s_red[JT / 32];
+  __shared__ int s_wcnt[(JT / 32) * MAXK];
   __shared__ int s_j1, s_jk, s_slow;
   const int b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int n = min(n_peaks ? n_peaks[b] : K, K);
@@ -368,27 +530,49 @@ __global__ void __launch_bounds__(JT) jaccard_kernel(const double* __restrict__ 
     const double w = G[m * 6 + 2];
     G[m * 6 + 2] = w < 0.0 ? 0.0 : (w > 100.0 ? 100.0 : w);  // NaN stays NaN like np.clip
   }
+  if (n == 0 || M == 0) {  // nothing can match (block-uniform): J = 0, counters still count the sample
+    if (inter_out)
+      for (int i = tid; i < K * Mmax; i += JT) { inter_out[(long long)b * K * Mmax + i] = 0; uni_out[(long long)b * K * Mmax + i] = 0; }
+    if (tid == 0) {
+      j_flags[b * 2] = 0; j_flags[b * 2 + 1] = 0;
+      if (counters) {
+        atomicAdd(reinterpret_cast<unsigned long long*>(counters) + 1, 1ull);
+        atomicAdd(reinterpret_cast<unsigned long long*>(counters) + 3, 1ull);
+      }
+    }
+    return;
+  }
   if (tid == 0) { s_j1 = 0; s_jk = 0; s_slow = 0; }
   if (tid < n) tg_make_rect(P + tid * 5, &s_pred[tid]);
   __syncthreads();
   int all_fast = 1;
   for (int k = 0; k < n; ++k) all_fast &= s_pred[k].fast;
-  // predicted rectangles: row masks + areas
+  // predicted rectangles: row masks + areas.  Thread = scanline of every fast rectangle in turn (no barrier between
+  // rectangles: per-warp partial areas go through shared memory once); oversized ones take the CTA-wide slow count.
   for (int k = 0; k < n; ++k) {
     const TgRect* R = &s_pred[k];
+    if (!R->fast) continue;
     int cnt = 0;
-    if (R->fast) {
-      const int X = R->x0 + tid;
-      uint32_t* row = s_mask + ((long long)k * TG_MAXROWS + tid) * TG_WORDS;
-      if (X <= R->x1) {
-        tg_row_mask(R, X, row);
+    const int X = R->x0 + tid;
+    uint32_t* row = s_mask + ((long long)k * TG_MAXROWS + tid) * TG_WORDS;
+    if (X <= R->x1) {
+      tg_row_mask(R, X, row);
 #pragma unroll
-        for (int w = 0; w < TG_WORDS; ++w) cnt += __popc(row[w]);
-      }
-      cnt = block_sum(cnt, s_red);
-    } else {
-      cnt = slow_count(R, nullptr, s_red);
+      for (int w = 0; w < TG_WORDS; ++w) cnt += __popc(row[w]);
     }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    if (lane == 0) s_wcnt[warp * MAXK + k] = cnt;
+  }
+  __syncthreads();
+  if (tid < n && s_pred[tid].fast) {
+    int t = 0;
+    for (int w = 0; w < JT / 32; ++w) t += s_wcnt[w * MAXK + tid];
+    s_parea[tid] = t;
+  }
+  for (int k = 0; k < n && !all_fast; ++k) {  // block-uniform
+    if (s_pred[k].fast) continue;
+    const int cnt = slow_count(&s_pred[k], nullptr, s_red);
     if (tid == 0) s_parea[k] = cnt;
   }
   __syncthreads();
@@ -399,69 +583,89 @@ __global__ void __launch_bounds__(JT) jaccard_kernel(const double* __restrict__ 
     __syncthreads();
   }
   if (all_fast) {
-    // ---- warp-per-GT path
-    for (int m = warp; m < M; m += JT / 32) {
-      const double* g = G + m * 6;
-      uint32_t pass = 0;
-      for (int k = 0; k < n; ++k) {
-        const double tp = P[k * 5 + 4], tg = g[4];
-        if (!(fabs(tp - tg) > 30.0 && fabs(tp + tg) > 30.0)) pass |= 1u << k;
-      }
-      if (!pass) continue;  // warp-uniform
-      TgRect Gr;
-      tg_make_rect(g, &Gr);  // every lane computes the same rectangle (no shared-memory round trip)
-      if (!Gr.fast) {  // oversized GT (only possible with edit_gt == 0): handled by the CTA-synchronous path below
-        if (lane == 0) s_slow = 1;
-        continue;
-      }
-      if (!inter_out) {  // J only needs pairs that can intersect: drop gated predictions whose boxes miss this GT
-        uint32_t keep = 0;
-        for (int k = 0; k < n; ++k) if ((pass >> k) & 1u) {
-          const TgRect* R = &s_pred[k];
-          if (!(R->x1 < Gr.x0 || R->x0 > Gr.x1 || R->y1 < Gr.y0 || R->y0 > Gr.y1)) keep |= 1u << k;
+    // ---- phase 1 (thread per GT): angle gate, corner arithmetic (float64 trig) and bounding-box cull run once per
+    // ground-truth rectangle, in parallel across the CTA; survivors are compacted into a work list.
+    // ---- phase 2 (warp per surviving GT, no CTA-wide barrier inside): lane = scanline, row mask by exact integer
+    // scanline arithmetic, popc(A & B) against the predictions that passed, warp-shuffle reductions.
+    for (int m0 = 0; m0 < M; m0 += JT) {
+      if (tid == 0) s_nlist = 0;
+      __syncthreads();
+      const int mt = m0 + tid;
+      if (mt < M) {
+        const double* g = G + mt * 6;
+        uint32_t pass = 0;
+        for (int k = 0; k < n; ++k) {
+          const double tp = P[k * 5 + 4], tg = g[4];
+          if (!(fabs(tp - tg) > 30.0 && fabs(tp + tg) > 30.0)) pass |= 1u << k;
         }
-        pass = keep;
-        if (!pass) continue;
+        if (pass) {
+          TgRect Gr;
+          tg_make_rect(g, &Gr);
+          if (!Gr.fast) {
+            s_slow = 1;  // oversized GT (only possible with edit_gt == 0): handled by the CTA-synchronous path below
+          } else {
+            if (!inter_out) {  // J only needs pairs that can intersect: drop gated predictions whose boxes miss this GT
+              uint32_t keep = 0;
+              for (int k = 0; k < n; ++k) if ((pass >> k) & 1u) {
+                const TgRect* R = &s_pred[k];
+                if (!(R->x1 < Gr.x0 || R->x0 > Gr.x1 || R->y1 < Gr.y0 || R->y0 > Gr.y1)) keep |= 1u << k;
+              }
+              pass = keep;
+            }
+            if (pass) {
+              s_gr[tid] = Gr;
+              s_pass[tid] = pass;
+              s_list[atomicAdd(&s_nlist, 1)] = tid;
+            }
+          }
+        }
       }
-      int garea = 0;
-      int inter[MAXK];
+      __syncthreads();
+      const int nl = s_nlist;
+      for (int li = warp; li < nl; li += JT / 32) {
+        const int t = s_list[li], m = m0 + t;
+        const TgRect Gr = s_gr[t];
+        const uint32_t pass = s_pass[t];
+        int garea = 0;
+        int inter[MAXK];
 #pragma unroll 1
-      for (int k = 0; k < n; ++k) inter[k] = 0;
-      for (int X = Gr.x0 + lane; X <= Gr.x1; X += 32) {
-        uint32_t grow[TG_WORDS];
-        tg_row_mask(&Gr, X, grow);
+        for (int k = 0; k < n; ++k) inter[k] = 0;
+        for (int X = Gr.x0 + lane; X <= Gr.x1; X += 32) {
+          uint32_t grow[TG_WORDS];
+          tg_row_mask(&Gr, X, grow);
 #pragma unroll
-        for (int w = 0; w < TG_WORDS; ++w) garea += __popc(grow[w]);
+          for (int w = 0; w < TG_WORDS; ++w) garea += __popc(grow[w]);
+          for (int k = 0; k < n; ++k) {
+            if (!((pass >> k) & 1u)) continue;
+            const TgRect* R = &s_pred[k];
+            if (X < R->x0 || X > R->x1) continue;
+            const uint32_t* prow = s_mask + ((long long)k * TG_MAXROWS + (X - R->x0)) * TG_WORDS;
+            const int dw = Gr.yw0 - R->yw0;
+            int c = 0;
+#pragma unroll
+            for (int w = 0; w < TG_WORDS; ++w) {
+              const int pw = w + dw;
+              if (pw >= 0 && pw < TG_WORDS) c += __popc(grow[w] & prow[pw]);
+            }
+            inter[k] += c;
+          }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) garea += __shfl_xor_sync(0xffffffffu, garea, o);
         for (int k = 0; k < n; ++k) {
           if (!((pass >> k) & 1u)) continue;
-          const TgRect* R = &s_pred[k];
-          if (X < R->x0 || X > R->x1) continue;
-          const uint32_t* prow = s_mask + ((long long)k * TG_MAXROWS + (X - R->x0)) * TG_WORDS;
-          const int dw = Gr.yw0 - R->yw0;
-          int c = 0;
+          int it = inter[k];
 #pragma unroll
-          for (int w = 0; w < TG_WORDS; ++w) {
-            const int pw = w + dw;
-            if (pw >= 0 && pw < TG_WORDS) c += __popc(grow[w] & prow[pw]);
+          for (int o = 16; o > 0; o >>= 1) it += __shfl_xor_sync(0xffffffffu, it, o);
+          const int uni = s_parea[k] + garea - it;
+          if (lane == 0) {
+            if (inter_out) { inter_out[((long long)b * K + k) * Mmax + m] = it; uni_out[((long long)b * K + k) * Mmax + m] = uni; }
+            if (uni > 0 && 4LL * it > (long long)uni) { atomicOr(&s_jk, 1); if (k == 0) atomicOr(&s_j1, 1); }
           }
-          inter[k] += c;
         }
       }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) garea += __shfl_xor_sync(0xffffffffu, garea, o);
-      for (int k = 0; k < n; ++k) {
-        if (!((pass >> k) & 1u)) continue;
-        int it = inter[k];
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) it += __shfl_xor_sync(0xffffffffu, it, o);
-        const int uni = s_parea[k] + garea - it;
-        if (lane == 0) {
-          if (inter_out) { inter_out[((long long)b * K + k) * Mmax + m] = it; uni_out[((long long)b * K + k) * Mmax + m] = uni; }
-          if (uni > 0 && 4LL * it > (long long)uni) { atomicOr(&s_jk, 1); if (k == 0) atomicOr(&s_j1, 1); }
-        }
-      }
+      __syncthreads();
     }
-    __syncthreads();
   }
   // ---- CTA-synchronous path: samples with oversized predictions, and oversized GT rectangles of any sample
   const bool need_slow = !all_fast || s_slow;  // block-uniform (read after the barrier above)
@@ -501,16 +705,19 @@ __global__ void __launch_bounds__(JT) jaccard_kernel(const double* __restrict__ 
   }
 }
 
-inline void scan_geometry(int H, int W, int* nbands, int* nwarps) {
-  *nbands = (H + BAND - 1) / BAND;
+// Band height: tall bands when there are enough maps to fill the GPU anyway (at least ~4 CTAs per SM), short ones otherwise.
+inline void scan_geometry(int B, int H, int W, int* nbands, int* nwarps, int* band) {
   *nwarps = (W + STRIP - 1) / STRIP;
+  const long long ctas_large = (long long)B * ((H + BAND_LARGE - 1) / BAND_LARGE);
+  *band = ctas_large >= 4 * 148 ? BAND_LARGE : BAND_SMALL;
+  *nbands = (H + *band - 1) / *band;
 }
 
 }  // namespace
 
 extern "C" int64_t crog_detect_workspace_bytes(int32_t B, int32_t H, int32_t W, int32_t K) {
-  int nb, nw;
-  scan_geometry(H, W, &nb, &nw);
+  int nb, nw, band;
+  scan_geometry(B, H, W, &nb, &nw, &band);
   (void)K;
   return (int64_t)B * nb * nw * SEG_BYTES + (int64_t)B * 4 + 256;
 }
@@ -523,15 +730,22 @@ extern "C" int crog_detect_grasps(const float* q, const float* sin_m, const floa
   CROG_REQUIRE(B <= 65535, CROG_E_BADSHAPE, "detect_grasps: at most 65535 maps per call");
   CROG_REQUIRE(aligned16(q) && aligned16(workspace), CROG_E_BADALIGN, "detect_grasps: 16B alignment");
   if (B == 0) return CROG_OK;
-  int nb, nw;
-  scan_geometry(H, W, &nb, &nw);
+  int nb, nw, band;
+  scan_geometry(B, H, W, &nb, &nw, &band);
   cudaStream_t s = (cudaStream_t)stream;
   uint8_t* ws = (uint8_t*)workspace;
   int* flags = (int*)(ws + (((int64_t)B * nb * nw * SEG_BYTES + 15) / 16) * 16);
-  const size_t smem = (size_t)nw * (CAPW + TSEL) * 8;
+  const size_t smem_lists = (size_t)nw * (CAPW + TSEL) * 8;
+  const size_t smem_fast = (size_t)SCAN_NST * SCAN_R * W * 4 + smem_lists + 2 * SCAN_NST * 8;
   static bool attr = false;
-  if (!attr) { CROG_CUDA_OK(cudaFuncSetAttribute(peak_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * (CAPW + TSEL) * 8)); attr = true; }
-  peak_scan_kernel<<<dim3(nb, B), nw * 32, smem, s>>>(q, H, W, threshold, nw, ws);
+  if (!attr) {
+    CROG_CUDA_OK(cudaFuncSetAttribute(peak_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      SCAN_NST * SCAN_R * 8 * STRIP * 4 + 8 * (CAPW + TSEL) * 8 + 2 * SCAN_NST * 8));
+    CROG_CUDA_OK(cudaFuncSetAttribute(peak_scan_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * (CAPW + TSEL) * 8));
+    attr = true;
+  }
+  if (W % 4 == 0 && (long long)H * W >= 2 && !getenv("CROG_SCAN_GENERIC")) peak_scan_kernel<<<dim3(nb, B), (nw + 1) * 32, smem_fast, s>>>(q, H, W, threshold, nw, band, ws);
+  else peak_scan_generic_kernel<<<dim3(nb, B), nw * 32, smem_lists, s>>>(q, H, W, threshold, nw, band, ws);
   CROG_LAUNCH_OK("peak_scan");
   peak_select_kernel<<<(B + 3) / 4, 128, 0, s>>>(sin_m, cos_m, wid, B, H, W, K, nb * nw, ws, flags, peaks, n_peaks, grasps);
   CROG_LAUNCH_OK("peak_select");

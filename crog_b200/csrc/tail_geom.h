@@ -60,8 +60,14 @@ TG_HD int tg_ceildiv(int p, int q) {  // q > 0
 
 TG_HD void tg_box_points(float cx, float cy, float w, float h, float ang_deg, float* o8) {
   const double rad = (double)ang_deg * 3.141592653589793 / 180.0;
-  const float b = TG_MUL((float)cos(rad), 0.5f);
-  const float a = TG_MUL((float)sin(rad), 0.5f);
+#if defined(__CUDA_ARCH__)
+  double sn, cs;
+  sincos(rad, &sn, &cs);  // one range reduction for both
+#else
+  const double sn = sin(rad), cs = cos(rad);
+#endif
+  const float b = TG_MUL((float)cs, 0.5f);
+  const float a = TG_MUL((float)sn, 0.5f);
   o8[0] = TG_SUB(TG_SUB(cx, TG_MUL(a, h)), TG_MUL(b, w));
   o8[1] = TG_SUB(TG_ADD(cy, TG_MUL(b, h)), TG_MUL(a, w));
   o8[2] = TG_SUB(TG_ADD(cx, TG_MUL(a, h)), TG_MUL(b, w));
@@ -136,12 +142,14 @@ TG_HD void tg_row_mask(const TgRect* R, int X, uint32_t* out) {
       int Q = xb - xa;
       int P = ya * Q + (X - xa) * (yb - ya);
       if (Q < 0) { Q = -Q; P = -P; }
+      const int fl = tg_floordiv(P, Q);             // one division serves both bounds
+      const int ce = fl + ((P - fl * Q) != 0 ? 1 : 0);
       if (rs) {  // counts for Y <= ceil(Y*) - 1  -> prefix mask
-        const int A = tg_ceildiv(P, Q) - 1;
+        const int A = ce - 1;
         for (int w = 0; w < TG_WORDS; ++w) rpar[w] ^= tg_word_range(R->yw0 + w, -BIG, A);
       }
       if (ls) {  // counts for Y >= floor(Y*) + 1 -> suffix mask
-        const int B = tg_floordiv(P, Q) + 1;
+        const int B = fl + 1;
         for (int w = 0; w < TG_WORDS; ++w) lpar[w] ^= tg_word_range(R->yw0 + w, B, BIG);
       }
     }

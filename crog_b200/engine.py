@@ -95,6 +95,59 @@ class GraspEvaluator:
         flags = GE.jacquard_batched(grasps, n, gt, gt_count, counters=self.counters)
         return post, peaks, n, grasps, flags
 
+    @torch.no_grad()
+    def stream(self, host_batches):
+        """End-to-end evaluation over HOST batches with the input copies hidden behind the previous batch's compute.
+
+        ``host_batches`` yields ``(img, word, gt, gt_count)`` CPU tensors (pinned memory for truly asynchronous copies).
+        Two device staging slots are filled on a copy stream: while batch k runs on the compute stream, batch k+1 is
+        already crossing PCIe.  For every batch the decoded grasps / peak counts / J flags are copied back and the
+        host waits for them (the caller reads the result of every step); yields ``(n_peaks, grasps, j_flags)`` as
+        pinned CPU tensors that stay valid until the next-but-one iteration."""
+        dev = self.counters.device
+        main = torch.cuda.current_stream(dev)
+        if getattr(self, "_copy_stream", None) is None:
+            self._copy_stream = torch.cuda.Stream(device=dev)
+            self._slots = [None, None]
+            self._ready = [torch.cuda.Event(), torch.cuda.Event()]
+            self._free = [torch.cuda.Event(), torch.cuda.Event()]
+            self._done = [torch.cuda.Event(), torch.cuda.Event()]
+            self._hout = [None, None]
+        it = iter(host_batches)
+
+        def prefetch(k):
+            try:
+                hb = next(it)
+            except StopIteration:
+                return False
+            s = k & 1
+            if self._slots[s] is None or any(d.shape != h.shape or d.dtype != h.dtype for d, h in zip(self._slots[s], hb)):
+                self._slots[s] = [torch.empty(h.shape, dtype=h.dtype, device=dev) for h in hb]
+            with torch.cuda.stream(self._copy_stream):
+                if k >= 2:
+                    self._copy_stream.wait_event(self._free[s])  # batch k-2 no longer reads this slot
+                for d, h in zip(self._slots[s], hb):
+                    d.copy_(h, non_blocking=True)
+                self._ready[s].record(self._copy_stream)
+            return True
+
+        k, more = 0, prefetch(0)
+        while more:
+            s = k & 1
+            more = prefetch(k + 1)
+            main.wait_event(self._ready[s])
+            img, word, gt, cnt = self._slots[s]
+            _, _, n, grasps, flags = self.step(img, word, gt, cnt)
+            self._free[s].record(main)
+            if self._hout[s] is None or self._hout[s][1].shape != grasps.shape:
+                self._hout[s] = [torch.empty(t.shape, dtype=t.dtype).pin_memory() for t in (n, grasps, flags)]
+            for h, d in zip(self._hout[s], (n, grasps, flags)):
+                h.copy_(d, non_blocking=True)
+            self._done[s].record(main)
+            self._done[s].synchronize()
+            yield tuple(self._hout[s])
+            k += 1
+
     def reduce(self) -> torch.Tensor:
         import torch.distributed as dist
 

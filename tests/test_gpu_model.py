@@ -155,3 +155,27 @@ def test_engine_end_to_end_j_parity():
         assert np.allclose(gg[b, :k, 4], g_ref[b, :k, 4], rtol=0, atol=1e-5)
     assert np.array_equal(flags.cpu().numpy(), j_ref)
     assert np.array_equal(ev.reduce().cpu().numpy(), c_ref)
+
+
+def test_engine_stream_matches_step():
+    """GraspEvaluator.stream (pinned host batches, copies overlapped with the previous batch) returns exactly what
+    step() returns for the same batches, in order, and accumulates the same counters."""
+    from crog_b200.engine import GraspEvaluator
+
+    Lw, B = 17, 2
+    cfg, sd, model = _build(Lw, "perturbed", "bf16")
+    batches = []
+    for k in range(4):
+        img, word = synth.make_inputs(B, Lw, seed_img=10 + k, seed_txt=20 + k)
+        gt, cnt = synth.make_gt_rects(B, 64, seed=30 + k)
+        batches.append((img.pin_memory(), word.pin_memory(), torch.from_numpy(gt).pin_memory(), torch.from_numpy(cnt).pin_memory()))
+    ev1, ev2 = GraspEvaluator(model), GraspEvaluator(model)
+    want = []
+    for img, word, gt, cnt in batches:
+        _, _, n, grasps, flags = ev1.step(img.cuda(), word.cuda(), gt.cuda(), cnt.cuda())
+        want.append((n.cpu().clone(), grasps.cpu().clone(), flags.cpu().clone()))
+    got = [tuple(t.clone() for t in out) for out in ev2.stream(iter(batches))]
+    assert len(got) == len(want)
+    for (n1, g1, f1), (n2, g2, f2) in zip(want, got):
+        assert torch.equal(n1, n2) and torch.equal(g1, g2) and torch.equal(f1, f2)
+    assert torch.equal(ev1.counters.cpu(), ev2.counters.cpu())
