@@ -2,6 +2,8 @@
 // self-attention 676 tokens, decoder cross-attention 676 x L with key padding).
 // v1: CUDA-core streaming softmax, one query per thread, K/V tiles of 64 keys staged in shared
 // memory and broadcast to the warp; fp32 math throughout.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace {
@@ -117,7 +119,7 @@ __global__ void __launch_bounds__(QB) attention_kernel(const T* __restrict__ q, 
 }  // namespace
 
 int crog_attention_tc(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, void* o, int ldo, int B, int heads,
-                      int Tq, int Tk, float scale, cudaStream_t stream);
+                      int Tq, int Tk, float scale, const int64_t* pad_word, cudaStream_t stream);
 
 extern "C" int crog_attention(const void* q, int32_t ldq, const void* k, int32_t ldk, const void* v, int32_t ldv, void* o,
                               int32_t ldo, int32_t B, int32_t heads, int32_t Tq, int32_t Tk, float scale, int32_t causal,
@@ -127,10 +129,11 @@ extern "C" int crog_attention(const void* q, int32_t ldq, const void* k, int32_t
   if (B == 0 || Tq == 0) return CROG_OK;
   CROG_REQUIRE(B <= 65535 && heads <= 65535, CROG_E_BADSHAPE, "attention: grid too large");
   cudaStream_t s = (cudaStream_t)stream;
-  // dense bf16 attentions with enough keys to fill a tensor-core tile go to the tcgen05 kernel; the causal text
-  // attention (L <= 77) and the cross attention over <= 77 word tokens stay on CUDA cores
-  if (dtype == CROG_BF16 && !causal && pad_word == nullptr && Tk >= 128)
-    return crog_attention_tc(q, ldq, k, ldk, v, ldv, o, ldo, B, heads, Tq, Tk, scale, s);
+  // bf16 attentions with many queries go to the tcgen05 kernel: the dense self-attentions, and the cross-attention
+  // over <= 77 word tokens (one masked key tile; scores and P.V on the tensor core instead of 4352 LDS + FMA per
+  // query on CUDA cores).  The causal text attention (L <= 77 queries) stays on CUDA cores.
+  if (dtype == CROG_BF16 && !causal && (Tk >= 128 || (Tq >= 128 && !getenv("CROG_ATTN_CROSS_SIMT"))))
+    return crog_attention_tc(q, ldq, k, ldk, v, ldv, o, ldo, B, heads, Tq, Tk, scale, (const int64_t*)pad_word, s);
   dim3 grid((Tq + QB - 1) / QB, heads, B);
   if (dtype == CROG_F32)
     crog_launch(attention_kernel<float>, grid, dim3(QB), 0, s, (const float*)q, ldq, (const float*)k, ldk, (const float*)v, ldv, (float*)o, ldo, Tq, Tk, scale, causal, pad_word);

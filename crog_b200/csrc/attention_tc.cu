@@ -23,7 +23,8 @@ constexpr int TMEM_COLS = 256, TM_S = 0, TM_O = 128;
 __global__ void __launch_bounds__(192, 2) attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ,
                                                                const __grid_constant__ CUtensorMap tmK,
                                                                const __grid_constant__ CUtensorMap tmV, bf16* __restrict__ o,
-                                                               int ldo, int Tq, int Tk, float scale_log2e) {
+                                                               int ldo, int Tq, int Tk, float scale_log2e,
+                                                               const int64_t* __restrict__ pad_word) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SM_BAR);
@@ -103,14 +104,37 @@ __global__ void __launch_bounds__(192, 2) attention_tc_kernel(const __grid_const
       mbar_wait(b_sfull, j & 1);
       tc_fence_after();
       const int kvalid = Tk - j * KT;  // keys >= kvalid belong to the next sample / padding
+      const bool full = kvalid >= KT && pad_word == nullptr;  // CTA-uniform: only the last key tile / padded words need masking
+      uint32_t km[4] = {0u, 0u, 0u, 0u};  // bit i of km[c / 32]: key c + i takes part (in range and not a padding word)
+      if (!full) {
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) {
+          const int key = cc * 32 + lane;
+          bool ok = key < kvalid;
+          if (ok && pad_word) ok = pad_word[(long long)b * Tk + j * KT + key] != 0;  // key_padding_mask = (word == 0)
+          km[cc] = __ballot_sync(0xffffffffu, ok);
+        }
+      }
       float tmax = -INFINITY;
 #pragma unroll 1
       for (int c = 0; c < KT; c += 32) {
+        if (c >= kvalid) break;
         uint32_t r[32];
         tc_ld32(t_s + c, r);
         tc_wait_ld();
+        if (full || (c + 32 <= kvalid && pad_word == nullptr)) {
+          float m0 = -INFINITY, m1 = -INFINITY;  // two independent FMNMX3 chains
 #pragma unroll
-        for (int i = 0; i < 32; ++i) if (c + i < kvalid) tmax = fmaxf(tmax, __uint_as_float(r[i]));
+          for (int i = 0; i < 32; i += 4) {
+            m0 = fmaxf(fmaxf(m0, __uint_as_float(r[i])), __uint_as_float(r[i + 1]));
+            m1 = fmaxf(fmaxf(m1, __uint_as_float(r[i + 2])), __uint_as_float(r[i + 3]));
+          }
+          tmax = fmaxf(fmaxf(tmax, m0), m1);
+        } else {
+          const uint32_t m = km[c >> 5];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) if ((m >> i) & 1u) tmax = fmaxf(tmax, __uint_as_float(r[i]));
+        }
       }
       const float nm = fmaxf(mx, tmax);
       const float corr = exp2f((mx - nm) * scale_log2e);
@@ -118,18 +142,36 @@ __global__ void __launch_bounds__(192, 2) attention_tc_kernel(const __grid_const
       float psum = 0.f;
 #pragma unroll 1
       for (int c = 0; c < KT; c += 32) {
-        uint32_t r[32];
-        tc_ld32(t_s + c, r);
-        tc_wait_ld();
         uint32_t pk[16];
+        if (c < kvalid) {
+          uint32_t r[32];
+          tc_ld32(t_s + c, r);
+          tc_wait_ld();
+          if (full || (c + 32 <= kvalid && pad_word == nullptr)) {
+            float s0 = 0.f, s1 = 0.f;
 #pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          float p0 = (c + i < kvalid) ? exp2f(__uint_as_float(r[i]) * scale_log2e - nms) : 0.f;
-          float p1 = (c + i + 1 < kvalid) ? exp2f(__uint_as_float(r[i + 1]) * scale_log2e - nms) : 0.f;
-          __nv_bfloat162 hh = __floats2bfloat162_rn(p0, p1);
-          // the row sum must match what the tensor core will see (bf16-rounded probabilities)
-          psum += __low2float(hh) + __high2float(hh);
-          pk[i >> 1] = *reinterpret_cast<uint32_t*>(&hh);
+            for (int i = 0; i < 32; i += 2) {
+              const float p0 = exp2f(__uint_as_float(r[i]) * scale_log2e - nms);
+              const float p1 = exp2f(__uint_as_float(r[i + 1]) * scale_log2e - nms);
+              __nv_bfloat162 hh = __floats2bfloat162_rn(p0, p1);
+              s0 += p0; s1 += p1;
+              pk[i >> 1] = *reinterpret_cast<uint32_t*>(&hh);
+            }
+            psum += s0 + s1;
+          } else {
+            const uint32_t m = km[c >> 5];
+#pragma unroll
+            for (int i = 0; i < 32; i += 2) {
+              const float p0 = ((m >> i) & 1u) ? exp2f(__uint_as_float(r[i]) * scale_log2e - nms) : 0.f;
+              const float p1 = ((m >> (i + 1)) & 1u) ? exp2f(__uint_as_float(r[i + 1]) * scale_log2e - nms) : 0.f;
+              __nv_bfloat162 hh = __floats2bfloat162_rn(p0, p1);
+              psum += p0 + p1;
+              pk[i >> 1] = *reinterpret_cast<uint32_t*>(&hh);
+            }
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) pk[i] = 0u;  // padding keys: P = 0
         }
         // keys c..c+31 -> atom (c / 64), 16-byte units ((c % 64) / 8 + u), swizzled with the row
         uint8_t* base = prow + (c >> 6) * 16384;
@@ -177,7 +219,7 @@ __global__ void __launch_bounds__(192, 2) attention_tc_kernel(const __grid_const
 }  // namespace
 
 int crog_attention_tc(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, void* o, int ldo, int B, int heads,
-                      int Tq, int Tk, float scale, cudaStream_t stream) {
+                      int Tq, int Tk, float scale, const int64_t* pad_word, cudaStream_t stream) {
   static bool attr = false;
   if (!attr) {
     CROG_CUDA_OK(cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL));
@@ -191,7 +233,7 @@ int crog_attention_tc(const void* q, int ldq, const void* k, int ldk, const void
   rc = crog_encode_2d_bf16(&tmV, v, (uint64_t)heads * HD, (uint64_t)B * Tk, (uint64_t)ldv, KT);
   if (rc) return rc;
   dim3 grid((Tq + QT - 1) / QT, heads, B);
-  crog_launch(attention_tc_kernel, grid, dim3(192), SM_TOTAL, stream, tmQ, tmK, tmV, (bf16*)o, ldo, Tq, Tk, scale * 1.4426950408889634f);
+  crog_launch(attention_tc_kernel, grid, dim3(192), SM_TOTAL, stream, tmQ, tmK, tmV, (bf16*)o, ldo, Tq, Tk, scale * 1.4426950408889634f, pad_word);
   CROG_LAUNCH_OK("attention_tc");
   return CROG_OK;
 }

@@ -482,8 +482,8 @@ int dispatch(const CrogGemm* g, cudaStream_t stream) {
   // contraction is long enough to be tensor/L2 bound rather than epilogue bound
   if (g->N % 256 == 0 && (long long)g->taps * g->cin >= 1024) {
     // long contractions: the TMA feed is the pace (96 B/clk/SM at full tensor rate), so a fourth 48 KB stage in flight
-    // is worth more than a second epilogue group
-    if (((long long)g->taps * g->cin >= 2048 || getenv("CROG_GEMM_4STAGE_ALL")) && !getenv("CROG_GEMM_3STAGE")) return launch<256, 4, 2, MODE, false, 4>(g, stream);
+    // is worth more than a second epilogue group (measured 3-12 % per layer; CROG_GEMM_3STAGE restores the old config)
+    if (!getenv("CROG_GEMM_3STAGE")) return launch<256, 4, 2, MODE, false, 4>(g, stream);
     return launch<256, 3, 2, MODE>(g, stream);
   }
   return launch<128, 4, 3, MODE>(g, stream);
