@@ -38,13 +38,20 @@ enum { MODE_LEGACY = 0, MODE_TMA_BF16 = 1, MODE_TMA_F32 = 2 };
 // EPI_WARPS = 8: two independent 4-warp epilogue groups (group g drains tiles g, g+2, ...), for short contractions
 // where the epilogue is the pace; EPI_WARPS = 4: one group drains every tile (alternating accumulator buffers), which
 // frees 32 KB of staging for one more operand stage when the contraction is long and the TMA feed is the pace.
-template <int BN, int STAGES, int NBUF, bool CONV3, int EPI_WARPS>
+// PAIR: two CTAs of a cluster (one TPC) work on one 256 x BN tile with tcgen05 cta_group::2: each CTA stages its own
+// 128 rows of A and HALF of the weights (BN/2 rows), the leader issues M=256 MMAs that read both halves, and each CTA's
+// TMEM receives its own 128 x BN accumulator.  Per CTA and k-block that is 32 KB written + 32 KB read from shared
+// memory instead of 48 + 48: at full tensor rate 125 B/clk instead of 187 B/clk against a 128 B/clk shared-memory port,
+// which is what caps the single-CTA 128 x 256 tile at ~67 % tensor utilisation.
+template <int BN, int STAGES, int NBUF, bool CONV3, int EPI_WARPS, bool PAIR = false>
 struct Cfg {
+  static_assert(!(PAIR && CONV3), "the CTA-pair path is for the generic k-loop");
   static constexpr int NUM_THREADS = 64 + EPI_WARPS * 32;
   static constexpr int A_ROWS = CONV3 ? BM + 2 : BM;
   static constexpr int A_TX = A_ROWS * BK * 2;                 // bytes one A box delivers
   static constexpr int A_BYTES = ((A_TX + 1023) / 1024) * 1024;
-  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int B_ROWS = PAIR ? BN / 2 : BN;            // weight rows this CTA stages
+  static constexpr int B_BYTES = B_ROWS * BK * 2;
   static constexpr int STAGE_BYTES = CONV3 ? A_BYTES : A_BYTES + ((B_BYTES + 1023) / 1024) * 1024;
   static constexpr int BRES_BYTES = CONV3 ? 9 * B_BYTES : 0;   // resident weights
   static constexpr int SUB = BN > 32 ? 32 : BN;               // legacy: columns staged at a time
@@ -59,14 +66,15 @@ struct Cfg {
   static_assert(NBUF >= 2 && STG_WARP >= 32 * PITCH, "staging too small");
 };
 
-template <int BN, int STAGES, int NBUF, int MODE, bool CONV3, int EPI_WARPS>
+template <int BN, int STAGES, int NBUF, int MODE, bool CONV3, int EPI_WARPS, bool PAIR>
 __global__ void __launch_bounds__(64 + EPI_WARPS * 32, 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                    const __grid_constant__ CUtensorMap tmB,
                                                                    const __grid_constant__ CUtensorMap tmOut,
                                                                    const __grid_constant__ CUtensorMap tmRes,
                                                                    const CrogGemm g, int n_tiles, int total_tiles) {
-  using L = Cfg<BN, STAGES, NBUF, CONV3, EPI_WARPS>;
+  using L = Cfg<BN, STAGES, NBUF, CONV3, EPI_WARPS, PAIR>;
   constexpr int GROUPS = EPI_WARPS / 4;
+  constexpr int MT = PAIR ? 2 * BM : BM;  // rows of one tile (over the CTA pair)
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment for SWIZZLE_128B tiles; plain pointer arithmetic keeps the shared address space so the
   // epilogue's staging accesses compile to LDS / STS instead of generic loads
@@ -76,6 +84,9 @@ __global__ void __launch_bounds__(64 + EPI_WARPS * 32, 1) gemm_tc_kernel(const _
 
   pdl_launch();  // the successor may start its prologue as soon as this grid is resident
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;               // 0 = leader (issues the MMAs)
+  const int tile0 = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;  // both CTAs of a pair walk the same tiles
+  const int tstep = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   const int kchunks = g.cin / BK;
   const int num_kb = CONV3 ? 3 : g.taps * kchunks;  // CONV3: one k-block per ky band
   const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + STAGES), tfull0 = smem_u32(bars + 2 * STAGES),
@@ -89,15 +100,20 @@ __global__ void __launch_bounds__(64 + EPI_WARPS * 32, 1) gemm_tc_kernel(const _
       tma_prefetch_desc(&tmOut);
       if (g.residual) tma_prefetch_desc(&tmRes);
     }
-    for (int s = 0; s < STAGES; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(tfull0 + 8 * s, 1); mbar_init(tempty0 + 8 * s, 4 * 32); }
+    // pair: the leader's full barrier collects one arrive(+expect_tx) per CTA, its tempty the epilogue threads of both
+    for (int s = 0; s < STAGES; ++s) { mbar_init(full0 + 8 * s, PAIR ? 2 : 1); mbar_init(empty0 + 8 * s, 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(tfull0 + 8 * s, 1); mbar_init(tempty0 + 8 * s, (PAIR ? 2 : 1) * 4 * 32); }
     for (int s = 0; s < EPI_WARPS * NBUF; ++s) mbar_init(res0 + 8 * s, 1);
     mbar_init(bres, 1);
     fence_barrier_init();
   }
-  if (warp == 1) tc_alloc(smem_u32(tmem_slot), L::TMEM_COLS);
+  if (warp == 1) {
+    if constexpr (PAIR) tc_alloc_pair(smem_u32(tmem_slot), L::TMEM_COLS);
+    else tc_alloc(smem_u32(tmem_slot), L::TMEM_COLS);
+  }
   tc_fence_before();
   __syncthreads();
+  if constexpr (PAIR) cluster_sync_all();  // the peer's barriers are initialised before anything arrives on them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   pdl_wait();  // everything above overlapped the predecessor's tail; its outputs are visible from here on
@@ -108,7 +124,7 @@ __global__ void __launch_bounds__(64 + EPI_WARPS * 32, 1) gemm_tc_kernel(const _
       if constexpr (CONV3) {
         mbar_expect_tx(bres, L::BRES_BYTES);
         for (int t = 0; t < 9; ++t) tma_load_2d(smem_u32(smem + L::BRES_OFF + t * L::B_BYTES), &tmB, t * BK, 0, bres);
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        for (int tile = tile0; tile < total_tiles; tile += tstep) {
           const long long row0 = (long long)tile * BM;  // n_tiles == 1
           for (int ky = 0; ky < 3; ++ky, ++kbg) {
             const int s = kbg % STAGES, it = kbg / STAGES;
@@ -118,27 +134,36 @@ __global__ void __launch_bounds__(64 + EPI_WARPS * 32, 1) gemm_tc_kernel(const _
           }
         }
       } else
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int tile = tile0; tile < total_tiles; tile += tstep) {
         const int n_t = tile % n_tiles, m_t = tile / n_tiles;
-        const TileRows tr = tile_rows(g, m_t, BM);
+        TileRows tr = tile_rows(g, m_t, MT);
+        if constexpr (PAIR) tr.row0 += (long long)rank * BM;  // shared weights only: tiles are plain row ranges
         const int wrow0 = n_t * BN + (g.w_sample_stride > 0 ? tr.wsample * (int)(g.w_sample_stride / ((long long)g.taps * g.cin)) : 0);
         for (int kb = 0; kb < num_kb; ++kb, ++kbg) {
           const int s = kbg % STAGES, it = kbg / STAGES;
           mbar_wait(empty0 + 8 * s, (it & 1) ^ 1);
           const uint32_t sa = smem_u32(smem + s * L::STAGE_BYTES), sb = sa + L::A_BYTES;
           const int tap = kb / kchunks, c0 = (kb % kchunks) * BK;
-          mbar_expect_tx(full0 + 8 * s, L::A_BYTES + L::B_BYTES);
-          tma_load_2d(sa, &tmA, c0, (int)(tr.row0 + tap_shift(g.taps, tap, g.W)), full0 + 8 * s);
-          tma_load_2d(sb, &tmB, kb * BK, wrow0, full0 + 8 * s);
+          if constexpr (PAIR) {
+            // both CTAs report to the LEADER's full barrier; this CTA stages its own rows of A and its half of the weights
+            const uint32_t lfull = mapa_shared(full0 + 8 * s, 0);
+            mbar_expect_tx_cluster(lfull, L::A_BYTES + L::B_BYTES);
+            tma_load_2d_pair(sa, &tmA, c0, (int)(tr.row0 + tap_shift(g.taps, tap, g.W)), lfull);
+            tma_load_2d_pair(sb, &tmB, kb * BK, wrow0 + (int)rank * L::B_ROWS, lfull);
+          } else {
+            mbar_expect_tx(full0 + 8 * s, L::A_BYTES + L::B_BYTES);
+            tma_load_2d(sa, &tmA, c0, (int)(tr.row0 + tap_shift(g.taps, tap, g.W)), full0 + 8 * s);
+            tma_load_2d(sb, &tmB, kb * BK, wrow0, full0 + 8 * s);
+          }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(BM, BN);
+    if (lane == 0 && rank == 0) {
+      constexpr uint32_t idesc = make_idesc(MT, BN);
       int kbg = 0, i = 0;
       if constexpr (CONV3) mbar_wait(bres, 0);
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++i) {
+      for (int tile = tile0; tile < total_tiles; tile += tstep, ++i) {
         const int as = i & 1;
         mbar_wait(tempty0 + 8 * as, ((i >> 1) & 1) ^ 1);  // epilogue group `as` has drained this accumulator buffer
         tc_fence_after();
@@ -169,12 +194,20 @@ __global__ void __launch_bounds__(64 + EPI_WARPS * 32, 1) gemm_tc_kernel(const _
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + s * L::STAGE_BYTES), sb = sa + L::A_BYTES;
           const uint64_t da = make_sdesc(sa), db = make_sdesc(sb);
+          if constexpr (PAIR) {
 #pragma unroll
-          for (int k = 0; k < BK / UMMA_K; ++k)
-            tc_mma_bf16(tacc, da + (uint64_t)(k * UMMA_K * 2 / 16), db + (uint64_t)(k * UMMA_K * 2 / 16), idesc, (kb | k) != 0);
-          tc_commit(empty0 + 8 * s);  // frees the smem slot once these MMAs retire
+            for (int k = 0; k < BK / UMMA_K; ++k)
+              tc_mma_bf16_pair(tacc, da + (uint64_t)(k * UMMA_K * 2 / 16), db + (uint64_t)(k * UMMA_K * 2 / 16), idesc, (kb | k) != 0);
+            tc_commit_pair(empty0 + 8 * s, 3);  // frees this slot in BOTH CTAs once these MMAs retire
+          } else {
+#pragma unroll
+            for (int k = 0; k < BK / UMMA_K; ++k)
+              tc_mma_bf16(tacc, da + (uint64_t)(k * UMMA_K * 2 / 16), db + (uint64_t)(k * UMMA_K * 2 / 16), idesc, (kb | k) != 0);
+            tc_commit(empty0 + 8 * s);  // frees the smem slot once these MMAs retire
+          }
         }
-        tc_commit(tfull0 + 8 * as);  // accumulator complete
+        if constexpr (PAIR) tc_commit_pair(tfull0 + 8 * as, 3);  // accumulator complete, in both CTAs
+        else tc_commit(tfull0 + 8 * as);  // accumulator complete
       }
     }
   } else {
@@ -194,9 +227,9 @@ __global__ void __launch_bounds__(64 + EPI_WARPS * 32, 1) gemm_tc_kernel(const _
       uint32_t nld = 0, ncs = 0;   // residual chunks requested / chunks consumed (warp-uniform)
       int pf_i = grp, pf_c = 0;    // prefetch cursor: tile ordinal, chunk in tile
       auto issue_prefetch = [&]() {
-        const int tile = blockIdx.x + pf_i * (int)gridDim.x;
+        const int tile = tile0 + pf_i * tstep;
         if (tile >= total_tiles) return;
-        const int n0 = (tile % n_tiles) * BN, row = (tile / n_tiles) * BM + q * 32;
+        const int n0 = (tile % n_tiles) * BN, row = (tile / n_tiles) * MT + (int)rank * BM + q * 32;
         if (lane == 0) {
           const uint32_t b = nld % NBUF;
           mbar_expect_tx(rbar0 + 8 * b, STG_BUF);
@@ -208,11 +241,11 @@ __global__ void __launch_bounds__(64 + EPI_WARPS * 32, 1) gemm_tc_kernel(const _
       if (has_res)
         for (int j = 0; j < NBUF - 1; ++j) issue_prefetch();
       for (int i = grp;; i += GROUPS) {
-        const int tile = blockIdx.x + i * (int)gridDim.x;
+        const int tile = tile0 + i * tstep;
         if (tile >= total_tiles) break;
         const int buf = i & 1;
         const uint32_t tfull = tfull0 + 8 * buf, tempty = tempty0 + 8 * buf;
-        const int n0 = (tile % n_tiles) * BN, row0 = (tile / n_tiles) * BM;
+        const int n0 = (tile % n_tiles) * BN, row0 = (tile / n_tiles) * MT + (int)rank * BM;
         const RowMap m = map_row(g, (long long)row0 + q * 32 + lane, g.M);
         const int nvc = min(NCH, (g.N - n0 + CW - 1) / CW);  // chunks with at least one real column
         mbar_wait(tfull, (i >> 1) & 1);
@@ -228,9 +261,10 @@ __global__ void __launch_bounds__(64 + EPI_WARPS * 32, 1) gemm_tc_kernel(const _
 #pragma unroll
             for (int j = 0; j < 32; ++j) acc[h * 32 + j] = __uint_as_float(r[j]);
           }
-          if (c == nvc - 1) {  // last read of this accumulator buffer: hand it back to the MMA warp
+          if (c == nvc - 1) {  // last read of this accumulator buffer: hand it back to the (leader's) MMA warp
             tc_fence_before();
-            mbar_arrive(tempty);
+            if constexpr (PAIR) mbar_arrive_cluster(mapa_shared(tempty, 0));
+            else mbar_arrive(tempty);
           }
           const int ncol = n0 + c * CW;
           if (m.valid) {
@@ -316,12 +350,13 @@ __global__ void __launch_bounds__(64 + EPI_WARPS * 32, 1) gemm_tc_kernel(const _
       constexpr int PASSES = 32 / RPP;
       const int u = lane % UPR, rsub = lane / UPR;
       for (int i = grp;; i += GROUPS) {
-        const int tile = blockIdx.x + i * (int)gridDim.x;
+        const int tile = tile0 + i * tstep;
         if (tile >= total_tiles) break;
         const int buf = i & 1;
         const uint32_t tfull = tfull0 + 8 * buf, tempty = tempty0 + 8 * buf;
         const int n_t = tile % n_tiles, m_t = tile / n_tiles;
-        const TileRows tr = tile_rows(g, m_t, BM);
+        TileRows tr = tile_rows(g, m_t, MT);
+        if constexpr (PAIR) tr.row0 += (long long)rank * BM;
         const int n0 = n_t * BN;
         const RowMap m = map_row(g, tr.row0 + q * 32 + lane, tr.row_end);
         const int my_orow = m.valid ? m.orow : -1;
@@ -351,7 +386,8 @@ __global__ void __launch_bounds__(64 + EPI_WARPS * 32, 1) gemm_tc_kernel(const _
           }
           if (sbi == nvs - 1) {
             tc_fence_before();
-            mbar_arrive(tempty);
+            if constexpr (PAIR) mbar_arrive_cluster(mapa_shared(tempty, 0));
+            else mbar_arrive(tempty);
           }
           if (m.valid)
             epilogue_math<SUB>(g, m, n0 + cbase, acc, g.scale ? g.scale + n0 + cbase : nullptr, g.bias ? g.bias + n0 + cbase : nullptr);
@@ -423,25 +459,27 @@ __global__ void __launch_bounds__(64 + EPI_WARPS * 32, 1) gemm_tc_kernel(const _
   }
   tc_fence_before();
   __syncthreads();
+  if constexpr (PAIR) cluster_sync_all();  // neither CTA may leave while the other can still signal its barriers / TMEM
   if (warp == 1) {
     tc_fence_after();
-    tc_dealloc(tmem_base, L::TMEM_COLS);
+    if constexpr (PAIR) tc_dealloc_pair(tmem_base, L::TMEM_COLS);
+    else tc_dealloc(tmem_base, L::TMEM_COLS);
   }
 }
 
 // ---------------------------------------------------------------- host side
 int g_num_sms = 0;
 
-template <int BN, int STAGES, int NBUF, int MODE, bool CONV3 = false, int EPI_WARPS = 8>
+template <int BN, int STAGES, int NBUF, int MODE, bool CONV3 = false, int EPI_WARPS = 8, bool PAIR = false>
 int launch(const CrogGemm* g, cudaStream_t stream) {
-  using L = Cfg<BN, STAGES, NBUF, CONV3, EPI_WARPS>;
+  using L = Cfg<BN, STAGES, NBUF, CONV3, EPI_WARPS, PAIR>;
   static_assert(L::TOTAL <= 227 * 1024, "shared memory budget");
   static bool attr_set = false;  // per-process; device attribute is re-set cheaply if another device is used
   static int attr_dev = -1;
   int dev = 0;
   CROG_CUDA_OK(cudaGetDevice(&dev));
   if (!attr_set || attr_dev != dev) {
-    CROG_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES, NBUF, MODE, CONV3, EPI_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+    CROG_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES, NBUF, MODE, CONV3, EPI_WARPS, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
     CROG_CUDA_OK(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
     attr_set = true; attr_dev = dev;
   }
@@ -451,7 +489,7 @@ int launch(const CrogGemm* g, cudaStream_t stream) {
   if (rc) return rc;
   uint64_t wrows = (uint64_t)g->N;
   if (g->w_sample_stride > 0) wrows = (uint64_t)(g->w_sample_stride / Ktot) * (uint64_t)(g->M / g->sample_rows);
-  rc = crog_encode_2d(&tmB, g->w, CROG_BF16, (uint64_t)Ktot, wrows, (uint64_t)Ktot, BN);
+  rc = crog_encode_2d(&tmB, g->w, CROG_BF16, (uint64_t)Ktot, wrows, (uint64_t)Ktot, L::B_ROWS);
   if (rc) return rc;
   if (MODE != MODE_LEGACY) {
     rc = crog_encode_2d(&tmOut, g->out, g->out_dtype, (uint64_t)g->N, (uint64_t)g->M, (uint64_t)g->out_ld, 32);
@@ -465,10 +503,22 @@ int launch(const CrogGemm* g, cudaStream_t stream) {
     tmOut = tmA; tmRes = tmA;  // unused
   }
   const int n_tiles = (g->N + BN - 1) / BN;
-  const int total = num_m_tiles(*g, BM) * n_tiles;
+  const int total = num_m_tiles(*g, PAIR ? 2 * BM : BM) * n_tiles;
   if (total == 0) return CROG_OK;
+  if constexpr (PAIR) {
+    // one cluster of two CTAs (an SM pair of one TPC) per tile stream
+    const int pairs = total < g_num_sms / 2 ? total : g_num_sms / 2;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * pairs); cfg.blockDim = dim3(L::NUM_THREADS); cfg.dynamicSmemBytes = L::TOTAL; cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    CROG_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, STAGES, NBUF, MODE, CONV3, EPI_WARPS, PAIR>, tmA, tmB, tmOut, tmRes, *g, n_tiles, total));
+    return CROG_OK;
+  }
   const int grid = total < g_num_sms ? total : g_num_sms;
-  crog_launch(gemm_tc_kernel<BN, STAGES, NBUF, MODE, CONV3, EPI_WARPS>, dim3(grid), dim3(L::NUM_THREADS), L::TOTAL, stream, tmA, tmB, tmOut, tmRes, *g, n_tiles, total);
+  crog_launch(gemm_tc_kernel<BN, STAGES, NBUF, MODE, CONV3, EPI_WARPS, PAIR>, dim3(grid), dim3(L::NUM_THREADS), L::TOTAL, stream, tmA, tmB, tmOut, tmRes, *g, n_tiles, total);
   CROG_LAUNCH_OK("gemm_tc");
   return CROG_OK;
 }
@@ -483,6 +533,10 @@ int dispatch(const CrogGemm* g, cudaStream_t stream) {
   if (g->N % 256 == 0 && (long long)g->taps * g->cin >= 1024) {
     // long contractions: the TMA feed is the pace (96 B/clk/SM at full tensor rate), so a fourth 48 KB stage in flight
     // is worth more than a second epilogue group (measured 3-12 % per layer; CROG_GEMM_3STAGE restores the old config)
+    // CTA pairs (cta_group::2) whenever there is at least one 256-row tile per pair: +2-5 % on the long convolutions
+    // (proj.vis.3: 1350 -> 1422 TFLOP/s); CROG_GEMM_PAIR=0 falls back to single-CTA tiles
+    const char* pe = getenv("CROG_GEMM_PAIR");  // read per call (launches are graph-captured; tests toggle it)
+    if (g->w_sample_stride == 0 && g->M >= 256 * 74 && !(pe && pe[0] == '0')) return launch<256, 6, 2, MODE, false, 4, true>(g, stream);
     if (!getenv("CROG_GEMM_3STAGE")) return launch<256, 4, 2, MODE, false, 4>(g, stream);
     return launch<256, 3, 2, MODE>(g, stream);
   }

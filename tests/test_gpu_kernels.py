@@ -402,3 +402,42 @@ def test_reference_signature_wrappers():
     assert gt[0, 3] == 20 and gt[0, 2] == 100
     assert GE.calculate_jacquard_index([], np.array([[200., 200., 50., 20., 5., 1.]])) == 0
     assert GE.calculate_max_iou([[200, 200, 60, 20, 10]], [[200, 200, 60, 20, 10, 1]]) == 1.0
+
+
+@pytest.mark.parametrize("case", ["conv3x3_pad2pad_tma", "conv3x3_pad2compact_legacy", "linear_residual_f32"])
+def test_gemm_cta_pair_matches_single_cta(case, monkeypatch):
+    """The cta_group::2 path (two CTAs share one 256 x 256 tile) must give the same bytes as the single-CTA tile loop:
+    same k order, same fp32 accumulation, same epilogue code.  M is not a multiple of 256, so the last tile has a
+    partly / fully out-of-range CTA."""
+    torch.manual_seed(5)
+    dt = torch.bfloat16
+    if case.startswith("conv3x3"):
+        B, H, W, Cin, Cout = 6, 58, 60, 256, 256  # M = 6*60*62 = 22320 padded rows (> 256*74, not a multiple of 256)
+        x = torch.randn(B, Cin, H, W, device="cuda")
+        w = torch.randn(Cout, Cin, 3, 3, device="cuda") * (Cin * 9) ** -0.5
+        sc, bi = torch.rand(Cout, device="cuda") + 0.5, torch.randn(Cout, device="cuda")
+        a = pad_nhwc(x, dt)
+        out_padded = case.endswith("tma")
+
+        def run():
+            rows = B * (H + 2) * (W + 2) if out_padded else B * H * W
+            out = torch.zeros((rows, Cout), device="cuda", dtype=dt)
+            run_gemm(a, conv_w(w, dt), Cout, out, taps=9, H=H, W=W, in_padded=True, out_padded=out_padded,
+                     sample_rows=(H + 2) * (W + 2), scale=sc, bias=bi, act=L.ACT_RELU, impl=L.IMPL_TCGEN05)
+            return out
+    else:
+        M, N, K = 256 * 80 + 77, 512, 2048
+        a = (torch.randn(M, K, device="cuda") * 0.5).to(dt)
+        w = (torch.randn(N, K, device="cuda") * K ** -0.5).to(dt)
+        bi = torch.randn(N, device="cuda")
+        res = torch.randn(M, N, device="cuda")
+
+        def run():
+            out = res.clone()
+            run_gemm(a, w, N, out, bias=bi, residual=out, impl=L.IMPL_TCGEN05)
+            return out
+    monkeypatch.setenv("CROG_GEMM_PAIR", "0")  # single-CTA tiles
+    want = run()
+    monkeypatch.delenv("CROG_GEMM_PAIR")       # default dispatch: CTA pairs for these shapes
+    got = run()
+    assert torch.equal(got, want), f"max diff {maxerr(got, want)}"
