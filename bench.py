@@ -51,7 +51,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50",
                                           "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except Exception:
@@ -79,24 +79,52 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def cpu_port_samples_per_sec(word_len: int, n_samples: int, threads: int):
-    """The reference's CPU path restated (oracle port): fp32 torch forward + sigmoid/bicubic + serial decode/Jaccard loop."""
+_CPU_STATE = {}
+
+
+def workload_config(B: int, Lw: int, world: int):
+    """The `config` object of the JSON line (identical for both arms)."""
+    return {"workload": f"CROG R50 (crog_multiple_r50.yaml shapes) batched inference + grasp decode + Jaccard, batch {B}/GPU, "
+                        f"416x416, L={Lw}, bf16, random-init (seeded) weights",
+            "global_batch": B * world, "parallelism": f"dp{world}",
+            "l2": "no explicit flush: one step streams ~6 GB of activations, far above the 126 MB L2"}
+
+
+def cpu_port_samples_per_sec(word_len: int, n_samples: int, threads: int, fwd_batch: int = 1):
+    """The reference's CPU path restated (oracle port): fp32 torch forward on `threads` host threads, sigmoid/bicubic,
+    then the serial per-sample decode / Jaccard loop (engine/crog_engine.py:478-527).  `fwd_batch` = samples per forward
+    (the reference's test script uses 1, test_crog.py:62; 8 fills the cores better)."""
     from oracle import crog_forward as O
     from oracle import grasp_tail_c as TC
 
     torch.set_num_threads(threads)
-    cfg = synth.default_cfg(word_len)
-    sd = synth.make_state_dict(cfg, 0, "perturbed")
-    img, word = synth.make_inputs(n_samples, word_len)
-    gt, cnt = synth.make_gt_rects(n_samples, 64, seed=4)
+    key = (word_len, n_samples)
+    if key not in _CPU_STATE:
+        cfg = synth.default_cfg(word_len)
+        _CPU_STATE.clear()
+        _CPU_STATE[key] = (cfg, synth.make_state_dict(cfg, 0, "perturbed"), synth.make_inputs(n_samples, word_len),
+                           synth.make_gt_rects(n_samples, 64, seed=4))
+    cfg, sd, (img, word), (gt, cnt) = _CPU_STATE[key]
     O.crog_forward(sd, cfg, img[:1], word[:1])  # warm-up (thread pool, allocator)
     t0 = time.perf_counter()
-    for b in range(n_samples):  # the reference evaluates with batch_size=1 (test_crog.py:62)
-        maps, _ = O.crog_forward(sd, cfg, img[b:b + 1], word[b:b + 1])
+    for b in range(0, n_samples, fwd_batch):
+        e = min(b + fwd_batch, n_samples)
+        maps, _ = O.crog_forward(sd, cfg, img[b:e], word[b:e])
         post = [p.numpy() for p in O.postprocess(maps, (416, 416))]
-        TC.tail_batch(post[1], post[2], post[3], post[4], gt[b:b + 1], cnt[b:b + 1])
+        for i in range(e - b):  # serial per-sample tail, as in the reference
+            TC.tail_batch(post[1][i:i + 1], post[2][i:i + 1], post[3][i:i + 1], post[4][i:i + 1], gt[b + i:b + i + 1], cnt[b + i:b + i + 1])
     dt = time.perf_counter() - t0
     return n_samples / dt, dt
+
+
+def cpu_baseline(word_len: int, n_samples: int, threads: int):
+    """Best of the two ways of driving the CPU path (1 or 8 samples per forward) on a bounded sample."""
+    best = None
+    for fb in (1, 8):
+        v, dt = cpu_port_samples_per_sec(word_len, n_samples, threads, fb)
+        if best is None or v > best[0]:
+            best = (v, dt, fb)
+    return best
 
 
 def run_reference(args):
@@ -106,11 +134,13 @@ def run_reference(args):
     threads = os.cpu_count() or 1
     n = args.cpu_samples
     vals = []
-    for _ in range(args.warmup):
-        cpu_port_samples_per_sec(args.word_len, 1, threads)
+    n = max(8, min(n, 16))  # bounded per-step sample: K steps x 16 samples stays within a few minutes
+    fb = 8
+    for _ in range(max(args.warmup, 1)):
+        cpu_port_samples_per_sec(args.word_len, n, threads, fb)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        v, _ = cpu_port_samples_per_sec(args.word_len, n, threads)
+        v, _ = cpu_port_samples_per_sec(args.word_len, n, threads, fb)
         vals.append(v)
     total = time.perf_counter() - t0
     value = float(np.median(vals))
@@ -118,9 +148,10 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * total / max(args.steps, 1), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"CROG R50 inference + grasp decode + Jaccard, 416x416, L={args.word_len}, CPU fp32, batch 1 per forward"},
+        "config": workload_config(args.batch, args.word_len, max(args.gpus, 1)),
         "cpu_baseline": {"value": value, "unit": "samples/s", "cores": threads, "kind": "port",
-                         "sample": f"{n} samples per step: oracle/crog_forward.py (torch CPU fp32) + oracle/grasp_tail.c, serial loop"},
+                         "sample": f"{n} samples per step ({fb} per forward): oracle/crog_forward.py (torch CPU fp32, all host threads) + "
+                                   "oracle/grasp_tail.c serial decode/Jaccard loop; the reference itself is Python and cannot travel to the GPU box"},
         "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -215,12 +246,12 @@ def run_tail(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=64, help="samples per GPU per step")
     ap.add_argument("--word-len", type=int, default=17)
-    ap.add_argument("--cpu-samples", type=int, default=4, help="bounded CPU-baseline sample")
+    ap.add_argument("--cpu-samples", type=int, default=48, help="bounded CPU-baseline sample (about 10-20 s of CPU work)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--workload", default="forward", choices=["forward", "tail"])
@@ -352,9 +383,13 @@ def main():
         alg = sum(plan.gemm_alg_flops.values())
         t_gemm = float(durs[is_gemm].sum()) / 1e3
         achieved = alg / t_gemm / 1e12
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "r1_gemm_traffic.json")  # per-launch DRAM bytes of this kernel family (ncu)
+        if os.path.exists(tp):
+            traffic = json.load(open(tp)).get("dram_bytes_per_launch_avg")
         roof = {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05 implicit GEMM, all conv/linear layers)",
                 "achieved": achieved, "peak": tf_peak, "unit": "TFLOP/s", "frac": achieved / tf_peak, "peak_source": which + " sustained",
-                "traffic": None, "launches": int(is_gemm.sum()), "alg_gflop_per_launch_avg": alg / 1e9 / max(int(is_gemm.sum()), 1),
+                "traffic": traffic, "launches": int(is_gemm.sum()), "alg_gflop_per_launch_avg": alg / 1e9 / max(int(is_gemm.sum()), 1),
                 "share_of_forward": t_gemm / (float(durs.sum()) / 1e3),
                 "whole_step_frac_of_peak": ALG_GFLOP_PER_SAMPLE.get(Lw, 137.56) * 1e9 * (value / world) / 1e12 / tf_peak}
         order = np.argsort(-durs)[:12]
@@ -368,9 +403,10 @@ def main():
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
-        v, dt = cpu_port_samples_per_sec(Lw, args.cpu_samples, threads)
+        v, dt, fb = cpu_baseline(Lw, args.cpu_samples, threads)
         cpu = {"value": v, "unit": "samples/s", "cores": threads, "kind": "port",
-               "sample": f"{args.cpu_samples} samples, batch 1 per forward ({dt:.1f} s): oracle torch-CPU fp32 forward + C decode/Jaccard"}
+               "sample": f"{args.cpu_samples} samples of the same workload, {fb} per forward ({dt:.1f} s; best of 1 / 8 per forward): "
+                         "oracle torch-CPU fp32 forward + sigmoid/bicubic + C decode/Jaccard serial loop"}
 
     if rank == 0:
         launches_per_step = plan.n_launches + 1 + 3 + 1  # forward + sigmoid/bicubic + (scan, select, exact) + jaccard
@@ -378,10 +414,7 @@ def main():
             "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
             "data": "synthetic",
-            "config": {"workload": f"CROG R50 (crog_multiple_r50.yaml shapes) batched inference + grasp decode + Jaccard, batch {B}/GPU, "
-                                   f"416x416, L={Lw}, bf16, random-init (seeded) weights",
-                       "global_batch": B * world, "parallelism": f"dp{world}",
-                       "l2": "no explicit flush: one step streams ~6 GB of activations, far above the 126 MB L2"},
+            "config": workload_config(B, Lw, world),
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches_per_step * args.steps,
             "roofline": roof, "cpu_baseline": cpu, "j_counters": counters, "top_ops_ms": op_table,
         }

@@ -20,9 +20,10 @@ __global__ void __launch_bounds__(256) resample_kernel(const T* __restrict__ in,
   const int OH = MODE == 1 ? H / 2 : (MODE == 2 ? 2 * H : H);
   const int OW = MODE == 1 ? W / 2 : (MODE == 2 ? 2 * W : W);
   const int cgs = C / 8;
-  const int b = blockIdx.x / OH, oy = blockIdx.x % OH;
+  const int rows_per_b = MODE == 2 ? H + 1 : OH;  // bilinear: one CTA per output row PAIR
+  const int b = blockIdx.x / rows_per_b, oy = blockIdx.x % rows_per_b;
   const T* ip = in;
-  T* op = out + pix_row(b, oy, 0, OH, OW, out_padded) * out_ld;
+  T* op = out + pix_row(b, MODE == 2 ? 0 : oy, 0, OH, OW, out_padded) * out_ld;
   const int n = OW * cgs;
   if (MODE == 0) {
     ip = in + pix_row(b, oy, 0, H, W, in_padded) * in_ld;
@@ -47,34 +48,58 @@ __global__ void __launch_bounds__(256) resample_kernel(const T* __restrict__ in,
       store8(op + (long long)ox * out_ld + cg * 8, v);
     }
   } else {
-    // F.interpolate(scale_factor=2, mode='bilinear', align_corners=False)
-    const float sy = fmaxf((oy + 0.5f) * 0.5f - 0.5f, 0.f);
-    const int y0 = (int)sy, y1 = min(y0 + 1, H - 1);
-    const float ly = sy - y0, hy = 1.f - ly;
-    const T* r0 = in + pix_row(b, y0, 0, H, W, in_padded) * in_ld;
-    const T* r1 = in + pix_row(b, y1, 0, H, W, in_padded) * in_ld;
-    for (int i = threadIdx.x; i < n; i += 256) {
-      const int ox = i / cgs, cg = i - ox * cgs;
-      const float sx = fmaxf((ox + 0.5f) * 0.5f - 0.5f, 0.f);
-      const int x0 = (int)sx, x1 = min(x0 + 1, W - 1);
-      const float lx = sx - x0, hx = 1.f - lx;
-      float v[8], a[8], c[8], d[8];
-      load8(r0 + (long long)x0 * in_ld + cg * 8, v);
-      load8(r0 + (long long)x1 * in_ld + cg * 8, a);
-      load8(r1 + (long long)x0 * in_ld + cg * 8, c);
-      load8(r1 + (long long)x1 * in_ld + cg * 8, d);
+    // F.interpolate(scale_factor=2, mode='bilinear', align_corners=False).  Output rows 2k-1 and 2k read input rows
+    // k-1 and k (clamped) with weights (.75,.25) / (.25,.75), and the same holds for columns, so one thread turns a
+    // 2x2 input neighbourhood (four 16-byte loads) into a 2x2 output block: a quarter of the loads and about a
+    // third of the instructions of the one-output-per-thread form.  CTA = output row pair k in [0, H].
+    const int k = oy;  // here blockIdx.x enumerates (b, k) with k in [0, H]  (OH := H + 1 in the launch)
+    const int ya = max(k - 1, 0), yb = min(k, H - 1);
+    const T* r0 = in + pix_row(b, ya, 0, H, W, in_padded) * in_ld;
+    const T* r1 = in + pix_row(b, yb, 0, H, W, in_padded) * in_ld;
+    const int oy0 = 2 * k - 1, oy1 = 2 * k;  // valid if in [0, 2H)
+    T* o0 = oy0 >= 0 ? out + pix_row(b, oy0, 0, 2 * H, 2 * W, out_padded) * out_ld : nullptr;
+    T* o1 = oy1 < 2 * H ? out + pix_row(b, oy1, 0, 2 * H, 2 * W, out_padded) * out_ld : nullptr;
+    const int nj = (W + 1) * cgs;
+    for (int i = threadIdx.x; i < nj; i += 256) {
+      const int j = i / cgs, cg = i - j * cgs;
+      const int xa = max(j - 1, 0), xb = min(j, W - 1);
+      float p[8], q[8], r[8], t[8];  // (ya,xa) (ya,xb) (yb,xa) (yb,xb)
+      load8(r0 + (long long)xa * in_ld + cg * 8, p);
+      load8(r0 + (long long)xb * in_ld + cg * 8, q);
+      load8(r1 + (long long)xa * in_ld + cg * 8, r);
+      load8(r1 + (long long)xb * in_ld + cg * 8, t);
+      const int ox0 = 2 * j - 1, ox1 = 2 * j;
+      // the reference computes hy*(hx*a + lx*b) + ly*(hx*c + lx*d) with (l, h) = (.25, .75) for odd and (.75, .25) for
+      // even output coordinates; at the clamped borders both taps coincide, so the same formula holds there
+      float v[8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) v[j] = hy * (hx * v[j] + lx * a[j]) + ly * (hx * c[j] + lx * d[j]);
-      store8(op + (long long)ox * out_ld + cg * 8, v);
+      for (int half = 0; half < 4; ++half) {
+        const bool oddy = (half & 2) == 0, oddx = (half & 1) == 0;  // half 0: (oy0, ox0), 1: (oy0, ox1), 2: (oy1, ox0), 3: (oy1, ox1)
+        T* orow = oddy ? o0 : o1;
+        const int ox = oddx ? ox0 : ox1;
+        if (orow == nullptr || ox < 0 || ox >= 2 * W) continue;
+        const float ly = (!oddy && k == 0) ? 0.f : (oddy ? 0.25f : 0.75f), hy = 1.f - ly;  // row / column 0: sy clamps to 0
+        const float lx = (!oddx && j == 0) ? 0.f : (oddx ? 0.25f : 0.75f), hx = 1.f - lx;
+        // odd outputs (2k-1): sy = k - 0.75 -> y0 = k-1, ly = .25; even (2k): sy = k - .25 -> y0 = k-1, ly = .75;
+        // row 0 / col 0 clamp to sy = 0 (ly = 0): with ya == yb the blend is the same value
+#pragma unroll
+        for (int c = 0; c < 8; ++c) v[c] = hy * (hx * p[c] + lx * q[c]) + ly * (hx * r[c] + lx * t[c]);
+        store8(orow + (long long)ox * out_ld + cg * 8, v);
+      }
     }
   }
 }
 
 // ------------------------------------------------------------------ stem conv1 (3->cout, 3x3, stride 2, pad 1)
+// Thread = (two horizontally adjacent output pixels) x (8 output channels): the 3 x 5 x 3 input window is loaded once
+// for both pixels (45 scalar loads instead of 54) and every weight vector read from shared memory feeds 16 FMAs
+// (the one-pixel form was bound by its LDS stream at 4 FMAs per LDS.128).  Channel groups are the fastest thread
+// index, so a pixel's cout channels are one contiguous store.  Only channels [0, cout) are written: the padding
+// channels of the zero-initialised plan buffer stay zero.
 template <typename T>
-__global__ void stem_conv1_kernel(const float* __restrict__ img, int B, int Hin, int Win, const float* __restrict__ w,
-                                  const float* __restrict__ scale, const float* __restrict__ bias, int cout,
-                                  T* __restrict__ out, int out_ld) {
+__global__ void __launch_bounds__(128) stem_conv1_kernel(const float* __restrict__ img, int B, int Hin, int Win,
+                                                          const float* __restrict__ w, const float* __restrict__ scale,
+                                                          const float* __restrict__ bias, int cout, T* __restrict__ out, int out_ld) {
   extern __shared__ __align__(16) float sw[];  // [27][cout] + scale + bias
   pdl_launch();  // the weights below are constants of the plan: staging them overlaps the predecessor's tail
   for (int i = threadIdx.x; i < 27 * cout; i += blockDim.x) {
@@ -84,41 +109,56 @@ __global__ void stem_conv1_kernel(const float* __restrict__ img, int B, int Hin,
   for (int i = threadIdx.x; i < cout; i += blockDim.x) { sw[27 * cout + i] = scale[i]; sw[28 * cout + i] = bias[i]; }
   __syncthreads();
   pdl_wait();
-  const int OH = Hin / 2, OW = Win / 2;
-  const long long total = (long long)B * OH * OW;
+  const int OH = Hin / 2, OW = Win / 2, OWP = (OW + 1) / 2, cgs = cout / 8;
+  const long long total = (long long)B * OH * OWP * cgs;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int ox = (int)(i % OW);
-    const int oy = (int)((i / OW) % OH);
-    const int b = (int)(i / ((long long)OW * OH));
-    float x[27];
+    const int cg = (int)(i % cgs);
+    long long t = i / cgs;
+    const int oxp = (int)(t % OWP);
+    t /= OWP;
+    const int oy = (int)(t % OH), b = (int)(t / OH);
+    const int ox = 2 * oxp;
+    float x[3][3][5];
+#pragma unroll
+    for (int ci = 0; ci < 3; ++ci)
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky) {
+        const int iy = 2 * oy + ky - 1;
+        const float* rowp = img + ((long long)(b * 3 + ci) * Hin + iy) * Win;
+#pragma unroll
+        for (int kx = 0; kx < 5; ++kx) {
+          const int ix = 2 * ox + kx - 1;
+          x[ci][ky][kx] = (iy >= 0 && iy < Hin && ix >= 0 && ix < Win) ? __ldg(rowp + ix) : 0.f;
+        }
+      }
+    float v0[8], v1[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { v0[j] = 0.f; v1[j] = 0.f; }
+    const int c0 = cg * 8;
 #pragma unroll
     for (int ci = 0; ci < 3; ++ci)
 #pragma unroll
       for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
         for (int kx = 0; kx < 3; ++kx) {
-          const int iy = 2 * oy + ky - 1, ix = 2 * ox + kx - 1;
-          x[ci * 9 + ky * 3 + kx] = (iy >= 0 && iy < Hin && ix >= 0 && ix < Win)
-                                        ? __ldg(img + ((long long)(b * 3 + ci) * Hin + iy) * Win + ix) : 0.f;
-        }
-    T* o = out + pix_row(b, oy, ox, OH, OW, 1) * out_ld;
-    for (int c0 = 0; c0 < out_ld; c0 += 8) {
-      float v[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) v[j] = 0.f;
-      if (c0 + 8 <= cout) {  // cout is a multiple of 8: whole groups only
-#pragma unroll
-        for (int k = 0; k < 27; ++k) {
+          const int k = ci * 9 + ky * 3 + kx;
           const float4 w0 = *reinterpret_cast<const float4*>(&sw[k * cout + c0]);
           const float4 w1 = *reinterpret_cast<const float4*>(&sw[k * cout + c0 + 4]);
-          v[0] = fmaf(x[k], w0.x, v[0]); v[1] = fmaf(x[k], w0.y, v[1]); v[2] = fmaf(x[k], w0.z, v[2]); v[3] = fmaf(x[k], w0.w, v[3]);
-          v[4] = fmaf(x[k], w1.x, v[4]); v[5] = fmaf(x[k], w1.y, v[5]); v[6] = fmaf(x[k], w1.z, v[6]); v[7] = fmaf(x[k], w1.w, v[7]);
+          const float a = x[ci][ky][kx], c = x[ci][ky][kx + 2];
+          v0[0] = fmaf(a, w0.x, v0[0]); v0[1] = fmaf(a, w0.y, v0[1]); v0[2] = fmaf(a, w0.z, v0[2]); v0[3] = fmaf(a, w0.w, v0[3]);
+          v0[4] = fmaf(a, w1.x, v0[4]); v0[5] = fmaf(a, w1.y, v0[5]); v0[6] = fmaf(a, w1.z, v0[6]); v0[7] = fmaf(a, w1.w, v0[7]);
+          v1[0] = fmaf(c, w0.x, v1[0]); v1[1] = fmaf(c, w0.y, v1[1]); v1[2] = fmaf(c, w0.z, v1[2]); v1[3] = fmaf(c, w0.w, v1[3]);
+          v1[4] = fmaf(c, w1.x, v1[4]); v1[5] = fmaf(c, w1.y, v1[5]); v1[6] = fmaf(c, w1.z, v1[6]); v1[7] = fmaf(c, w1.w, v1[7]);
         }
 #pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j] * sw[27 * cout + c0 + j] + sw[28 * cout + c0 + j], 0.f);
-      }
-      store8(o + c0, v);
+    for (int j = 0; j < 8; ++j) {
+      const float sc = sw[27 * cout + c0 + j], bi = sw[28 * cout + c0 + j];
+      v0[j] = fmaxf(v0[j] * sc + bi, 0.f);
+      v1[j] = fmaxf(v1[j] * sc + bi, 0.f);
     }
+    T* o = out + pix_row(b, oy, ox, OH, OW, 1) * out_ld + c0;
+    store8(o, v0);
+    if (ox + 1 < OW) store8(o + out_ld, v1);
   }
 }
 
@@ -369,7 +409,7 @@ extern "C" int crog_resample(const void* in, int32_t in_ld, int32_t in_padded, v
   if (mode == 1) CROG_REQUIRE(H % 2 == 0 && W % 2 == 0, CROG_E_BADSHAPE, "avgpool2 needs even H,W");
   const int OH = mode == 1 ? H / 2 : (mode == 2 ? 2 * H : H), OW = mode == 1 ? W / 2 : (mode == 2 ? 2 * W : W);
   if ((long long)B * OH * OW * C == 0) return CROG_OK;
-  const int g = B * OH;
+  const int g = mode == 2 ? B * (H + 1) : B * OH;
   cudaStream_t s = (cudaStream_t)stream;
 #define RS(T, M) crog_launch(resample_kernel<T, M>, dim3(g), dim3(256), 0, s, (const T*)in, in_ld, in_padded, (T*)out, out_ld, out_padded, B, H, W, C)
   if (dtype == CROG_F32) { if (mode == 0) RS(float, 0); else if (mode == 1) RS(float, 1); else RS(float, 2); }
@@ -382,7 +422,7 @@ extern "C" int crog_resample(const void* in, int32_t in_ld, int32_t in_padded, v
 extern "C" int crog_stem_conv1(const float* img, int32_t B, int32_t Hin, int32_t Win, const float* w, const float* scale,
                                const float* bias, int32_t cout, void* out, int32_t out_ld, int32_t out_dtype, void* stream) {
   CROG_REQUIRE(Hin % 2 == 0 && Win % 2 == 0 && out_ld % 8 == 0 && cout <= out_ld && cout % 8 == 0, CROG_E_BADSHAPE, "stem_conv1: bad shape");
-  const long long total = (long long)B * (Hin / 2) * (Win / 2);
+  const long long total = (long long)B * (Hin / 2) * ((Win / 2 + 1) / 2) * (cout / 8);  // (pixel pair, 8-channel group) threads
   if (total == 0) return CROG_OK;
   const int g = grid_for(total, 128);
   const size_t sm = (size_t)(29 * cout) * sizeof(float);

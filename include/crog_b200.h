@@ -104,7 +104,8 @@ int crog_resample(const void* in, int32_t in_ld, int32_t in_padded, void* out, i
                   int32_t dtype, void* stream);
 
 /* Stem conv1: 3x3 stride 2 pad 1 on NCHW fp32 images + folded BN + ReLU, writing the padded
- * NHWC layout (model/clip.py:165-170,208-211). w [cout,3,3,3] fp32. out channels >= cout are zeroed. */
+ * NHWC layout (model/clip.py:165-170,208-211). w [cout,3,3,3] fp32. Only channels [0, cout) of the interior pixels are
+ * written: halo pixels and the padding channels [cout, out_ld) must already be zero (the caller's zero-initialised buffer). */
 int crog_stem_conv1(const float* img, int32_t B, int32_t Hin, int32_t Win, const float* w,
                     const float* scale, const float* bias, int32_t cout, void* out, int32_t out_ld,
                     int32_t out_dtype, void* stream);
