@@ -84,9 +84,11 @@ __global__ void __launch_bounds__(64 + EPI_WARPS * 32, 1) gemm_tc_kernel(const _
 
   pdl_launch();  // the successor may start its prologue as soon as this grid is resident
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;               // 0 = leader (issues the MMAs)
-  const int tile0 = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;  // both CTAs of a pair walk the same tiles
-  const int tstep = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  // Written as expressions, not variables: with named copies of blockIdx.x / gridDim.x nvcc schedules the single-CTA
+  // CONV3 kernels 11 % slower (measured A/B on one box: stem.conv2 260 -> 292 us) although the SASS mix is identical.
+#define rank (PAIR ? cluster_ctarank() : 0u)                          /* 0 = leader (issues the MMAs) */
+#define tile0 (PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x)       /* both CTAs of a pair walk the same tiles */
+#define tstep (PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x)
   const int kchunks = g.cin / BK;
   const int num_kb = CONV3 ? 3 : g.taps * kchunks;  // CONV3: one k-block per ky band
   const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + STAGES), tfull0 = smem_u32(bars + 2 * STAGES),
@@ -466,6 +468,10 @@ __global__ void __launch_bounds__(64 + EPI_WARPS * 32, 1) gemm_tc_kernel(const _
     else tc_dealloc(tmem_base, L::TMEM_COLS);
   }
 }
+
+#undef rank
+#undef tile0
+#undef tstep
 
 // ---------------------------------------------------------------- host side
 int g_num_sms = 0;
