@@ -208,8 +208,8 @@ def run_tail(args):
         counters = torch.zeros(4, dtype=torch.int64, device=dev)
 
         def step():
-            peaks_, npk, grasps = GE.detect_grasps_batched(q, s, c, w, K)
-            GE.jacquard_batched(grasps, npk, d_gt, d_cnt, counters=counters)
+            # sub-batches on two streams: the Jaccard rasterisation of one overlaps the peak scan of the next
+            peaks_, npk, grasps, _ = GE.decode_and_score_batched(q, s, c, w, d_gt, d_cnt, K, counters=counters, chunks=args.tail_chunks)
             return peaks_, npk, grasps
 
         for _ in range(max(args.warmup, 3)):
@@ -239,7 +239,7 @@ def run_tail(args):
                                    "(value) and 'stress' (iid uniform + plateaus) below", "l2": "inputs (2.8 GB of quality maps) exceed L2"},
             "roofline": {"bound": "hbm", "kernel": "peak_scan_kernel + peak_select + jaccard", "achieved": r["gbs"], "peak": hbm_peak,
                          "unit": "GB/s", "frac": r["gbs"] / hbm_peak, "peak_source": which, "traffic": None},
-            "stress": res["stress"], "blobs": res["blobs"], "gpu_launches": 4 * args.steps}
+            "stress": res["stress"], "blobs": res["blobs"], "gpu_launches": 4 * args.tail_chunks * args.steps}
     print(json.dumps(line), flush=True)
 
 
@@ -256,6 +256,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--workload", default="forward", choices=["forward", "tail"])
     ap.add_argument("--tail-maps", type=int, default=4096)
+    ap.add_argument("--tail-chunks", type=int, default=1, help="sub-batches of the tail (scan of i+1 overlaps Jaccard of i)")
     ap.add_argument("--dump-ops", default=None, help="write the per-op CUDA-event table (eager replay) to this file")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
@@ -391,6 +392,7 @@ def main():
                 "achieved": achieved, "peak": tf_peak, "unit": "TFLOP/s", "frac": achieved / tf_peak, "peak_source": which + " sustained",
                 "traffic": traffic, "launches": int(is_gemm.sum()), "alg_gflop_per_launch_avg": alg / 1e9 / max(int(is_gemm.sum()), 1),
                 "share_of_forward": t_gemm / (float(durs.sum()) / 1e3),
+                "autotuned_layers": sum(1 for v in plan.tile_choice.values() if v[0] != 0),
                 "whole_step_frac_of_peak": ALG_GFLOP_PER_SAMPLE.get(Lw, 137.56) * 1e9 * (value / world) / 1e12 / tf_peak}
         order = np.argsort(-durs)[:12]
         op_table = [{"op": names[i], "ms": round(float(durs[i]), 4)} for i in order]
@@ -398,7 +400,9 @@ def main():
             with open(args.dump_ops, "w") as f:
                 for i, n in enumerate(names):
                     gf = plan.gemm_alg_flops.get(n, 0) / 1e9
-                    f.write(f"{i:4d} {n:50s} {durs[i]:9.4f} ms {gf:10.2f} GF {gf / max(durs[i], 1e-9):9.1f} TF/s\n")
+                    tc = plan.tile_choice.get(n)
+                    tcs = f"  tile_cfg {tc[0]} ({tc[1]:.1f} us vs heuristic {tc[2]:.1f} us)" if tc else ""
+                    f.write(f"{i:4d} {n:50s} {durs[i]:9.4f} ms {gf:10.2f} GF {gf / max(durs[i], 1e-9):9.1f} TF/s{tcs}\n")
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

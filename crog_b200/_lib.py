@@ -15,6 +15,9 @@ SO_PATH = os.path.join(_HERE, "lib", "libcrog_b200.so")
 F32, BF16 = 0, 1
 ACT_NONE, ACT_RELU, ACT_QUICKGELU, ACT_TANH = 0, 1, 2, 3
 IMPL_AUTO, IMPL_SIMT, IMPL_TCGEN05 = 0, 1, 2
+# CROG_TILE_* of include/crog_b200.h (CrogGemm.tile_cfg)
+(TILE_AUTO, TILE_128x128, TILE_128x256, TILE_128x256_E8, TILE_PAIR_256x256, TILE_PAIR_256x256_E8, TILE_PAIR_256x128,
+ TILE_128x64, TILE_CONV3, TILE_COUNT) = range(10)
 RS_COPY, RS_AVGPOOL2, RS_BILINEAR2, RS_SUBSAMPLE2, RS_BILINEAR2_AC = 0, 1, 2, 3, 4
 
 
@@ -31,7 +34,7 @@ class CrogGemm(C.Structure):
         ("addmat_rows", C.c_int32), ("act", C.c_int32), ("gate", C.c_void_p), ("scale2", C.c_void_p),
         ("bias2", C.c_void_p), ("residual", C.c_void_p), ("res_ld", C.c_int32), ("residual_relu", C.c_int32),
         ("out", C.c_void_p), ("out_ld", C.c_int32), ("out_dtype", C.c_int32), ("impl", C.c_int32),
-        ("out_sample_rows", C.c_int32),
+        ("out_sample_rows", C.c_int32), ("tile_cfg", C.c_int32),
     ]
 
 
@@ -45,6 +48,7 @@ SIGNATURES = {
     "crog_resample": (C.c_int, [_P, _I, _I, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
     "crog_stem_conv1": (C.c_int, [_P, _I, _I, _I, _P, _P, _P, _I, _P, _I, _I, _P]),
     "crog_layernorm": (C.c_int, [_P, _I, _P, _P, _P, _P, _I, _L, _I, _F, _P]),
+    "crog_layernorm_chain": (C.c_int, [_P, _I, _P, _P, _P, _P, _P, _P, _P, _I, _L, _I, _F, _P]),
     "crog_embed_tokens": (C.c_int, [_P, _P, _P, _P, _I, _I, _I, _P]),
     "crog_gather_eot": (C.c_int, [_P, _P, _I, _P, _I, _I, _I, _I, _P]),
     "crog_attention": (C.c_int, [_P, _I, _P, _I, _P, _I, _P, _I, _I, _I, _I, _I, _F, _I, _P, _I, _P]),

@@ -203,6 +203,68 @@ __global__ void layernorm_kernel(const TI* __restrict__ x, const float* __restri
   }
 }
 
+// Two chained LayerNorms of the decoder (layers.py:318-329): y = residual + LN1(x) is the new fp32 residual stream, and
+// the next sub-layer immediately normalises it again (z = LN2(y)).  One warp per row keeps y in registers, so the second
+// normalisation costs no second pass over HBM; arithmetic and rounding are those of two layernorm_kernel launches.
+template <typename TI, typename TO, int CH>
+__global__ void layernorm_chain_kernel(const TI* __restrict__ x, const float* __restrict__ g1, const float* __restrict__ b1,
+                                       const float* residual, float* y, const float* __restrict__ g2,
+                                       const float* __restrict__ b2, TO* __restrict__ z, long long rows, float eps) {
+  constexpr int D = CH * 256;
+  pdl_launch();
+  pdl_wait();
+  const int lane = threadIdx.x & 31;
+  const long long row = blockIdx.x * (long long)(blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  float v[CH][8], r[CH][8];
+  float s = 0.f;
+#pragma unroll
+  for (int c = 0; c < CH; ++c) {
+    load8(x + row * D + (c * 32 + lane) * 8, v[c]);
+    load8(residual + row * D + (c * 32 + lane) * 8, r[c]);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s += v[c][j];
+  }
+  float mean = warp_sum(s) * (1.f / D);
+  float q = 0.f;
+#pragma unroll
+  for (int c = 0; c < CH; ++c)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { const float d = v[c][j] - mean; q += d * d; }
+  float rstd = rsqrtf(warp_sum(q) * (1.f / D) + eps);
+  s = 0.f;
+#pragma unroll
+  for (int c = 0; c < CH; ++c) {
+    const int col = (c * 32 + lane) * 8;
+    float g8[8], b8[8];
+    load8(g1 + col, g8); load8(b1 + col, b8);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float o = (v[c][j] - mean) * rstd * g8[j] + b8[j];
+      o += r[c][j];
+      v[c][j] = o;
+      s += o;
+    }
+    store8(y + row * D + col, v[c]);
+  }
+  mean = warp_sum(s) * (1.f / D);
+  q = 0.f;
+#pragma unroll
+  for (int c = 0; c < CH; ++c)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { const float d = v[c][j] - mean; q += d * d; }
+  rstd = rsqrtf(warp_sum(q) * (1.f / D) + eps);
+#pragma unroll
+  for (int c = 0; c < CH; ++c) {
+    const int col = (c * 32 + lane) * 8;
+    float g8[8], b8[8], o8[8];
+    load8(g2 + col, g8); load8(b2 + col, b8);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o8[j] = (v[c][j] - mean) * rstd * g8[j] + b8[j];
+    store8(z + row * D + col, o8);
+  }
+}
+
 // ------------------------------------------------------------------ text embedding / EOT gather
 __global__ void embed_kernel(const int64_t* __restrict__ word, const float* __restrict__ emb, const float* __restrict__ pos,
                              float* __restrict__ out, int B, int L, int D) {
@@ -450,6 +512,27 @@ extern "C" int crog_layernorm(const void* x, int32_t x_dtype, const float* gamma
 #undef LN_D
 #undef LN
   CROG_LAUNCH_OK("layernorm");
+  return CROG_OK;
+}
+
+extern "C" int crog_layernorm_chain(const void* x, int32_t x_dtype, const float* g1, const float* b1, const float* residual,
+                                    float* y, const float* g2, const float* b2, void* z, int32_t z_dtype, int64_t rows,
+                                    int32_t D, float eps, void* stream) {
+  CROG_REQUIRE(D == 512 || D == 256, CROG_E_BADSHAPE, "layernorm_chain: D=%d unsupported", D);
+  CROG_REQUIRE(x && g1 && b1 && residual && y && g2 && b2 && z, CROG_E_BADSHAPE, "layernorm_chain: null operand");
+  if (rows == 0) return CROG_OK;
+  const int wpb = 8;
+  const int g = (int)((rows + wpb - 1) / wpb);
+  cudaStream_t s = (cudaStream_t)stream;
+#define LNC(TI, TO, CH) crog_launch(layernorm_chain_kernel<TI, TO, CH>, dim3(g), dim3(wpb * 32), 0, s, (const TI*)x, g1, b1, residual, y, g2, b2, (TO*)z, (long long)rows, eps)
+#define LNC_D(TI, TO) do { if (D == 256) LNC(TI, TO, 1); else LNC(TI, TO, 2); } while (0)
+  if (x_dtype == CROG_F32 && z_dtype == CROG_F32) LNC_D(float, float);
+  else if (x_dtype == CROG_F32) LNC_D(float, bf16);
+  else if (z_dtype == CROG_F32) LNC_D(bf16, float);
+  else LNC_D(bf16, bf16);
+#undef LNC_D
+#undef LNC
+  CROG_LAUNCH_OK("layernorm_chain");
   return CROG_OK;
 }
 

@@ -531,12 +531,40 @@ int launch(const CrogGemm* g, cudaStream_t stream) {
 
 template <int MODE>
 int dispatch(const CrogGemm* g, cudaStream_t stream) {
-  if (g->N <= 64 && g->taps == 9 && g->cin == BK && g->w_sample_stride == 0 && !getenv("CROG_GEMM_NO_CONV3"))
-    return launch<64, 5, 2, MODE, true>(g, stream);
+  const long long Ktot = (long long)g->taps * g->cin;
+  const bool conv3_ok = g->N <= 64 && g->taps == 9 && g->cin == BK && g->w_sample_stride == 0;
+  const bool pair_ok = g->w_sample_stride == 0 && g->M > BM;  // shared weights, more than one CTA's worth of rows
+  if (g->tile_cfg != CROG_TILE_AUTO) {
+    // forced configuration (plan-time autotuner, tests): every one of them accumulates the k-blocks in the same order
+    switch (g->tile_cfg) {
+      case CROG_TILE_128x128: return launch<128, 4, 3, MODE>(g, stream);
+      case CROG_TILE_128x256:
+        CROG_REQUIRE(g->N > 128, CROG_E_BADSHAPE, "gemm_tc: 128x256 tiles need N > 128");
+        return launch<256, 4, 2, MODE, false, 4>(g, stream);
+      case CROG_TILE_128x256_E8:
+        CROG_REQUIRE(g->N > 128, CROG_E_BADSHAPE, "gemm_tc: 128x256 tiles need N > 128");
+        return launch<256, 3, 2, MODE>(g, stream);
+      case CROG_TILE_PAIR_256x256:
+        CROG_REQUIRE(pair_ok && g->N > 128, CROG_E_BADSHAPE, "gemm_tc: CTA-pair 256x256 tiles need shared weights, M > 128, N > 128");
+        return launch<256, 6, 2, MODE, false, 4, true>(g, stream);
+      case CROG_TILE_PAIR_256x256_E8:
+        CROG_REQUIRE(pair_ok && g->N > 128, CROG_E_BADSHAPE, "gemm_tc: CTA-pair 256x256 tiles need shared weights, M > 128, N > 128");
+        return launch<256, 4, 2, MODE, false, 8, true>(g, stream);
+      case CROG_TILE_PAIR_256x128:
+        CROG_REQUIRE(pair_ok && g->N > 64, CROG_E_BADSHAPE, "gemm_tc: CTA-pair 256x128 tiles need shared weights, M > 128, N > 64");
+        return launch<128, 6, 2, MODE, false, 8, true>(g, stream);
+      case CROG_TILE_128x64: return launch<64, 5, 3, MODE>(g, stream);
+      case CROG_TILE_CONV3:
+        CROG_REQUIRE(conv3_ok, CROG_E_BADSHAPE, "gemm_tc: CONV3 tiles need a shared 3x3 kernel with cin == 64 and N <= 64");
+        return launch<64, 5, 2, MODE, true>(g, stream);
+      default: CROG_REQUIRE(false, CROG_E_BADSHAPE, "gemm_tc: unknown tile_cfg %d", g->tile_cfg);
+    }
+  }
+  if (conv3_ok && !getenv("CROG_GEMM_NO_CONV3")) return launch<64, 5, 2, MODE, true>(g, stream);
   if (g->N <= 64) return launch<64, 5, 3, MODE>(g, stream);
   // 128 x 256 tiles cut the L2 -> smem operand traffic per FLOP by 25 % ((BM+BN)/(BM*BN)); worth it when the
   // contraction is long enough to be tensor/L2 bound rather than epilogue bound
-  if (g->N % 256 == 0 && (long long)g->taps * g->cin >= 1024) {
+  if (g->N % 256 == 0 && Ktot >= 1024) {
     // long contractions: the TMA feed is the pace (96 B/clk/SM at full tensor rate), so a fourth 48 KB stage in flight
     // is worth more than a second epilogue group (measured 3-12 % per layer; CROG_GEMM_3STAGE restores the old config)
     // CTA pairs (cta_group::2) whenever there is at least one 256-row tile per pair: +2-5 % on the long convolutions

@@ -12,6 +12,7 @@ through ``load_state_dict`` (random init otherwise).
 """
 from __future__ import annotations
 
+import os
 from typing import Dict, Optional, Tuple
 
 import torch
@@ -41,6 +42,7 @@ class CROG(nn.Module):
         self.precision = precision or getattr(cfg, "precision", "bf16")
         self.use_cuda_graph = use_cuda_graph
         self.gemm_impl = L.IMPL_AUTO
+        self.autotune = True  # time the tcgen05 tile configurations per layer when a plan is built (CROG_AUTOTUNE=0: off)
         gen = torch.Generator().manual_seed(0)
         for s in crog_tensor_specs(cfg):
             mod, leaf = _holder(self, s.name)
@@ -97,6 +99,8 @@ class CROG(nn.Module):
         if plan is None:
             with torch.cuda.device(dev):
                 plan = ForwardPlan(self.state_dict(), self.cfg, batch, self.precision, dev, size, self.gemm_impl, keep)
+                if self.autotune and os.environ.get("CROG_AUTOTUNE", "1") != "0":
+                    plan.autotune()
             self._plans[key] = plan
         return plan
 

@@ -133,6 +133,8 @@ class ForwardPlan:
         self._ev = None
         self.gemm_flops = 0
         self.gemm_alg_flops: Dict[str, int] = {}
+        self.gemm_ops: List[tuple] = []  # (name, descriptor, launch fn) of every GEMM, for the plan-time tile autotuner
+        self.tile_choice: Dict[str, tuple] = {}  # name -> (tile_cfg, us, heuristic us) once autotune() has run
         sd = {k: v.detach().to(self.dev) for k, v in sd.items()}
         self.sd = sd
         S = input_size
@@ -201,6 +203,7 @@ class ForwardPlan:
         lib = self.lib
         ref = C.byref(g)
         self._add(name, lambda s: L.check(lib.crog_gemm(ref, s)))
+        self.gemm_ops.append((name, g, self.ops[-1]))
         rows_eff = a.B * a.H * a.W if a.H > 0 else a.rows
         self.gemm_flops += 2 * rows_eff * N * taps * cin
         # algorithmic FLOPs of the reference op (no channel padding, no halo rows) for roofline accounting
@@ -223,6 +226,18 @@ class ForwardPlan:
         a = (x.ptr, L.dtype_code(x.t.dtype), g.data_ptr(), b.data_ptr(), residual.ptr if residual else None, out.ptr,
              L.dtype_code(out.t.dtype), x.rows, x.C, LN_EPS)
         self._add(name, lambda s: L.check(lib.crog_layernorm(*a, s)))
+        if self._keep_all:
+            self.keep[name] = out
+
+    def layernorm_chain(self, name: str, x: Act, p1: str, stream_: Act, p2: str, out: Act):
+        """stream_ += LN(x; p1); out = LN(stream_; p2) in one pass (csrc/elementwise.cu: layernorm_chain_kernel)."""
+        lib = self.lib
+        g1, b1 = self.f32(self.sd[p1 + ".weight"]), self.f32(self.sd[p1 + ".bias"])
+        g2, b2 = self.f32(self.sd[p2 + ".weight"]), self.f32(self.sd[p2 + ".bias"])
+        assert x.ld == x.C and out.ld == out.C and stream_.ld == stream_.C and stream_.t.dtype == torch.float32
+        a = (x.ptr, L.dtype_code(x.t.dtype), g1.data_ptr(), b1.data_ptr(), stream_.ptr, stream_.ptr, g2.data_ptr(), b2.data_ptr(),
+             out.ptr, L.dtype_code(out.t.dtype), x.rows, x.C, LN_EPS)
+        self._add(name, lambda s: L.check(lib.crog_layernorm_chain(*a, s)))
         if self._keep_all:
             self.keep[name] = out
 
@@ -482,17 +497,16 @@ class ForwardPlan:
             self.attention(p + ".self_attn", qkv.cols(0, D), qkv.cols(D, 2 * D), qkv.cols(2 * D, 3 * D), att, heads, T, T)
             self.gemm(p + ".self_attn.out_proj", att, self.wt(sd[p + ".self_attn.out_proj.weight"]), D, tmp,
                       bias=self.f32(sd[p + ".self_attn.out_proj.bias"]))
-            self.layernorm(p + ".self_attn_norm", tmp, p + ".self_attn_norm", vis, residual=vis)
+            # vis += LN(self-attention output); v2 = norm2(vis): chained in one pass (layers.py:318-322)
+            self.layernorm_chain(p + ".self_attn_norm+norm2", tmp, p + ".self_attn_norm", vis, p + ".norm2", v2)
             w_in, b_in = sd[p + ".multihead_attn.in_proj_weight"].float(), sd[p + ".multihead_attn.in_proj_bias"].float()
-            self.layernorm(p + ".norm2", vis, p + ".norm2", v2)
             self.gemm(p + ".cross.q", v2, self.wt(w_in[:D]), D, qc, addmat=self.f32(vp @ w_in[:D].t() + b_in[:D]))
             addkv = torch.cat([tp @ w_in[D:2 * D].t(), torch.zeros(Lt, D, device=self.dev)], 1) + b_in[D:]
             self.gemm(p + ".cross.kv", wordfeat, self.wt(w_in[D:]), 2 * D, kv, addmat=self.f32(addkv))
             self.attention(p + ".cross_attn", qc, kv.cols(0, D), kv.cols(D, 2 * D), att, heads, T, Lt, pad_word=self.word)
             self.gemm(p + ".cross.out_proj", att, self.wt(sd[p + ".multihead_attn.out_proj.weight"]), D, tmp,
                       bias=self.f32(sd[p + ".multihead_attn.out_proj.bias"]))
-            self.layernorm(p + ".cross_attn_norm", tmp, p + ".cross_attn_norm", vis, residual=vis)
-            self.layernorm(p + ".norm3", vis, p + ".norm3", v2)
+            self.layernorm_chain(p + ".cross_attn_norm+norm3", tmp, p + ".cross_attn_norm", vis, p + ".norm3", v2)
             self.gemm(p + ".ffn.0", v2, self.wt(sd[p + ".ffn.0.weight"]), cfg.dim_ffn, ff, bias=self.f32(sd[p + ".ffn.0.bias"]),
                       act=L.ACT_RELU)
             self.layernorm(p + ".ffn.3", ff, p + ".ffn.3", ff2)
@@ -543,6 +557,71 @@ class ForwardPlan:
         self.out = torch.zeros((NH, B, 1, H2, W2), device=self.dev, dtype=torch.float32)
         a2 = (z.ptr, z.ld, self.out.data_ptr(), B, H2, W2, NH)
         self._add("proj.gather", lambda s: L.check(lib.crog_dynconv_gather(*a2, s)))
+
+    # ------------------------------------------------------------------ plan-time tile autotuner
+    def autotune(self, reps: int = 4, min_gain: float = 0.03) -> Dict[str, tuple]:
+        """Pick the tcgen05 tile configuration of every GEMM of this plan by timing the applicable CROG_TILE_* ones on
+        the plan's own buffers (CUDA events on the current stream).  All configurations accumulate the k-blocks in the
+        same order and share the epilogue, so the choice changes speed only, never a bit of the result
+        (tests/test_gpu_kernels.py::test_tile_cfgs_bit_identical).  A forced configuration replaces the built-in
+        heuristic only when it is more than `min_gain` faster.  Launch-identical layers (same shape, layout and
+        epilogue) are timed once."""
+        if self.precision != "bf16" or self.impl == L.IMPL_SIMT:
+            return {}
+        lib = self.lib
+        s = L.stream_ptr()
+        # realistic operands: one forward on random inputs (zero buffers would flatter every configuration)
+        self._random_inputs()
+        self.run(stream=s)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+        def clock(fn) -> float:
+            fn(s)  # first launch of an instantiation sets its attributes; also warms the operands' L2 lines
+            best = float("inf")
+            for _ in range(2):
+                e0.record()
+                for _ in range(reps):
+                    fn(s)
+                e1.record()
+                e1.synchronize()
+                best = min(best, e0.elapsed_time(e1) * 1e3 / reps)
+            return best
+
+        memo: Dict[tuple, tuple] = {}
+        for name, g, fn in self.gemm_ops:
+            key = (g.M, g.N, g.cin, g.taps, g.a_ld, g.out_ld, g.res_ld, g.H, g.W, g.in_padded, g.out_padded, g.out_dtype,
+                   g.w_sample_stride, g.out_sample_rows, g.act, bool(g.residual), bool(g.addmat), bool(g.gate), bool(g.scale))
+            if key not in memo:
+                g.tile_cfg = L.TILE_AUTO
+                base = clock(fn)
+                best_cfg, best_us = L.TILE_AUTO, base
+                for cfg_id in range(1, L.TILE_COUNT):
+                    g.tile_cfg = cfg_id
+                    if lib.crog_gemm(C.byref(g), s) != 0:
+                        continue  # configuration does not apply to this shape
+                    us = clock(fn)
+                    if us < best_us:
+                        best_cfg, best_us = cfg_id, us
+                if best_us > base * (1.0 - min_gain):
+                    best_cfg, best_us = L.TILE_AUTO, base
+                memo[key] = (best_cfg, best_us, base)
+            g.tile_cfg = memo[key][0]
+            self.tile_choice[name] = memo[key]
+        torch.cuda.synchronize()
+        self._zero_inputs()
+        return self.tile_choice
+
+    def _random_inputs(self):
+        gen = torch.Generator(device="cpu").manual_seed(1234)
+        self.img.copy_(torch.randn(self.img.shape, generator=gen))
+        w = torch.zeros(self.word.shape, dtype=torch.int64)
+        w[:, 0], w[:, 1:5], w[:, 5] = 49406, 1000, 49407
+        self.word.copy_(w)
+
+    def _zero_inputs(self):
+        self.img.zero_()
+        self.word.zero_()
 
     # ------------------------------------------------------------------ execution
     def run(self, stream: Optional[int] = None, fork_text: bool = True):

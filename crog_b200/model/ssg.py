@@ -10,6 +10,8 @@ graph; there is no CPU path.  The training branch (losses, model/ssg.py:281-529)
 """
 from __future__ import annotations
 
+import os
+
 from typing import Dict, Optional, Tuple
 
 import torch
@@ -84,6 +86,8 @@ class SSG(nn.Module):
         if plan is None:
             with torch.cuda.device(dev):
                 plan = SSGPlan(self.state_dict(), self.cfg, batch, self.precision, dev, self.gemm_impl, keep)
+                if os.environ.get("CROG_AUTOTUNE", "1") != "0":
+                    plan.autotune()  # per-layer tcgen05 tile choice (bf16 plans only; results are unchanged)
             self._plans[key] = plan
         return plan
 

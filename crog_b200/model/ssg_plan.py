@@ -33,6 +33,7 @@ class SSGPlan(ForwardPlan):
         self.impl = gemm_impl
         self.ops, self.op_names, self.keep, self._keep_all, self._hold = [], [], {}, keep, []
         self.n_launches, self.gemm_flops, self.gemm_alg_flops = 0, 0, {}
+        self.gemm_ops, self.tile_choice = [], {}
         self._side = self._ev = None
         self.text_range = (0, 0)
         self.sd = {k: v.detach().to(self.dev) for k, v in sd.items()}
@@ -41,6 +42,15 @@ class SSGPlan(ForwardPlan):
         self.rgb = torch.zeros((batch, 3, S, S), device=self.dev, dtype=torch.float32)
         self.depth = torch.zeros((batch, 1, S, S), device=self.dev, dtype=torch.float32)
         self._build()
+
+    def _random_inputs(self):
+        gen = torch.Generator(device="cpu").manual_seed(1234)
+        self.rgb.copy_(torch.rand(self.rgb.shape, generator=gen))
+        self.depth.copy_(torch.rand(self.depth.shape, generator=gen))
+
+    def _zero_inputs(self):
+        self.rgb.zero_()
+        self.depth.zero_()
 
     def run(self, stream: Optional[int] = None, fork_text: bool = False):
         s = stream if stream is not None else L.stream_ptr()

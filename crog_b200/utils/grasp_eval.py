@@ -95,6 +95,52 @@ def jacquard_batched(grasps: torch.Tensor, n_peaks: Optional[torch.Tensor], gt: 
     return (flags, inter, uni) if want_counts else flags
 
 
+_side_streams = {}
+
+
+def decode_and_score_batched(q: torch.Tensor, sin: torch.Tensor, cos: torch.Tensor, wid: torch.Tensor, gt: torch.Tensor,
+                             gt_count: torch.Tensor, num_grasps: int = 5, counters: Optional[torch.Tensor] = None,
+                             chunks: int = 4, threshold: float = 0.4, edit_gt: bool = True):
+    """detect_grasps (grasp_eval.py:289-302) followed by calculate_jacquard_index (:362-374) over a batch, issued as
+    `chunks` sub-batches on two streams: the HBM-bound peak scan of sub-batch i+1 runs while the integer rasterisation
+    of sub-batch i (ALU / latency bound, ~3 KB per sample) occupies the otherwise idle issue slots.  Same kernels, same
+    bytes, same results as detect_grasps_batched + jacquard_batched; returns (peaks, n_peaks, grasps, j_flags)."""
+    lib = L.lib()
+    assert q.is_cuda and q.dtype == torch.float32 and q.dim() == 3
+    assert gt.is_cuda and gt.dtype == torch.float64 and gt.is_contiguous() and gt_count.dtype == torch.int32
+    q, sin, cos, wid = [t.contiguous() for t in (q, sin, cos, wid)]
+    B, H, W = q.shape
+    K, M = int(num_grasps), gt.shape[1]
+    dev = q.device
+    peaks = torch.empty((B, K, 2), dtype=torch.int32, device=dev)
+    n = torch.empty((B,), dtype=torch.int32, device=dev)
+    grasps = torch.empty((B, K, 5), dtype=torch.float64, device=dev)
+    flags = torch.empty((B, 2), dtype=torch.int32, device=dev)
+    chunks = max(1, min(int(chunks), B))
+    per = (B + chunks - 1) // chunks
+    cptr = counters.data_ptr() if counters is not None else None
+    with torch.cuda.device(dev):
+        main = torch.cuda.current_stream()
+        side = _side_streams.get(dev.index)
+        if side is None:
+            side = _side_streams[dev.index] = torch.cuda.Stream(device=dev, priority=-1)
+        ws = _workspace(per, H, W, K, dev)  # the detect kernels of successive sub-batches are ordered on `main`
+        for b0 in range(0, B, per):
+            nb = min(per, B - b0)
+            L.check(lib.crog_detect_grasps(q[b0:].data_ptr(), sin[b0:].data_ptr(), cos[b0:].data_ptr(), wid[b0:].data_ptr(), nb, H, W,
+                                           K, float(threshold), peaks[b0:].data_ptr(), n[b0:].data_ptr(), grasps[b0:].data_ptr(),
+                                           ws.data_ptr(), main.cuda_stream))
+            ev = torch.cuda.Event()
+            ev.record(main)
+            side.wait_event(ev)
+            L.check(lib.crog_jaccard(grasps[b0:].data_ptr(), n[b0:].data_ptr(), K, gt[b0:].data_ptr(), gt_count[b0:].data_ptr(), M, nb,
+                                     None, None, flags[b0:].data_ptr(), cptr, int(edit_gt), side.cuda_stream))
+        done = torch.cuda.Event()
+        done.record(side)
+        main.wait_event(done)
+    return peaks, n, grasps, flags
+
+
 # ----------------------------------------------------------------------- reference-signature wrappers
 def detect_grasps(grasp_quality_mask, grasp_sin_mask, grasp_cos_mask, grasp_wid_mask, num_grasps=5):
     """utils/grasp_eval.py:289-302: returns (list of [x, y, w, 20, angle_deg], angle map)."""

@@ -90,7 +90,23 @@ typedef struct CrogGemm {
   int32_t out_sample_rows;/* compact output: rows per sample in the OUTPUT matrix (0: H*W). Lets several feature
                              levels of one sample land back to back in one [B, sum_l H_l*W_l, N] tensor (torch.cat of
                              model/ssg.py:266-269): pass `out` already offset to the level's first row. */
+  int32_t tile_cfg;       /* tcgen05 tile configuration: 0 = built-in heuristic, CROG_TILE_* = forced (the plan-time
+                             autotuner times the applicable ones per layer; every configuration accumulates the k-blocks
+                             in the same order, so results are bit-identical across them).  A configuration that does
+                             not apply to the shape returns CROG_E_BADSHAPE. */
 } CrogGemm;
+enum {
+  CROG_TILE_AUTO = 0,
+  CROG_TILE_128x128 = 1,        /* one CTA, 128 x 128 tiles, 4 operand stages, two epilogue groups */
+  CROG_TILE_128x256 = 2,        /* one CTA, 128 x 256 tiles, 4 stages, one epilogue group */
+  CROG_TILE_128x256_E8 = 3,     /* one CTA, 128 x 256 tiles, 3 stages, two epilogue groups */
+  CROG_TILE_PAIR_256x256 = 4,   /* CTA pair (cta_group::2), 256 x 256 tiles, 6 stages, one epilogue group per CTA */
+  CROG_TILE_PAIR_256x256_E8 = 5,/* CTA pair, 256 x 256 tiles, 4 stages, two epilogue groups per CTA */
+  CROG_TILE_PAIR_256x128 = 6,   /* CTA pair, 256 x 128 tiles, 6 stages, two epilogue groups per CTA */
+  CROG_TILE_128x64 = 7,         /* one CTA, 128 x 64 tiles, 5 stages */
+  CROG_TILE_CONV3 = 8,          /* 128 x 64 tiles, resident 3x3 weights, one TMA box per ky band (N <= 64, cin == 64) */
+  CROG_TILE_COUNT = 9
+};
 int crog_gemm(const CrogGemm* g, void* stream);
 
 /* ------------------------------------------------------------------ layout / resampling
@@ -114,6 +130,12 @@ int crog_stem_conv1(const float* img, int32_t B, int32_t Hin, int32_t Win, const
  * out = residual + y (fp32 residual stream).  x_dtype/out_dtype are CROG_F32|CROG_BF16. */
 int crog_layernorm(const void* x, int32_t x_dtype, const float* gamma, const float* beta, const float* residual,
                    void* out, int32_t out_dtype, int64_t rows, int32_t D, float eps, void* stream);
+
+/* Two chained LayerNorms of a decoder layer (layers.py:318-329): y = residual + LN(x; g1, b1) (the fp32 residual
+ * stream; y may alias residual), z = LN(y; g2, b2).  Same arithmetic as two crog_layernorm calls, one pass over HBM. */
+int crog_layernorm_chain(const void* x, int32_t x_dtype, const float* g1, const float* b1, const float* residual,
+                         float* y, const float* g2, const float* b2, void* z, int32_t z_dtype, int64_t rows,
+                         int32_t D, float eps, void* stream);
 
 /* Token embedding + positional embedding (clip.py:440-443): out[b*L+l] = emb[word[b,l]] + pos[l], fp32. */
 int crog_embed_tokens(const int64_t* word, const float* emb, const float* pos, float* out, int32_t B,

@@ -442,3 +442,137 @@ def test_gemm_cta_pair_matches_single_cta(case, monkeypatch):
     monkeypatch.delenv("CROG_GEMM_PAIR")       # default dispatch: CTA pairs for these shapes
     got = run()
     assert torch.equal(got, want), f"max diff {maxerr(got, want)}"
+
+
+@pytest.mark.parametrize("case", ["conv3x3_pad2pad", "conv3x3_pad2compact", "conv3x3_cin64_n64", "linear_k512_addmat_bf16",
+                                  "linear_k64_residual_relu", "linear_n128_f32_residual", "linear_ragged_n"])
+def test_tile_cfgs_bit_identical(case):
+    """Every CROG_TILE_* configuration the plan-time autotuner may pick (single CTA 128x64/128x128/128x256, CTA pairs
+    256x256 / 256x128 with one or two epilogue groups, CONV3) accumulates the k-blocks in the same order through the same
+    epilogue, so a forced configuration must reproduce the heuristic's bytes exactly; inapplicable ones must refuse."""
+    torch.manual_seed(11)
+    dt = torch.bfloat16
+    if case.startswith("conv3x3"):
+        if case == "conv3x3_cin64_n64":
+            B, H, W, Cin, Cout = 3, 37, 41, 64, 64
+        else:
+            B, H, W, Cin, Cout = 4, 30, 33, 128, 256  # M = 4*32*35 = 4480 padded rows: ragged last pair tile
+        x = torch.randn(B, Cin, H, W, device="cuda")
+        w = torch.randn(Cout, Cin, 3, 3, device="cuda") * (Cin * 9) ** -0.5
+        sc, bi = torch.rand(Cout, device="cuda") + 0.5, torch.randn(Cout, device="cuda")
+        a, wk = pad_nhwc(x, dt), conv_w(w, dt)
+        out_padded = case != "conv3x3_pad2compact"
+
+        def run(cfg):
+            rows = B * (H + 2) * (W + 2) if out_padded else B * H * W
+            out = torch.zeros((rows, Cout), device="cuda", dtype=dt)
+            run_gemm(a, wk, Cout, out, taps=9, H=H, W=W, in_padded=True, out_padded=out_padded,
+                     sample_rows=(H + 2) * (W + 2), scale=sc, bias=bi, act=L.ACT_RELU, impl=L.IMPL_TCGEN05, tile_cfg=cfg)
+            return out
+    else:
+        M, N, K, odt = {"linear_k512_addmat_bf16": (676 * 5 + 3, 1536, 512, dt), "linear_k64_residual_relu": (5000, 256, 64, dt),
+                        "linear_n128_f32_residual": (2704 + 129, 128, 512, torch.float32),
+                        "linear_ragged_n": (1000, 328, 256, dt)}[case]
+        a = (torch.randn(M, K, device="cuda") * 0.5).to(dt)
+        w = (torch.randn(N, K, device="cuda") * K ** -0.5).to(dt)
+        bi = torch.randn(N, device="cuda")
+        res = torch.randn(M, N, device="cuda").to(odt)
+        addmat = torch.randn(97, N, device="cuda") if "addmat" in case else None
+
+        def run(cfg):
+            out = res.clone()
+            run_gemm(a, w, N, out, bias=bi, residual=None if addmat is not None else out, residual_relu="relu" in case,
+                     addmat=addmat, sample_rows=97 if addmat is not None else 0, impl=L.IMPL_TCGEN05, tile_cfg=cfg)
+            return out
+    want = run(L.TILE_AUTO)
+    ran = []
+    for cfg in range(1, L.TILE_COUNT):
+        try:
+            got = run(cfg)
+        except L.CrogError:
+            continue  # does not apply to this shape
+        ran.append(cfg)
+        assert torch.equal(got, want), f"tile_cfg {cfg}: max diff {maxerr(got, want)}"
+    assert L.TILE_128x128 in ran and L.TILE_128x64 in ran
+    if case != "conv3x3_cin64_n64":
+        assert L.TILE_PAIR_256x128 in ran
+    else:
+        assert L.TILE_CONV3 in ran
+
+
+def test_plan_autotune_keeps_results():
+    """The plan-time autotuner changes tile configurations only: maps before and after are bit-identical."""
+    from crog_b200 import synth
+    from crog_b200.model import CROG
+
+    cfg = synth.default_cfg(17)
+    model = CROG(cfg, precision="bf16", use_cuda_graph=False)
+    model.load_state_dict(synth.make_state_dict(cfg, 0, "perturbed"))
+    model = model.cuda()
+    model.autotune = False
+    img, word = synth.make_inputs(2, 17)
+    want = torch.stack(model(img.cuda(), word.cuda())[0])
+    plan = model.plan_for(2, 416)
+    choice = plan.autotune(reps=2, min_gain=0.0)
+    assert len(choice) == len(plan.gemm_ops)
+    got = torch.stack(model(img.cuda(), word.cuda())[0])
+    assert torch.equal(got, want)
+
+
+@pytest.mark.parametrize("chunks", [1, 3, 4])
+def test_decode_and_score_pipelined_equals_serial(chunks):
+    """The two-stream, sub-batched tail issues the same kernels on slices: identical peaks, grasps, flags and counters."""
+    from crog_b200 import synth
+    from crog_b200.utils import grasp_eval as GE
+
+    n = 10
+    q, s, c, w = [torch.from_numpy(a).cuda() for a in synth.make_tail_maps(n, "blobs", 7, 160)]
+    gt, cnt = synth.make_gt_rects(n, 64, seed=4)
+    g1, g2 = torch.from_numpy(gt.copy()).cuda(), torch.from_numpy(gt.copy()).cuda()
+    dcnt = torch.from_numpy(cnt).cuda()
+    c1, c2 = torch.zeros(4, dtype=torch.int64, device="cuda"), torch.zeros(4, dtype=torch.int64, device="cuda")
+    pk, npk, gr = GE.detect_grasps_batched(q, s, c, w, 5)
+    fl = GE.jacquard_batched(gr, npk, g1, dcnt, counters=c1)
+    pk2, npk2, gr2, fl2 = GE.decode_and_score_batched(q, s, c, w, g2, dcnt, 5, counters=c2, chunks=chunks)
+    torch.cuda.synchronize()
+    assert torch.equal(npk, npk2) and torch.equal(fl, fl2) and torch.equal(c1, c2) and torch.equal(g1, g2)
+    for b in range(n):
+        k = int(npk[b])
+        assert torch.equal(pk[b, :k], pk2[b, :k]) and torch.equal(gr[b, :k], gr2[b, :k])
+
+
+def test_attention_lazy_rescale_and_chained_layernorm():
+    """(1) Logits that grow by far more than 2^8 from one key tile to the next force the in-TMEM rescale of the output
+    row (csrc/attention_tc.cu) on every tile; logits that shrink leave the stale reference maximum in place.
+    (2) crog_layernorm_chain equals two crog_layernorm calls."""
+    B, heads, T = 2, 2, 500
+    D = heads * 64
+    for grow in (True, False):
+        qkv = _rand(B * T, 3 * D, seed=31, scale=2.0)
+        f = 1.0 + 4.0 * (torch.arange(T, device=DEV) // 128).float()
+        if not grow:
+            f = f.flip(0)
+        qkv[:, D:2 * D] *= f.repeat(B)[:, None]
+        qkv = qkv.to(BF)
+        o = torch.zeros(B * T, D, device=DEV, dtype=BF)
+        es = qkv.element_size()
+        L.check(L.lib().crog_attention(qkv.data_ptr(), 3 * D, qkv.data_ptr() + D * es, 3 * D, qkv.data_ptr() + 2 * D * es, 3 * D,
+                                       o.data_ptr(), D, B, heads, T, T, 0.125, 0, None, L.BF16, L.stream_ptr()))
+        torch.cuda.synchronize()
+        want = _ref_attention(qkv[:, :D].float().view(B, T, D), qkv[:, D:2 * D].float().reshape(B, T, D),
+                              qkv[:, 2 * D:].float().reshape(B, T, D), heads, False, None)
+        assert torch.isfinite(o.float()).all()
+        assert relerr(o.view(B, T, D), want) < 8e-3, grow
+    rows, Dm = 1000, 512
+    x = _rand(rows, Dm, seed=32).to(BF)
+    res = _rand(rows, Dm, seed=33)
+    g1, b1, g2, b2 = [_rand(Dm, seed=34 + i) for i in range(4)]
+    y_ref, z_ref = res.clone(), torch.zeros(rows, Dm, device=DEV, dtype=BF)
+    lib = L.lib()
+    L.check(lib.crog_layernorm(x.data_ptr(), L.BF16, g1.data_ptr(), b1.data_ptr(), y_ref.data_ptr(), y_ref.data_ptr(), L.F32, rows, Dm, 1e-5, L.stream_ptr()))
+    L.check(lib.crog_layernorm(y_ref.data_ptr(), L.F32, g2.data_ptr(), b2.data_ptr(), None, z_ref.data_ptr(), L.BF16, rows, Dm, 1e-5, L.stream_ptr()))
+    y, z = res.clone(), torch.zeros(rows, Dm, device=DEV, dtype=BF)
+    L.check(lib.crog_layernorm_chain(x.data_ptr(), L.BF16, g1.data_ptr(), b1.data_ptr(), y.data_ptr(), y.data_ptr(), g2.data_ptr(), b2.data_ptr(),
+                                     z.data_ptr(), L.BF16, rows, Dm, 1e-5, L.stream_ptr()))
+    torch.cuda.synchronize()
+    assert maxerr(y, y_ref) <= 1e-6 * float(y_ref.abs().max()) and maxerr(z, z_ref) <= 2e-2
