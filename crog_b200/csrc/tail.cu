@@ -474,6 +474,9 @@ __global__ void angle_map_kernel(const float* __restrict__ s, const float* __res
 
 // ------------------------------------------------------------------ Jaccard
 constexpr int JT = 128;  // threads per sample CTA
+#ifndef JACCARD_CTAS_PER_SM
+#define JACCARD_CTAS_PER_SM 8  // latency / barrier bound kernel: more resident samples per SM (64 registers, 24.5 KB smem each)
+#endif
 
 __device__ __forceinline__ int block_sum(int v, int* s_red) {
 #pragma unroll
@@ -504,7 +507,7 @@ __device__ int slow_count(const TgRect* A, const TgRect* Bq, int* s_red) {
 // One CTA per sample.  Predicted rectangles are rasterised once into shared-memory row masks; then every warp takes
 // ground-truth rectangles round-robin (no CTA-wide barrier inside the loop): lane = scanline, row mask by exact integer
 // scanline arithmetic, popc(A & B) against the predictions that pass the angle gate, warp-shuffle reductions.
-__global__ void __launch_bounds__(JT, 6) jaccard_kernel(const double* __restrict__ grasps, const int* __restrict__ n_peaks, int K,
+__global__ void __launch_bounds__(JT, JACCARD_CTAS_PER_SM) jaccard_kernel(const double* __restrict__ grasps, const int* __restrict__ n_peaks, int K,
                                                      double* __restrict__ gt, const int* __restrict__ gt_count, int Mmax,
                                                      int* __restrict__ inter_out, int* __restrict__ uni_out,
                                                      int* __restrict__ j_flags, long long* __restrict__ counters, int edit_gt) {
@@ -771,7 +774,11 @@ extern "C" int crog_jaccard(const double* grasps, const int32_t* n_peaks, int32_
   if (B == 0) return CROG_OK;
   const size_t smem = (size_t)K * TG_MAXROWS * TG_WORDS * 4;
   static bool attr = false;
-  if (!attr) { CROG_CUDA_OK(cudaFuncSetAttribute(jaccard_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MAXK * TG_MAXROWS * TG_WORDS * 4)); attr = true; }
+  if (!attr) {
+    CROG_CUDA_OK(cudaFuncSetAttribute(jaccard_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MAXK * TG_MAXROWS * TG_WORDS * 4));
+    CROG_CUDA_OK(cudaFuncSetAttribute(jaccard_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    attr = true;
+  }
   jaccard_kernel<<<B, JT, smem, (cudaStream_t)stream>>>(grasps, n_peaks, K, gt, gt_count, Mmax, inter, uni, j_flags,
                                                         (long long*)counters, edit_gt);
   CROG_LAUNCH_OK("jaccard");
