@@ -77,6 +77,18 @@ class CROG(nn.Module):
             state_dict = {k[len("module."):]: v for k, v in state_dict.items()}
         return super().load_state_dict(state_dict, strict=strict, **kw)
 
+    def load_clip(self, clip, strict_shapes: bool = True):
+        """Initialise the backbone from a CLIP RN50 archive path (TorchScript ``RN50.pt``) or CLIP state-dict, with the
+        fp16 round trip of the reference's ``build_model(..., load_weights=True).float()`` (model/crog.py:20-23;
+        crog_b200/model/clip_ingest.py).  Returns (missing backbone names, unexpected archive names)."""
+        from .clip_ingest import clip_state_to_backbone, load_clip_archive
+
+        sd = load_clip_archive(clip) if isinstance(clip, (str, bytes)) or hasattr(clip, "__fspath__") else clip
+        new, missing, unexpected = clip_state_to_backbone(sd, self.cfg)
+        super().load_state_dict(new, strict=False)
+        self.invalidate()
+        return missing, unexpected
+
     def _apply(self, fn, *a, **kw):
         self.invalidate()
         return super()._apply(fn, *a, **kw)
