@@ -125,6 +125,7 @@ class ForwardPlan:
         self.impl = gemm_impl
         self.ops: List[Callable[[int], None]] = []
         self.op_names: List[str] = []
+        self.op_launches: List[int] = []  # kernel launches per recorded op (profiles/launch_list.py joins ncu rows on it)
         self.keep: Dict[str, Act] = {}
         self._keep_all = keep
         self._hold: List[object] = []  # keeps packed weights / descriptors alive
@@ -169,6 +170,7 @@ class ForwardPlan:
     def _add(self, name: str, fn: Callable[[int], None], launches: int = 1):
         self.ops.append(fn)
         self.op_names.append(name)
+        self.op_launches.append(launches)
         self.n_launches += launches
 
     # ------------------------------------------------------------------ op recorders

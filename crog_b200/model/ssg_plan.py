@@ -32,6 +32,7 @@ class SSGPlan(ForwardPlan):
         self.acode = L.dtype_code(self.adt)
         self.impl = gemm_impl
         self.ops, self.op_names, self.keep, self._keep_all, self._hold = [], [], {}, keep, []
+        self.op_launches = []
         self.n_launches, self.gemm_flops, self.gemm_alg_flops = 0, 0, {}
         self.gemm_ops, self.tile_choice = [], {}
         self._side = self._ev = None

@@ -1,5 +1,5 @@
 """Profiling helper (not a test): one eager forward of the bench workload, launches in plan order.
-usage: CROG_NO_FORK=1 ncu ... python tests/prof_forward.py [B]"""
+usage: CROG_NO_FORK=1 ncu ... python tests/prof_forward.py [B] [op-names-out.tsv]"""
 import os
 import sys
 
@@ -24,3 +24,9 @@ plan.run()
 torch.cuda.synchronize()
 torch.cuda.profiler.stop()
 print("ok", plan.n_launches)
+if len(sys.argv) > 2:  # op names, one line per kernel launch in plan order (profiles/launch_list.py joins them with the ncu rows)
+    with open(sys.argv[2], "w") as f:
+        for name, n in zip(plan.op_names, plan.op_launches):
+            tc = plan.tile_choice.get(name)
+            for _ in range(n):
+                f.write(f"{name}\t{tc[0] if tc else ''}\n")
