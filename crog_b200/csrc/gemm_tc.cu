@@ -61,7 +61,13 @@ struct Cfg {
   static constexpr int STG_OFF = BRES_OFF + BRES_BYTES;
   static constexpr int BAR_OFF = STG_OFF + EPI_WARPS * STG_WARP;
   static constexpr int NBARS = 2 * STAGES + 5 + EPI_WARPS * NBUF;  // full[S], empty[S], tfull[2], tempty[2], bres, res[8][NBUF]
-  static constexpr int TOTAL = BAR_OFF + NBARS * 8 + 16 + 1024;   // + tmem slot + alignment slack
+  // per epilogue group: this tile's scale / bias slice, double buffered by tile parity ([2][scale | bias][BN] floats);
+  // configurations whose operand ring leaves no room for it (long contractions, where the epilogue hides under the
+  // mainloop anyway) keep reading scale / bias through the read-only cache
+  static constexpr int SB_BYTES = (EPI_WARPS / 4) * 2 * 2 * BN * 4;
+  static constexpr int SB_OFF = ((BAR_OFF + NBARS * 8 + 16 + 15) / 16) * 16;
+  static constexpr bool SB = SB_OFF + SB_BYTES + 1024 <= 227 * 1024;
+  static constexpr int TOTAL = SB ? SB_OFF + SB_BYTES + 1024 : BAR_OFF + NBARS * 8 + 16 + 1024;   // + tmem slot + alignment slack
   static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
   static_assert(NBUF >= 2 && STG_WARP >= 32 * PITCH, "staging too small");
 };
@@ -217,6 +223,32 @@ __global__ void __launch_bounds__(64 + EPI_WARPS * 32, 1) gemm_tc_kernel(const _
     const int grp = ew >> 2;                 // this warp's group drains tiles grp, grp + GROUPS, ... (buffer = tile parity)
     const int q = warp & 3;                  // TMEM lane quarter this warp may read
     uint8_t* stg = smem + L::STG_OFF + ew * L::STG_WARP;
+    // scale / bias of the current tile in shared memory (see Cfg::SB): the group's 128 threads fetch the slice before
+    // they wait for the accumulator, store it, and meet on the group's named barrier (id 1 + grp)
+    float* sb_base = reinterpret_cast<float*>(smem + L::SB_OFF) + grp * (2 * 2 * BN);
+    const int gt = (ew & 3) * 32 + lane;     // thread index inside the group
+    auto stage_scale_bias = [&](int ord, int n0, uint32_t tfull_bar, uint32_t tfull_parity) -> const float* {
+      float* sbt = sb_base + (ord & 1) * (2 * BN);
+      if constexpr (L::SB) {
+        float v[(2 * BN + 127) / 128];
+#pragma unroll
+        for (int u = 0; u < (2 * BN + 127) / 128; ++u) {
+          const int idx = gt + u * 128, isb = idx >= BN, n = n0 + (isb ? idx - BN : idx);
+          v[u] = isb ? 0.f : 1.f;
+          const float* src = isb ? g.bias : g.scale;
+          if (idx < 2 * BN && n < g.N && src) v[u] = __ldg(src + n);
+        }
+        mbar_wait(tfull_bar, tfull_parity);
+#pragma unroll
+        for (int u = 0; u < (2 * BN + 127) / 128; ++u)
+          if (gt + u * 128 < 2 * BN) sbt[gt + u * 128] = v[u];
+        if (grp == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
+        else asm volatile("bar.sync 2, 128;" ::: "memory");
+      } else {
+        mbar_wait(tfull_bar, tfull_parity);
+      }
+      return sbt;
+    };
 
     if constexpr (MODE != MODE_LEGACY) {
       // ------------------------------------------------------------ TMA epilogue (identity row mapping)
@@ -227,18 +259,25 @@ __global__ void __launch_bounds__(64 + EPI_WARPS * 32, 1) gemm_tc_kernel(const _
       const uint32_t stg_u32 = smem_u32(stg), rbar0 = res0 + 8 * (ew * NBUF);
       const int sw = lane & 7;
       uint32_t nld = 0, ncs = 0;   // residual chunks requested / chunks consumed (warp-uniform)
-      int pf_i = grp, pf_c = 0;    // prefetch cursor: tile ordinal, chunk in tile
-      auto issue_prefetch = [&]() {
+      // prefetch cursor: tile ordinal, chunk in tile, and the tile's coordinates (recomputed once per tile: the two
+      // integer divisions per chunk cost ~500 clocks of every 3800-clock chunk in the in-kernel trace)
+      int pf_i = grp, pf_c = 0, pf_n0 = 0, pf_row = 0;
+      bool pf_ok = false;
+      auto pf_set_tile = [&]() {
         const int tile = tile0 + pf_i * tstep;
-        if (tile >= total_tiles) return;
-        const int n0 = (tile % n_tiles) * BN, row = (tile / n_tiles) * MT + (int)rank * BM + q * 32;
+        pf_ok = tile < total_tiles;
+        if (pf_ok) { pf_n0 = (tile % n_tiles) * BN; pf_row = (tile / n_tiles) * MT + (int)rank * BM + q * 32; }
+      };
+      pf_set_tile();
+      auto issue_prefetch = [&]() {
+        if (!pf_ok) return;
         if (lane == 0) {
           const uint32_t b = nld % NBUF;
           mbar_expect_tx(rbar0 + 8 * b, STG_BUF);
-          tma_load_2d(stg_u32 + b * STG_BUF, &tmRes, n0 + pf_c * CW, row, rbar0 + 8 * b);
+          tma_load_2d(stg_u32 + b * STG_BUF, &tmRes, pf_n0 + pf_c * CW, pf_row, rbar0 + 8 * b);
         }
         ++nld;
-        if (++pf_c == NCH || n0 + pf_c * CW >= g.N) { pf_c = 0; pf_i += GROUPS; }
+        if (++pf_c == NCH || pf_n0 + pf_c * CW >= g.N) { pf_c = 0; pf_i += GROUPS; pf_set_tile(); }
       };
       if (has_res)
         for (int j = 0; j < NBUF - 1; ++j) issue_prefetch();
@@ -250,7 +289,7 @@ __global__ void __launch_bounds__(64 + EPI_WARPS * 32, 1) gemm_tc_kernel(const _
         const int n0 = (tile % n_tiles) * BN, row0 = (tile / n_tiles) * MT + (int)rank * BM;
         const RowMap m = map_row(g, (long long)row0 + q * 32 + lane, g.M);
         const int nvc = min(NCH, (g.N - n0 + CW - 1) / CW);  // chunks with at least one real column
-        mbar_wait(tfull, (i >> 1) & 1);
+        const float* sbt = stage_scale_bias(i / GROUPS, n0, tfull, (i >> 1) & 1);
         tc_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN;
         for (int c = 0; c < nvc; ++c) {
@@ -274,8 +313,11 @@ __global__ void __launch_bounds__(64 + EPI_WARPS * 32, 1) gemm_tc_kernel(const _
             for (int h = 0; h < CW / 32; ++h) {
               if (ncol + h * 32 < g.N) {
                 float(&a32)[32] = *reinterpret_cast<float(*)[32]>(&acc[h * 32]);
-                epilogue_math<32>(g, m, ncol + h * 32, a32, g.scale ? g.scale + ncol + h * 32 : nullptr,
-                                  g.bias ? g.bias + ncol + h * 32 : nullptr);
+                if constexpr (L::SB)
+                  epilogue_math_smem<32>(g, m, ncol + h * 32, a32, sbt + c * CW + h * 32, sbt + BN + c * CW + h * 32);
+                else
+                  epilogue_math<32>(g, m, ncol + h * 32, a32, g.scale ? g.scale + ncol + h * 32 : nullptr,
+                                    g.bias ? g.bias + ncol + h * 32 : nullptr);
               }
             }
           }
@@ -366,7 +408,7 @@ __global__ void __launch_bounds__(64 + EPI_WARPS * 32, 1) gemm_tc_kernel(const _
 #pragma unroll
         for (int p = 0; p < PASSES; ++p) orow[p] = __shfl_sync(0xffffffffu, my_orow, p * RPP + rsub);
         const int nvs = min(NSUB, (g.N - n0 + SUB - 1) / SUB);
-        mbar_wait(tfull, (i >> 1) & 1);
+        const float* sbt = stage_scale_bias(i / GROUPS, n0, tfull, (i >> 1) & 1);
         tc_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN;
         for (int sbi = 0; sbi < nvs; ++sbi) {
@@ -391,8 +433,10 @@ __global__ void __launch_bounds__(64 + EPI_WARPS * 32, 1) gemm_tc_kernel(const _
             if constexpr (PAIR) mbar_arrive_cluster(mapa_shared(tempty, 0));
             else mbar_arrive(tempty);
           }
-          if (m.valid)
-            epilogue_math<SUB>(g, m, n0 + cbase, acc, g.scale ? g.scale + n0 + cbase : nullptr, g.bias ? g.bias + n0 + cbase : nullptr);
+          if (m.valid) {
+            if constexpr (L::SB && SUB % 4 == 0) epilogue_math_smem<SUB>(g, m, n0 + cbase, acc, sbt + cbase, sbt + BN + cbase);
+            else epilogue_math<SUB>(g, m, n0 + cbase, acc, g.scale ? g.scale + n0 + cbase : nullptr, g.bias ? g.bias + n0 + cbase : nullptr);
+          }
           float4* dst = reinterpret_cast<float4*>(stg + lane * L::PITCH);
 #pragma unroll
           for (int j = 0; j < SUB / 4; ++j) dst[j] = make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
@@ -554,6 +598,7 @@ int dispatch(const CrogGemm* g, cudaStream_t stream) {
         CROG_REQUIRE(pair_ok && g->N > 64, CROG_E_BADSHAPE, "gemm_tc: CTA-pair 256x128 tiles need shared weights, M > 128, N > 64");
         return launch<128, 6, 2, MODE, false, 8, true>(g, stream);
       case CROG_TILE_128x64: return launch<64, 5, 3, MODE>(g, stream);
+      case CROG_TILE_128x128_S3: return launch<128, 3, 3, MODE>(g, stream);
       case CROG_TILE_CONV3:
         CROG_REQUIRE(conv3_ok, CROG_E_BADSHAPE, "gemm_tc: CONV3 tiles need a shared 3x3 kernel with cin == 64 and N <= 64");
         return launch<64, 5, 2, MODE, true>(g, stream);
@@ -574,6 +619,8 @@ int dispatch(const CrogGemm* g, cudaStream_t stream) {
     if (!getenv("CROG_GEMM_3STAGE")) return launch<256, 4, 2, MODE, false, 4>(g, stream);
     return launch<256, 3, 2, MODE>(g, stream);
   }
+  // short contractions are epilogue bound: three operand stages leave room for the shared-memory scale / bias slice
+  if (Ktot < 1024) return launch<128, 3, 3, MODE>(g, stream);
   return launch<128, 4, 3, MODE>(g, stream);
 }
 

@@ -105,7 +105,10 @@ enum {
   CROG_TILE_PAIR_256x128 = 6,   /* CTA pair, 256 x 128 tiles, 6 stages, two epilogue groups per CTA */
   CROG_TILE_128x64 = 7,         /* one CTA, 128 x 64 tiles, 5 stages */
   CROG_TILE_CONV3 = 8,          /* 128 x 64 tiles, resident 3x3 weights, one TMA box per ky band (N <= 64, cin == 64) */
-  CROG_TILE_COUNT = 9
+  CROG_TILE_128x128_S3 = 9,     /* one CTA, 128 x 128 tiles, 3 operand stages, two epilogue groups, scale / bias of the tile
+                                   staged in shared memory (the 4-stage ring of CROG_TILE_128x128 leaves no room for it):
+                                   the default for short contractions, where the epilogue is the pace */
+  CROG_TILE_COUNT = 10
 };
 int crog_gemm(const CrogGemm* g, void* stream);
 
