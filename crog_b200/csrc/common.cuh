@@ -193,6 +193,25 @@ __device__ __forceinline__ void epilogue_math(const CrogGemm& g, const RowMap& m
   }
 }
 
+// Packed fp32 pairs (sm_100 FFMA2 / FADD2): two independent round-to-nearest operations per instruction, bit-identical
+// to the scalar forms.  The epilogues issue about one instruction per four clocks per warp, so halving the count of
+// the scale / bias and residual arithmetic is a direct saving.
+__device__ __forceinline__ void ffma2(float& a0, float& a1, float s0, float s1, float b0, float b1) {
+  unsigned long long a, sv, bv;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(a) : "f"(a0), "f"(a1));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(sv) : "f"(s0), "f"(s1));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(bv) : "f"(b0), "f"(b1));
+  asm("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(a) : "l"(sv), "l"(bv));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(a0), "=f"(a1) : "l"(a));
+}
+__device__ __forceinline__ void fadd2(float& a0, float& a1, float b0, float b1) {
+  unsigned long long a, bv;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(a) : "f"(a0), "f"(a1));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(bv) : "f"(b0), "f"(b1));
+  asm("add.rn.f32x2 %0, %0, %1;" : "+l"(a) : "l"(bv));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(a0), "=f"(a1) : "l"(a));
+}
+
 // The same epilogue math with scale / bias staged in shared memory by the caller (s_sc / s_bi point at the CNT values of
 // columns n0.., 16-byte aligned, already holding 1 / 0 where the layer has no scale / bias or the column is >= N): every
 // lane reads the same addresses, so the loads are LDS broadcasts instead of four dependent L2 round trips per 64
@@ -200,7 +219,7 @@ __device__ __forceinline__ void epilogue_math(const CrogGemm& g, const RowMap& m
 // 1850 of 3800 clocks per 64-column chunk in this step.)
 template <int CNT>
 __device__ __forceinline__ void epilogue_math_smem(const CrogGemm& g, const RowMap& m, int n0, float (&acc)[CNT], const float* s_sc,
-                                                   const float* s_bi) {
+                                                   const float* s_bi, bool relu_later = false) {
   const int nvalid = min(CNT, g.N - n0);
   if (g.addmat) {
     const float* ad = g.addmat + (long long)m.sp * g.N + n0;
@@ -219,12 +238,14 @@ __device__ __forceinline__ void epilogue_math_smem(const CrogGemm& g, const RowM
   for (int j = 0; j < CNT; j += 4) {
     const float4 s4 = *reinterpret_cast<const float4*>(s_sc + j);
     const float4 b4 = *reinterpret_cast<const float4*>(s_bi + j);
-    acc[j] = fmaf(acc[j], s4.x, b4.x); acc[j + 1] = fmaf(acc[j + 1], s4.y, b4.y);
-    acc[j + 2] = fmaf(acc[j + 2], s4.z, b4.z); acc[j + 3] = fmaf(acc[j + 3], s4.w, b4.w);
+    ffma2(acc[j], acc[j + 1], s4.x, s4.y, b4.x, b4.y);
+    ffma2(acc[j + 2], acc[j + 3], s4.z, s4.w, b4.z, b4.w);
   }
   if (g.act == CROG_ACT_RELU) {
+    if (!relu_later) {  // relu_later: the caller clamps the packed bf16 pairs instead (same bits, half the instructions)
 #pragma unroll
-    for (int j = 0; j < CNT; ++j) acc[j] = fmaxf(acc[j], 0.f);
+      for (int j = 0; j < CNT; ++j) acc[j] = fmaxf(acc[j], 0.f);
+    }
   } else if (g.act == CROG_ACT_QUICKGELU) {
 #pragma unroll
     for (int j = 0; j < CNT; ++j) acc[j] = quickgelu(acc[j]);

@@ -256,6 +256,9 @@ __global__ void __launch_bounds__(64 + EPI_WARPS * 32, 1) gemm_tc_kernel(const _
       constexpr int NCH = BN / CW;
       static_assert(BN % CW == 0, "tile must hold whole chunks");
       const bool has_res = g.residual != nullptr;
+      // bf16 outputs: ReLU commutes with the rounding, so it is applied to the packed pairs (HMNMX2) after the pack
+      const bool relu_late = L::SB && MODE == MODE_TMA_BF16 && g.act == CROG_ACT_RELU && !has_res && g.gate == nullptr;
+      const bool relu_packed = MODE == MODE_TMA_BF16 && (relu_late || (has_res && g.residual_relu));
       const uint32_t stg_u32 = smem_u32(stg), rbar0 = res0 + 8 * (ew * NBUF);
       const int sw = lane & 7;
       uint32_t nld = 0, ncs = 0;   // residual chunks requested / chunks consumed (warp-uniform)
@@ -314,7 +317,7 @@ __global__ void __launch_bounds__(64 + EPI_WARPS * 32, 1) gemm_tc_kernel(const _
               if (ncol + h * 32 < g.N) {
                 float(&a32)[32] = *reinterpret_cast<float(*)[32]>(&acc[h * 32]);
                 if constexpr (L::SB)
-                  epilogue_math_smem<32>(g, m, ncol + h * 32, a32, sbt + c * CW + h * 32, sbt + BN + c * CW + h * 32);
+                  epilogue_math_smem<32>(g, m, ncol + h * 32, a32, sbt + c * CW + h * 32, sbt + BN + c * CW + h * 32, relu_late);
                 else
                   epilogue_math<32>(g, m, ncol + h * 32, a32, g.scale ? g.scale + ncol + h * 32 : nullptr,
                                     g.bias ? g.bias + ncol + h * 32 : nullptr);
@@ -333,17 +336,18 @@ __global__ void __launch_bounds__(64 + EPI_WARPS * 32, 1) gemm_tc_kernel(const _
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                   const float2 f = __bfloat1622float2(h2[j]);
-                  acc[u * 8 + 2 * j] += f.x; acc[u * 8 + 2 * j + 1] += f.y;
+                  fadd2(acc[u * 8 + 2 * j], acc[u * 8 + 2 * j + 1], f.x, f.y);
                 }
               }
             } else {
 #pragma unroll
               for (int u = 0; u < 8; ++u) {
                 const float4 f = *reinterpret_cast<const float4*>(srow + ((u ^ sw) << 4));
-                acc[u * 4] += f.x; acc[u * 4 + 1] += f.y; acc[u * 4 + 2] += f.z; acc[u * 4 + 3] += f.w;
+                fadd2(acc[u * 4], acc[u * 4 + 1], f.x, f.y);
+                fadd2(acc[u * 4 + 2], acc[u * 4 + 3], f.z, f.w);
               }
             }
-            if (g.residual_relu) {
+            if (g.residual_relu && !relu_packed) {
 #pragma unroll
               for (int j = 0; j < CW; ++j) acc[j] = fmaxf(acc[j], 0.f);
             }
@@ -363,6 +367,11 @@ __global__ void __launch_bounds__(64 + EPI_WARPS * 32, 1) gemm_tc_kernel(const _
               __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&pk);
 #pragma unroll
               for (int j = 0; j < 4; ++j) h2[j] = __floats2bfloat162_rn(acc[u * 8 + 2 * j], acc[u * 8 + 2 * j + 1]);
+              if (relu_packed) {
+                const __nv_bfloat162 z2 = __floats2bfloat162_rn(0.f, 0.f);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) h2[j] = __hmax2(h2[j], z2);
+              }
               *reinterpret_cast<uint4*>(srow + ((u ^ sw) << 4)) = pk;
             }
           } else {
@@ -620,7 +629,7 @@ int dispatch(const CrogGemm* g, cudaStream_t stream) {
     return launch<256, 3, 2, MODE>(g, stream);
   }
   // short contractions are epilogue bound: three operand stages leave room for the shared-memory scale / bias slice
-  if (Ktot < 1024) return launch<128, 3, 3, MODE>(g, stream);
+  if (Ktot < 512) return launch<128, 3, 3, MODE>(g, stream);
   return launch<128, 4, 3, MODE>(g, stream);
 }
 
