@@ -215,10 +215,21 @@ def run_tail(args):
         for _ in range(max(args.warmup, 3)):
             out = step()
         torch.cuda.synchronize()
+        run = step
+        if not args.tail_no_graph and args.tail_chunks == 1:
+            # the four dependent launches of one step (scan, select, exact fallback, Jaccard) replayed as a CUDA graph:
+            # no host launch gaps between them (the forward is replayed the same way)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                out = step()
+            run = graph.replay
+            for _ in range(3):
+                run()
+            torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(args.steps):
-            step()
+            run()
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / args.steps
@@ -256,6 +267,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--workload", default="forward", choices=["forward", "tail"])
     ap.add_argument("--tail-maps", type=int, default=4096)
+    ap.add_argument("--tail-no-graph", action="store_true", help="launch the tail kernels eagerly instead of replaying a CUDA graph")
     ap.add_argument("--tail-chunks", type=int, default=1, help="sub-batches of the tail (scan of i+1 overlaps Jaccard of i)")
     ap.add_argument("--dump-ops", default=None, help="write the per-op CUDA-event table (eager replay) to this file")
     args = ap.parse_args()
