@@ -104,6 +104,7 @@ struct RowMap {
   int b;            // sample index
   int sp;           // interior pixel index (y*W+x) or row-in-sample
   int orow;         // output row (row counts fit 32 bits; multiply by the leading dimension in 64 bits)
+  float rs, sh;     // folded LayerNorm of the input rows (CrogGemm.row_stats_in): rstd and -mean * rstd; 1 and 0 otherwise
 };
 
 __device__ __forceinline__ RowMap map_row(const CrogGemm& g, long long r64, long long row_end) {
@@ -111,6 +112,7 @@ __device__ __forceinline__ RowMap map_row(const CrogGemm& g, long long r64, long
   const int r = (int)r64;
   m.valid = r64 < row_end;
   m.b = 0; m.sp = 0; m.orow = r;
+  m.rs = 1.f; m.sh = 0.f;
   if (!m.valid) return m;
   if (g.H == 0) {
     if (g.sample_rows > 0) { m.b = r / g.sample_rows; m.sp = r - m.b * g.sample_rows; }
@@ -137,6 +139,22 @@ __device__ __forceinline__ RowMap map_row(const CrogGemm& g, long long r64, long
   return m;
 }
 
+// Row statistics of a folded LayerNorm: sums the producer's per-chunk (sum, sum of squares) pairs of this row.
+__device__ __forceinline__ void load_row_stats(const CrogGemm& g, RowMap& m) {
+  if (!g.row_stats_in || !m.valid) return;
+  // 16-byte loads, eight in flight (a rolled loop of dependent 8-byte loads costs one L2 round trip per chunk)
+  const float4* p = reinterpret_cast<const float4*>(g.row_stats_in + (long long)m.orow * g.row_stats_chunks * 2);
+  float s = 0.f, q = 0.f;
+  const int n4 = g.row_stats_chunks >> 1;  // two (sum, sum^2) pairs per load; row_stats_chunks is even (checked on the host), so every row is 16-byte aligned
+#pragma unroll 8
+  for (int i = 0; i < n4; ++i) { const float4 v = __ldg(p + i); s += v.x + v.z; q += v.y + v.w; }
+  const float inv = 1.f / (float)g.row_stats_width;
+  const float mean = s * inv;
+  const float var = fmaxf(q * inv - mean * mean, 0.f);
+  m.rs = rsqrtf(var + g.row_stats_eps);
+  m.sh = -mean * m.rs;
+}
+
 __device__ __forceinline__ float quickgelu(float v) { return __fdividef(v, 1.f + __expf(-1.702f * v)); }
 
 // Epilogue math for CNT (multiple of 8) consecutive columns starting at n0 of one valid row: everything except the
@@ -161,7 +179,19 @@ __device__ __forceinline__ void epilogue_math(const CrogGemm& g, const RowMap& m
   }
   // scale and bias as one FFMA (a missing scale is 1, a missing bias 0, which keeps acc * s and acc + b exact), so
   // this path and the shared-memory one of the tcgen05 kernels (epilogue_math_smem) produce the same bits
-  if (sc || bi) {
+  if (g.row_stats_in) {  // folded LayerNorm: acc * rstd_r + (sh_r * s_n + c_n); sc = s, bi = c (both required)
+    if (nvalid == CNT) {
+#pragma unroll
+      for (int j = 0; j < CNT; j += 4) {
+        const float4 s4 = __ldg(reinterpret_cast<const float4*>(sc + j)), b4 = __ldg(reinterpret_cast<const float4*>(bi + j));
+        acc[j] = fmaf(acc[j], m.rs, fmaf(m.sh, s4.x, b4.x)); acc[j + 1] = fmaf(acc[j + 1], m.rs, fmaf(m.sh, s4.y, b4.y));
+        acc[j + 2] = fmaf(acc[j + 2], m.rs, fmaf(m.sh, s4.z, b4.z)); acc[j + 3] = fmaf(acc[j + 3], m.rs, fmaf(m.sh, s4.w, b4.w));
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < CNT; ++j) if (j < nvalid) acc[j] = fmaf(acc[j], m.rs, fmaf(m.sh, __ldg(sc + j), __ldg(bi + j)));
+    }
+  } else if (sc || bi) {
     if (nvalid == CNT) {
 #pragma unroll
       for (int j = 0; j < CNT; j += 4) {
@@ -234,12 +264,21 @@ __device__ __forceinline__ void epilogue_math_smem(const CrogGemm& g, const RowM
       for (int j = 0; j < CNT; ++j) if (j < nvalid) acc[j] += __ldg(ad + j);
     }
   }
+  if (g.row_stats_in) {  // folded LayerNorm (see epilogue_math): same arithmetic, s and c from shared memory
 #pragma unroll
-  for (int j = 0; j < CNT; j += 4) {
-    const float4 s4 = *reinterpret_cast<const float4*>(s_sc + j);
-    const float4 b4 = *reinterpret_cast<const float4*>(s_bi + j);
-    ffma2(acc[j], acc[j + 1], s4.x, s4.y, b4.x, b4.y);
-    ffma2(acc[j + 2], acc[j + 3], s4.z, s4.w, b4.z, b4.w);
+    for (int j = 0; j < CNT; j += 4) {
+      const float4 s4 = *reinterpret_cast<const float4*>(s_sc + j), b4 = *reinterpret_cast<const float4*>(s_bi + j);
+      acc[j] = fmaf(acc[j], m.rs, fmaf(m.sh, s4.x, b4.x)); acc[j + 1] = fmaf(acc[j + 1], m.rs, fmaf(m.sh, s4.y, b4.y));
+      acc[j + 2] = fmaf(acc[j + 2], m.rs, fmaf(m.sh, s4.z, b4.z)); acc[j + 3] = fmaf(acc[j + 3], m.rs, fmaf(m.sh, s4.w, b4.w));
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < CNT; j += 4) {
+      const float4 s4 = *reinterpret_cast<const float4*>(s_sc + j);
+      const float4 b4 = *reinterpret_cast<const float4*>(s_bi + j);
+      ffma2(acc[j], acc[j + 1], s4.x, s4.y, b4.x, b4.y);
+      ffma2(acc[j + 2], acc[j + 3], s4.z, s4.w, b4.z, b4.w);
+    }
   }
   if (g.act == CROG_ACT_RELU) {
     if (!relu_later) {  // relu_later: the caller clamps the packed bf16 pairs instead (same bits, half the instructions)

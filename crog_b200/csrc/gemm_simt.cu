@@ -72,7 +72,8 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const CrogGemm g, int n_
   __syncthreads();
   for (int it = tid; it < BM * (BN / 8); it += 256) {
     const int row = it / (BN / 8), cg = (it % (BN / 8)) * 8;
-    const RowMap m = map_row(g, tr.row0 + row, tr.row_end);
+    RowMap m = map_row(g, tr.row0 + row, tr.row_end);
+    load_row_stats(g, m);
     if (!m.valid || n0 + cg >= g.N) continue;
     float v[8];
 #pragma unroll
@@ -85,6 +86,7 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const CrogGemm g, int n_
 
 int crog_gemm_simt(const CrogGemm* g, cudaStream_t stream) {
   CROG_REQUIRE(g->cin % BK == 0, CROG_E_BADSHAPE, "gemm_simt: cin %d not a multiple of %d", g->cin, BK);
+  CROG_REQUIRE(!g->row_stats_out, CROG_E_BADSHAPE, "gemm_simt: the row-statistics producer exists on the tcgen05 path only");
   const int n_tiles = (g->N + BN - 1) / BN;
   const int grid = num_m_tiles(*g, BM) * n_tiles;
   if (grid == 0) return CROG_OK;

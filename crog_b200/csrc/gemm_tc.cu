@@ -257,7 +257,8 @@ __global__ void __launch_bounds__(64 + EPI_WARPS * 32, 1) gemm_tc_kernel(const _
       static_assert(BN % CW == 0, "tile must hold whole chunks");
       const bool has_res = g.residual != nullptr;
       // bf16 outputs: ReLU commutes with the rounding, so it is applied to the packed pairs (HMNMX2) after the pack
-      const bool relu_late = L::SB && MODE == MODE_TMA_BF16 && g.act == CROG_ACT_RELU && !has_res && g.gate == nullptr;
+      const bool relu_late = L::SB && MODE == MODE_TMA_BF16 && g.act == CROG_ACT_RELU && !has_res && g.gate == nullptr &&
+                             g.row_stats_out == nullptr;  // row statistics are taken of the clamped fp32 values
       const bool relu_packed = MODE == MODE_TMA_BF16 && (relu_late || (has_res && g.residual_relu));
       const uint32_t stg_u32 = smem_u32(stg), rbar0 = res0 + 8 * (ew * NBUF);
       const int sw = lane & 7;
@@ -290,7 +291,8 @@ __global__ void __launch_bounds__(64 + EPI_WARPS * 32, 1) gemm_tc_kernel(const _
         const int buf = i & 1;
         const uint32_t tfull = tfull0 + 8 * buf, tempty = tempty0 + 8 * buf;
         const int n0 = (tile % n_tiles) * BN, row0 = (tile / n_tiles) * MT + (int)rank * BM;
-        const RowMap m = map_row(g, (long long)row0 + q * 32 + lane, g.M);
+        RowMap m = map_row(g, (long long)row0 + q * 32 + lane, g.M);
+        load_row_stats(g, m);
         const int nvc = min(NCH, (g.N - n0 + CW - 1) / CW);  // chunks with at least one real column
         const float* sbt = stage_scale_bias(i / GROUPS, n0, tfull, (i >> 1) & 1);
         tc_fence_after();
@@ -322,6 +324,17 @@ __global__ void __launch_bounds__(64 + EPI_WARPS * 32, 1) gemm_tc_kernel(const _
                   epilogue_math<32>(g, m, ncol + h * 32, a32, g.scale ? g.scale + ncol + h * 32 : nullptr,
                                     g.bias ? g.bias + ncol + h * 32 : nullptr);
               }
+            }
+          }
+          if constexpr (MODE == MODE_TMA_BF16) {
+            if (g.row_stats_out && m.valid) {  // (sum, sum of squares) of this row's 64 outputs, for the LayerNorm folded into the next GEMM
+              float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+#pragma unroll
+              for (int j = 0; j < CW; j += 2) {
+                s0 += acc[j]; s1 += acc[j + 1];
+                q0 = fmaf(acc[j], acc[j], q0); q1 = fmaf(acc[j + 1], acc[j + 1], q1);
+              }
+              reinterpret_cast<float2*>(g.row_stats_out)[(long long)m.orow * g.row_stats_chunks + (ncol / CW)] = make_float2(s0 + s1, q0 + q1);
             }
           }
           const uint32_t b = ncs % NBUF;
@@ -411,7 +424,8 @@ __global__ void __launch_bounds__(64 + EPI_WARPS * 32, 1) gemm_tc_kernel(const _
         TileRows tr = tile_rows(g, m_t, MT);
         if constexpr (PAIR) tr.row0 += (long long)rank * BM;
         const int n0 = n_t * BN;
-        const RowMap m = map_row(g, tr.row0 + q * 32 + lane, tr.row_end);
+        RowMap m = map_row(g, tr.row0 + q * 32 + lane, tr.row_end);
+        load_row_stats(g, m);
         const int my_orow = m.valid ? m.orow : -1;
         int orow[PASSES];
 #pragma unroll
@@ -645,11 +659,21 @@ int crog_gemm_tc(const CrogGemm* g, cudaStream_t stream) {
   if (g->w_sample_stride > 0)
     CROG_REQUIRE(g->w_sample_stride % ((long long)g->taps * g->cin) == 0 && g->sample_rows > 0, CROG_E_BADSHAPE,
                  "gemm_tc: per-sample weights need whole rows");
+  if (g->row_stats_out || g->row_stats_in) {
+    CROG_REQUIRE(g->in_padded == 0 && g->out_padded == 0 && g->out_sample_rows == 0 && g->w_sample_stride == 0, CROG_E_BADSHAPE,
+                 "gemm_tc: folded LayerNorm needs the identity row mapping");
+    CROG_REQUIRE(g->row_stats_chunks > 0 && g->row_stats_chunks % 2 == 0 && g->row_stats_width > 0, CROG_E_BADSHAPE,
+                 "gemm_tc: row_stats_chunks (even) / row_stats_width");
+    CROG_REQUIRE(!g->row_stats_in || (g->scale && g->bias), CROG_E_BADSHAPE, "gemm_tc: the folded LayerNorm consumer needs scale (= s) and bias (= c)");
+    CROG_REQUIRE(!g->row_stats_out || (g->out_dtype == CROG_BF16 && g->N % 64 == 0 && g->row_stats_chunks == g->N / 64 && g->N > 16),
+                 CROG_E_BADSHAPE, "gemm_tc: the row-statistics producer writes bf16 through the TMA epilogue, N a multiple of 64");
+  }
   // TMA epilogue: output row == enumerated row (so the tile is one box of the output matrix), shared weights
   const bool identity = (g->H == 0) || (g->in_padded == g->out_padded);
   const int esz = g->out_dtype == CROG_BF16 ? 2 : 4;
   const bool tma_ok = identity && g->w_sample_stride == 0 && g->out_sample_rows == 0 && g->N > 16 && ((long long)g->out_ld * esz) % 16 == 0 &&
                       (!g->residual || ((long long)g->res_ld * esz) % 16 == 0) && !getenv("CROG_GEMM_LEGACY_EPILOGUE");
+  CROG_REQUIRE(!g->row_stats_out || tma_ok, CROG_E_BADSHAPE, "gemm_tc: the row-statistics producer needs the TMA epilogue (16-byte aligned rows, identity row mapping)");
   if (tma_ok) return g->out_dtype == CROG_BF16 ? dispatch<MODE_TMA_BF16>(g, stream) : dispatch<MODE_TMA_F32>(g, stream);
   if (g->N <= 16) return launch<16, 8, 2, MODE_LEGACY>(g, stream);
   return dispatch<MODE_LEGACY>(g, stream);

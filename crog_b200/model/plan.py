@@ -177,7 +177,8 @@ class ForwardPlan:
     def gemm(self, name: str, a: Act, w: torch.Tensor, N: int, out: Act, taps: int = 1, scale=None, bias=None,
              act: int = L.ACT_NONE, residual: Optional[Act] = None, residual_relu: bool = False, addmat=None,
              gate=None, scale2=None, bias2=None, w_sample_stride: int = 0, cin: Optional[int] = None,
-             alg_n: Optional[int] = None, alg_cin: Optional[int] = None, out_sample_rows: int = 0, out_row0: int = 0):
+             alg_n: Optional[int] = None, alg_cin: Optional[int] = None, out_sample_rows: int = 0, out_row0: int = 0,
+             row_stats_out: Optional[torch.Tensor] = None, row_stats_in: Optional[torch.Tensor] = None, row_stats_width: int = 0):
         g = L.CrogGemm()
         cin = cin if cin is not None else a.C
         assert w.shape[-1] == taps * cin, (name, tuple(w.shape), taps, cin)
@@ -199,6 +200,14 @@ class ForwardPlan:
         g.out, g.out_ld, g.out_dtype = out.ptr + out_row0 * out.ld * out.t.element_size(), out.ld, L.dtype_code(out.t.dtype)
         g.impl = self.impl
         g.out_sample_rows = out_sample_rows
+        if row_stats_out is not None:  # folded LayerNorm, producer side: (sum, sum^2) per row and 64-column chunk
+            assert row_stats_out.dtype == torch.float32 and row_stats_out.shape == (a.rows, N // 64, 2)
+            g.row_stats_out, g.row_stats_chunks, g.row_stats_width, g.row_stats_eps = row_stats_out.data_ptr(), N // 64, N, LN_EPS
+        if row_stats_in is not None:   # consumer side: scale = s, bias = c (see _decoder)
+            assert row_stats_in.dtype == torch.float32 and row_stats_in.shape[0] == a.rows and scale is not None and bias is not None
+            g.row_stats_in, g.row_stats_chunks, g.row_stats_width, g.row_stats_eps = (row_stats_in.data_ptr(), row_stats_in.shape[1],
+                                                                                   row_stats_width, LN_EPS)
+        self._hold.extend([row_stats_out, row_stats_in])
         if a.H > 0 and out_sample_rows == 0:
             assert out.H == a.H and out.W == a.W, name
         self._hold.extend([g, w, scale, bias, addmat, gate, scale2, bias2])
@@ -488,7 +497,12 @@ class ForwardPlan:
         qc = self.new(Hh, Ww, D)
         kv = self.new(0, 0, 2 * D, rows=B * Lt)
         ff = self.new(Hh, Ww, cfg.dim_ffn)
-        ff2 = self.new(Hh, Ww, cfg.dim_ffn)
+        # bf16 tcgen05 plans fold the FFN LayerNorm into ffn.4 (CROG_FFN_LN_FOLD=0: keep the separate LayerNorm pass)
+        fold_ln = (self.precision == "bf16" and self.impl != L.IMPL_SIMT and cfg.dim_ffn % 64 == 0 and
+                   os.environ.get("CROG_FFN_LN_FOLD", "1") != "0")
+        ff2 = None if fold_ln else self.new(Hh, Ww, cfg.dim_ffn)
+        ffn_stats = torch.zeros((rows, cfg.dim_ffn // 64, 2), device=self.dev, dtype=torch.float32) if fold_ln else None
+        self._hold.append(ffn_stats)
         i = 0
         while f"decoder.layers.{i}.norm1.weight" in sd:
             p = f"decoder.layers.{i}"
@@ -509,11 +523,24 @@ class ForwardPlan:
             self.gemm(p + ".cross.out_proj", att, self.wt(sd[p + ".multihead_attn.out_proj.weight"]), D, tmp,
                       bias=self.f32(sd[p + ".multihead_attn.out_proj.bias"]))
             self.layernorm_chain(p + ".cross_attn_norm+norm3", tmp, p + ".cross_attn_norm", vis, p + ".norm3", v2)
-            self.gemm(p + ".ffn.0", v2, self.wt(sd[p + ".ffn.0.weight"]), cfg.dim_ffn, ff, bias=self.f32(sd[p + ".ffn.0.bias"]),
-                      act=L.ACT_RELU)
-            self.layernorm(p + ".ffn.3", ff, p + ".ffn.3", ff2)
-            self.gemm(p + ".ffn.4", ff2, self.wt(sd[p + ".ffn.4.weight"]), D, vis, bias=self.f32(sd[p + ".ffn.4.bias"]),
-                      residual=vis)
+            if fold_ln:
+                # Linear -> ReLU -> LayerNorm(2048) -> Linear with the LayerNorm folded into the second contraction:
+                # LN(h) W^T = rstd (h W'^T) - mu rstd s + c,  W' = W gamma (per input column), s = row sums of the bf16 W',
+                # c = W beta + b.  ffn.0 also emits the per-row (sum h, sum h^2) partials; the 354 MB LayerNorm pass is gone.
+                w4, gam, bet = sd[p + ".ffn.4.weight"].float(), sd[p + ".ffn.3.weight"].float(), sd[p + ".ffn.3.bias"].float()
+                w4g = self.wt(w4 * gam[None, :])
+                s_vec = self.f32(w4g.float().sum(1))
+                c_vec = self.f32(w4 @ bet + sd[p + ".ffn.4.bias"].float())
+                self.gemm(p + ".ffn.0", v2, self.wt(sd[p + ".ffn.0.weight"]), cfg.dim_ffn, ff, bias=self.f32(sd[p + ".ffn.0.bias"]),
+                          act=L.ACT_RELU, row_stats_out=ffn_stats)
+                self.gemm(p + ".ffn.4", ff, w4g, D, vis, scale=s_vec, bias=c_vec, residual=vis, row_stats_in=ffn_stats,
+                          row_stats_width=cfg.dim_ffn)
+            else:
+                self.gemm(p + ".ffn.0", v2, self.wt(sd[p + ".ffn.0.weight"]), cfg.dim_ffn, ff, bias=self.f32(sd[p + ".ffn.0.bias"]),
+                          act=L.ACT_RELU)
+                self.layernorm(p + ".ffn.3", ff, p + ".ffn.3", ff2)
+                self.gemm(p + ".ffn.4", ff2, self.wt(sd[p + ".ffn.4.weight"]), D, vis, bias=self.f32(sd[p + ".ffn.4.bias"]),
+                          residual=vis)
             i += 1
         out = self.new(Hh, Ww, D)
         self.layernorm("decoder.norm", vis, "decoder.norm", out)

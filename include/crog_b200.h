@@ -94,6 +94,18 @@ typedef struct CrogGemm {
                              autotuner times the applicable ones per layer; every configuration accumulates the k-blocks
                              in the same order, so results are bit-identical across them).  A configuration that does
                              not apply to the shape returns CROG_E_BADSHAPE. */
+  /* LayerNorm folded into the next contraction (decoder FFN, model/layers.py:302-308: Linear -> ReLU -> LayerNorm ->
+     Linear).  LN(h) W^T = rstd_r (h W'^T) - mu_r rstd_r s + c with W' = W * gamma (columns), s_n = sum_k W'[n,k],
+     c = W beta + b: the producer GEMM also writes, per row and 64-column chunk, (sum h, sum h^2) of its fp32 outputs
+     (row_stats_out: M x N/64 x 2 fp32 values, bf16 TMA-epilogue path only), and the consumer GEMM (weights W', scale = s,
+     bias = c) reads them back (row_stats_in, row_stats_chunks pairs per row over row_stats_width values) and applies
+     out = acc * rstd_r + (-mu_r rstd_r) * s_n + c_n.  Plain row matrices / compact layouts only (output row ==
+     enumerated row). */
+  float* row_stats_out;
+  const float* row_stats_in;
+  int32_t row_stats_chunks;
+  int32_t row_stats_width;
+  float row_stats_eps;
 } CrogGemm;
 enum {
   CROG_TILE_AUTO = 0,

@@ -4,6 +4,8 @@ Floating-point kernels are compared with a plain PyTorch fp32 restatement of the
 (tolerance written at each assert); integer / index work (peaks, rasterised IoU, J flags) is
 compared bit-for-bit with the CPU oracle.
 """
+import ctypes as C
+
 import numpy as np
 import pytest
 import torch
@@ -29,7 +31,7 @@ def _rand(*shape, seed=0, scale=1.0):
 
 def test_library_and_device():
     lib = L.lib()
-    assert lib.crog_abi_version() == 2
+    assert lib.crog_abi_version() == 3
     assert lib.crog_check_device() == 0
 
 
@@ -576,3 +578,52 @@ def test_attention_lazy_rescale_and_chained_layernorm():
                                      z.data_ptr(), L.BF16, rows, Dm, 1e-5, L.stream_ptr()))
     torch.cuda.synchronize()
     assert maxerr(y, y_ref) <= 1e-6 * float(y_ref.abs().max()) and maxerr(z, z_ref) <= 2e-2
+
+
+def test_layernorm_folded_into_gemm():
+    """Linear -> ReLU -> LayerNorm -> Linear (decoder FFN, layers.py:302-308) with the LayerNorm folded into the second
+    GEMM (row statistics emitted by the first GEMM's epilogue) against the unfused kernels and an fp32 torch reference."""
+    torch.manual_seed(13)
+    M, D, Fh = 676 * 3 + 5, 512, 2048
+    dt = torch.bfloat16
+    x = (torch.randn(M, D, device=DEV) * 0.7).to(dt)
+    w0 = (torch.randn(Fh, D, device=DEV) * D ** -0.5)
+    b0 = torch.randn(Fh, device=DEV) * 0.3
+    gam, bet = torch.rand(Fh, device=DEV) + 0.5, torch.randn(Fh, device=DEV) * 0.2
+    w4 = torch.randn(D, Fh, device=DEV) * Fh ** -0.5
+    b4 = torch.randn(D, device=DEV) * 0.1
+    res = torch.randn(M, D, device=DEV)
+    # fp32 reference on the bf16-rounded operands
+    h = torch.relu(x.float() @ w0.to(dt).float().t() + b0)
+    want = torch.nn.functional.layer_norm(h, (Fh,), gam, bet, 1e-5) @ w4.t() + b4 + res
+
+    def gemm(a, w, N, out, **kw):
+        g = L.CrogGemm()
+        g.a, g.a_rows, g.a_ld, g.cin, g.taps, g.dtype, g.M = a.data_ptr(), a.shape[0], a.shape[1], a.shape[1], 1, L.BF16, a.shape[0]
+        g.w, g.N, g.out, g.out_ld, g.out_dtype, g.impl = w.data_ptr(), N, out.data_ptr(), out.shape[1], L.dtype_code(out.dtype), L.IMPL_TCGEN05
+        for k, v in kw.items():
+            setattr(g, k, v.data_ptr() if isinstance(v, torch.Tensor) else v)
+        L.check(L.lib().crog_gemm(C.byref(g), L.stream_ptr()))
+
+    # unfused: GEMM -> LayerNorm kernel -> GEMM
+    ff = torch.zeros(M, Fh, device=DEV, dtype=dt); ff2 = torch.zeros_like(ff)
+    gemm(x, w0.to(dt), Fh, ff, bias=b0, act=L.ACT_RELU)
+    L.check(L.lib().crog_layernorm(ff.data_ptr(), L.BF16, gam.data_ptr(), bet.data_ptr(), None, ff2.data_ptr(), L.BF16, M, Fh, 1e-5, L.stream_ptr()))
+    out_a = res.clone()
+    gemm(ff2, w4.to(dt), D, out_a, bias=b4, residual=out_a, res_ld=D)
+    # folded
+    stats = torch.zeros(M, Fh // 64, 2, device=DEV)
+    ffb = torch.zeros(M, Fh, device=DEV, dtype=dt)
+    gemm(x, w0.to(dt), Fh, ffb, bias=b0, act=L.ACT_RELU, row_stats_out=stats, row_stats_chunks=Fh // 64, row_stats_width=Fh, row_stats_eps=1e-5)
+    w4g = (w4 * gam[None, :]).to(dt)
+    s_vec, c_vec = w4g.float().sum(1).contiguous(), (w4 @ bet + b4).contiguous()
+    out_b = res.clone()
+    gemm(ffb, w4g, D, out_b, scale=s_vec, bias=c_vec, residual=out_b, res_ld=D, row_stats_in=stats, row_stats_chunks=Fh // 64,
+         row_stats_width=Fh, row_stats_eps=1e-5)
+    torch.cuda.synchronize()
+    assert torch.equal(ff, ffb)  # emitting the statistics does not change the producer's output
+    hs = ff.float()
+    assert torch.allclose(stats[..., 0].sum(1), hs.sum(1), rtol=2e-3, atol=2e-2) and torch.allclose(stats[..., 1].sum(1), (hs * hs).sum(1), rtol=4e-3)
+    ea, eb = relerr(out_a - res, want - res), relerr(out_b - res, want - res)
+    assert ea < 1e-2 and eb < 1e-2, (ea, eb)
+    assert eb < 1.5 * ea + 1e-3, (ea, eb)  # the fold is as accurate as the separate LayerNorm pass
