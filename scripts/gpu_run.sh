@@ -1,10 +1,6 @@
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_gpu_kernels.py -x -q -k "folded or tile_cfgs or plain_gemm or epilogue" 2>&1 | tail -5
-CROG_FFN_LN_FOLD=0 python scripts/bf16_err.py 2>&1 | tail -1
-CROG_FFN_LN_FOLD=1 python scripts/bf16_err.py 2>&1 | tail -1
-timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
-CROG_FFN_LN_FOLD=0 python bench.py --steps 30 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/bench_nofold.json 2> gpurun_out/bench_nofold.err
-python -c "import sys,json; d=json.loads(open('gpurun_out/bench_nofold.json').read().strip().splitlines()[-1]); print('nofold', d['value'], d['ms_per_step'], d['roofline']['achieved'])"
-python bench.py --steps 30 --warmup 3 --no-cpu-baseline --no-e2e --dump-ops gpurun_out/ops_tuned.txt > gpurun_out/bench_tuned.json 2> gpurun_out/bench_tuned.err
-python -c "import sys,json; d=json.loads(open('gpurun_out/bench_tuned.json').read().strip().splitlines()[-1]); print('fold', d['value'], d['ms_per_step'], d['roofline']['achieved'], d['clocks'])"
-grep -E "decoder.layers.0.ffn" gpurun_out/ops_tuned.txt
+M=gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active,sm__throughput.avg.pct_of_peak_sustained_elapsed
+CROG_NO_FORK=1 ncu --metrics $M --clock-control none --profile-from-start off --csv --log-file gpurun_out/launches_v4_raw.csv python tests/prof_forward.py 64 gpurun_out/ops_v4.tsv > gpurun_out/prof_fwd.log 2>&1
+tail -1 gpurun_out/prof_fwd.log
+ncu --set full --import-source on --clock-control none --profile-from-start off -k regex:gemm_tc -c 1 -o gpurun_out/gemm_l1c3_v4 -f python tests/prof_gemm_shape.py 692224 256 64 0 > gpurun_out/ncu_g.log 2>&1
+tail -1 gpurun_out/ncu_g.log
