@@ -10,7 +10,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_HERE, "lib", "libcrog_b200.so")
+SO_PATH = os.environ.get("CROG_B200_SO") or os.path.join(_HERE, "lib", "libcrog_b200.so")  # override: A/B of two builds
 
 F32, BF16 = 0, 1
 ACT_NONE, ACT_RELU, ACT_QUICKGELU, ACT_TANH = 0, 1, 2, 3

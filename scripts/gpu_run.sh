@@ -1,6 +1,8 @@
 mkdir -p gpurun_out
-M=gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active,sm__throughput.avg.pct_of_peak_sustained_elapsed
-CROG_NO_FORK=1 ncu --metrics $M --clock-control none --profile-from-start off --csv --log-file gpurun_out/launches_v4_raw.csv python tests/prof_forward.py 64 gpurun_out/ops_v4.tsv > gpurun_out/prof_fwd.log 2>&1
-tail -1 gpurun_out/prof_fwd.log
-ncu --set full --import-source on --clock-control none --profile-from-start off -k regex:gemm_tc -c 1 -o gpurun_out/gemm_l1c3_v4 -f python tests/prof_gemm_shape.py 692224 256 64 0 > gpurun_out/ncu_g.log 2>&1
-tail -1 gpurun_out/ncu_g.log
+for rep in 1 2; do
+for so in crog_b200/lib/libcrog_b200.so crog_b200/lib/libcrog_nb.so; do
+echo "== $so"
+CROG_B200_SO=$PWD/$so python tests/prof_gemm_shape.py 692224 256 64 0; CROG_B200_SO=$PWD/$so python tests/prof_gemm_shape.py 43264 1024 256 0
+CROG_B200_SO=$PWD/$so python bench.py --steps 30 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/b.json 2> gpurun_out/b.err
+python -c "import sys,json; d=json.loads(open('gpurun_out/b.json').read().strip().splitlines()[-1]); print('bench', d['value'], d['ms_per_step'], d['roofline']['achieved'], d['clocks']['sm_mhz'])"
+done; done
