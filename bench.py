@@ -59,14 +59,20 @@ class ClockSampler:
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append([c.strip() for c in line.split(",")] + [time.time()])
 
-    def stop(self):
+    def stop(self, window=None):
+        """`window` = (t0, t1) host times of the timed region: only samples taken inside it count (the sampler is
+        started early because nvidia-smi needs a few hundred ms to come up); without samples inside, the nearest ones."""
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
+        rows = self.rows
+        if window is not None:
+            inside = [r for r in rows if window[0] <= r[-1] <= window[1] + 0.06]
+            rows = inside if inside else sorted(rows, key=lambda r: min(abs(r[-1] - window[0]), abs(r[-1] - window[1])))[:3]
         sm, mx, reasons = [], [], set()
-        for r in self.rows:
+        for r in rows:
             try:
                 sm.append(float(r[1])); mx.append(float(r[2]))
                 for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
@@ -74,7 +80,7 @@ class ClockSampler:
                         reasons.add(name)
             except Exception:
                 pass
-        busy = sorted(sm)[len(sm) // 2:] if sm else []  # upper half = samples under load
+        busy = sm if window is not None else (sorted(sm)[len(sm) // 2:] if sm else [])  # no window: upper half = samples under load
         return {"sm_mhz": float(np.median(busy)) if busy else None, "sm_max_mhz": max(mx) if mx else None,
                 "reasons": sorted(reasons), "samples": len(sm)}
 
@@ -269,6 +275,7 @@ def main():
     ap.add_argument("--tail-maps", type=int, default=4096)
     ap.add_argument("--tail-no-graph", action="store_true", help="launch the tail kernels eagerly instead of replaying a CUDA graph")
     ap.add_argument("--tail-chunks", type=int, default=1, help="sub-batches of the tail (scan of i+1 overlaps Jaccard of i)")
+    ap.add_argument("--ncu-range", action="store_true", help="bracket the timed region with cudaProfilerStart/Stop (ncu --profile-from-start off)")
     ap.add_argument("--dump-ops", default=None, help="write the per-op CUDA-event table (eager replay) to this file")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
@@ -329,13 +336,19 @@ def main():
     def step_resident():
         ev.step(d_img, d_word, d_gt, d_cnt)
 
-    for _ in range(args.warmup):
-        step_resident()
     sampler = ClockSampler(local)
     if rank == 0:
-        sampler.start()
+        sampler.start()  # early: nvidia-smi takes a few hundred ms to deliver its first sample
+    for _ in range(args.warmup):
+        step_resident()
+    if args.ncu_range:
+        torch.cuda.profiler.start()
+    t_w0 = time.time()
     ms = timed(step_resident, args.steps)
-    clocks = sampler.stop() if rank == 0 else None
+    t_w1 = time.time()
+    if args.ncu_range:
+        torch.cuda.profiler.stop()
+    clocks = sampler.stop((t_w0, t_w1)) if rank == 0 else None
     value = world * B * args.steps / (ms / 1e3)
     ev.reduce()
     counters = ev.counters.tolist()
@@ -385,6 +398,10 @@ def main():
         for _ in range(reps):
             evs = [torch.cuda.Event(enable_timing=True) for _ in range(len(plan.ops) + 1)]
             s = L.stream_ptr()
+            # keep the GPU busy while the host enqueues the ~220 launches + events (a few ms of ctypes calls), so that the
+            # event-to-event durations are kernel times, not host launch gaps (the 10-20 us text-tower kernels otherwise
+            # wait for the host)
+            torch.cuda._sleep(int(1.2e7))
             evs[0].record()
             for i, fn in enumerate(plan.ops):
                 fn(s)

@@ -399,7 +399,10 @@ __global__ void sigmoid_bicubic_kernel(const float* __restrict__ in, float* __re
 }
 
 // Tiled variant: one CTA produces a 64 x 32 output tile from a <= 32 x 16 source tile staged (with the sigmoid
-// applied once per source pixel) in shared memory; stores are coalesced 128 B rows.
+// applied once per source pixel) in shared memory; stores are coalesced 128 B rows.  A thread owns one output column
+// and 8 consecutive output rows: the horizontal weights are computed once, and the horizontally filtered source rows
+// slide as a 4-row window down the column (a new source row costs 4 shared-memory reads + 4 FMA, and at scale 1/4 only
+// every fourth output row needs one), so an output costs ~15 instructions instead of ~100.
 constexpr int BT_OW = 64, BT_OH = 32, BT_SW = 32, BT_SH = 16;
 __global__ void __launch_bounds__(256) sigmoid_bicubic_tiled_kernel(const float* __restrict__ in, float* __restrict__ out, int B,
                                                                     int Hin, int Win, int Hout, int Wout, uint32_t sig_mask,
@@ -418,36 +421,41 @@ __global__ void __launch_bounds__(256) sigmoid_bicubic_tiled_kernel(const float*
     tile[ty][tx] = v;
   }
   __syncthreads();
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  float* dst = out + (long long)pl * Hout * Wout;
+  const int ox = ox0 + (threadIdx.x & 63), oyb = oy0 + (threadIdx.x >> 6) * 8;  // a warp = 32 consecutive columns, same rows
+  if (ox >= Wout) return;
+  const float rx = sw * ox;
+  const int ix = (int)floorf(rx);
+  const float fx = rx - ix;
+  const float wx[4] = {cc2(fx + 1.f), cc1(fx), cc1(1.f - fx), cc2(2.f - fx)};
+  const int sx = ix - 1 - ix_lo;
+  auto hrow = [&](int row) {  // horizontally filtered source row (same summation order as the reference formulation)
+    float r = 0.f;
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const int oy = oy0 + ty + 8 * j;
-    if (oy >= Hout) continue;
+    for (int c = 0; c < 4; ++c) r += tile[row][sx + c] * wx[c];
+    return r;
+  };
+  float* dst = out + (long long)pl * Hout * Wout + ox;
+  int cur = -1000;
+  float h0 = 0.f, h1 = 0.f, h2 = 0.f, h3 = 0.f;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int oy = oyb + j;
+    if (oy >= Hout) break;
     const float ry = sh * oy;
     const int iy = (int)floorf(ry);
     const float fy = ry - iy;
-    const float wy[4] = {cc2(fy + 1.f), cc1(fy), cc1(1.f - fy), cc2(2.f - fy)};
-    const int sy = iy - 1 - iy_lo;
-#pragma unroll
-    for (int i = 0; i < 2; ++i) {
-      const int ox = ox0 + tx + 32 * i;
-      if (ox >= Wout) continue;
-      const float rx = sw * ox;
-      const int ix = (int)floorf(rx);
-      const float fx = rx - ix;
-      const float wx[4] = {cc2(fx + 1.f), cc1(fx), cc1(1.f - fx), cc2(2.f - fx)};
-      const int sx = ix - 1 - ix_lo;
-      float acc = 0.f;
-#pragma unroll
-      for (int a = 0; a < 4; ++a) {
-        float r = 0.f;
-#pragma unroll
-        for (int c = 0; c < 4; ++c) r += tile[sy + a][sx + c] * wx[c];
-        acc += r * wy[a];
-      }
-      dst[(long long)oy * Wout + ox] = acc;
+    const int sy = iy - 1 - iy_lo;  // warp-uniform
+    if (sy != cur) {
+      if (sy == cur + 1) { h0 = h1; h1 = h2; h2 = h3; h3 = hrow(sy + 3); }
+      else { h0 = hrow(sy); h1 = hrow(sy + 1); h2 = hrow(sy + 2); h3 = hrow(sy + 3); }
+      cur = sy;
     }
+    float acc = 0.f;
+    acc += h0 * cc2(fy + 1.f);
+    acc += h1 * cc1(fy);
+    acc += h2 * cc1(1.f - fy);
+    acc += h3 * cc2(2.f - fy);
+    dst[(long long)oy * Wout] = acc;
   }
 }
 

@@ -1,8 +1,11 @@
 mkdir -p gpurun_out
-for rep in 1 2; do
-for so in crog_b200/lib/libcrog_b200.so crog_b200/lib/libcrog_nb.so; do
-echo "== $so"
-CROG_B200_SO=$PWD/$so python tests/prof_gemm_shape.py 692224 256 64 0; CROG_B200_SO=$PWD/$so python tests/prof_gemm_shape.py 43264 1024 256 0
-CROG_B200_SO=$PWD/$so python bench.py --steps 30 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/b.json 2> gpurun_out/b.err
-python -c "import sys,json; d=json.loads(open('gpurun_out/b.json').read().strip().splitlines()[-1]); print('bench', d['value'], d['ms_per_step'], d['roofline']['achieved'], d['clocks']['sm_mhz'])"
-done; done
+timeout 600 python -m pytest tests/test_gpu_kernels.py tests/test_gpu_model.py -x -q -k "sigmoid or engine or module_contract" 2>&1 | tail -3
+ncu --metrics gpu__time_duration.sum --clock-control none -k regex:sigmoid_bicubic --csv python -c "
+import torch, sys
+sys.path.insert(0,'.')
+from crog_b200.engine import postprocess
+maps=[torch.randn(64,1,104,104,device='cuda') for _ in range(5)]
+for _ in range(3): postprocess(maps,(416,416))
+torch.cuda.synchronize()
+" 2>&1 | grep -E "sigmoid" | tail -3
+python bench.py --steps 30 --no-cpu-baseline --no-e2e > gpurun_out/b.json 2> gpurun_out/b.err; python -c "import sys,json; d=json.loads(open('gpurun_out/b.json').read().strip().splitlines()[-1]); print('bench', d['value'], d['ms_per_step'], d['roofline']['achieved'], d['clocks'])"
