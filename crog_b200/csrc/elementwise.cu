@@ -408,6 +408,8 @@ __global__ void __launch_bounds__(256) sigmoid_bicubic_tiled_kernel(const float*
                                                                     int Hin, int Win, int Hout, int Wout, uint32_t sig_mask,
                                                                     float sh, float sw) {
   __shared__ float tile[BT_SH][BT_SW + 1];
+  __shared__ float4 s_wy[BT_OH];  // vertical weights of the tile's 32 output rows (the same for every column)
+  __shared__ int s_sy[BT_OH];     // first source row of each output row, relative to the staged tile
   const int pl = blockIdx.z, p = pl / B;
   const bool sig = (sig_mask >> p) & 1u;
   const int ox0 = blockIdx.x * BT_OW, oy0 = blockIdx.y * BT_OH;
@@ -420,8 +422,16 @@ __global__ void __launch_bounds__(256) sigmoid_bicubic_tiled_kernel(const float*
     if (sig) v = 1.f / (1.f + expf(-v));
     tile[ty][tx] = v;
   }
+  if (threadIdx.x < BT_OH) {
+    const float ry = sh * (oy0 + (int)threadIdx.x);
+    const int iy = (int)floorf(ry);
+    const float fy = ry - iy;
+    s_wy[threadIdx.x] = make_float4(cc2(fy + 1.f), cc1(fy), cc1(1.f - fy), cc2(2.f - fy));
+    s_sy[threadIdx.x] = iy - 1 - iy_lo;
+  }
   __syncthreads();
-  const int ox = ox0 + (threadIdx.x & 63), oyb = oy0 + (threadIdx.x >> 6) * 8;  // a warp = 32 consecutive columns, same rows
+  const int rg = threadIdx.x >> 6;  // row group: 8 consecutive output rows
+  const int ox = ox0 + (threadIdx.x & 63), oyb = oy0 + rg * 8;  // a warp = 32 consecutive columns, same rows
   if (ox >= Wout) return;
   const float rx = sw * ox;
   const int ix = (int)floorf(rx);
@@ -441,20 +451,18 @@ __global__ void __launch_bounds__(256) sigmoid_bicubic_tiled_kernel(const float*
   for (int j = 0; j < 8; ++j) {
     const int oy = oyb + j;
     if (oy >= Hout) break;
-    const float ry = sh * oy;
-    const int iy = (int)floorf(ry);
-    const float fy = ry - iy;
-    const int sy = iy - 1 - iy_lo;  // warp-uniform
+    const int sy = s_sy[rg * 8 + j];  // warp-uniform
+    const float4 wy = s_wy[rg * 8 + j];
     if (sy != cur) {
       if (sy == cur + 1) { h0 = h1; h1 = h2; h2 = h3; h3 = hrow(sy + 3); }
       else { h0 = hrow(sy); h1 = hrow(sy + 1); h2 = hrow(sy + 2); h3 = hrow(sy + 3); }
       cur = sy;
     }
     float acc = 0.f;
-    acc += h0 * cc2(fy + 1.f);
-    acc += h1 * cc1(fy);
-    acc += h2 * cc1(1.f - fy);
-    acc += h3 * cc2(2.f - fy);
+    acc += h0 * wy.x;
+    acc += h1 * wy.y;
+    acc += h2 * wy.z;
+    acc += h3 * wy.w;
     dst[(long long)oy * Wout] = acc;
   }
 }

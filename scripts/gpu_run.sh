@@ -8,4 +8,4 @@ maps=[torch.randn(64,1,104,104,device='cuda') for _ in range(5)]
 for _ in range(3): postprocess(maps,(416,416))
 torch.cuda.synchronize()
 " 2>&1 | grep -E "sigmoid" | tail -3
-python bench.py --steps 30 --no-cpu-baseline --no-e2e > gpurun_out/b.json 2> gpurun_out/b.err; python -c "import sys,json; d=json.loads(open('gpurun_out/b.json').read().strip().splitlines()[-1]); print('bench', d['value'], d['ms_per_step'], d['roofline']['achieved'], d['clocks'])"
+
