@@ -234,6 +234,15 @@ __device__ __forceinline__ void ffma2(float& a0, float& a1, float s0, float s1, 
   asm("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(a) : "l"(sv), "l"(bv));
   asm("mov.b64 {%0, %1}, %2;" : "=f"(a0), "=f"(a1) : "l"(a));
 }
+// (v0, v1) = (a, a) * (w0, w1) + (v0, v1)
+__device__ __forceinline__ void fma2_bcast(float& v0, float& v1, float a, float w0, float w1) {
+  unsigned long long v, av, wv;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(v) : "f"(v0), "f"(v1));
+  asm("mov.b64 %0, {%1, %1};" : "=l"(av) : "f"(a));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(wv) : "f"(w0), "f"(w1));
+  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(v) : "l"(av), "l"(wv));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(v0), "=f"(v1) : "l"(v));
+}
 __device__ __forceinline__ void fadd2(float& a0, float& a1, float b0, float b1) {
   unsigned long long a, bv;
   asm("mov.b64 %0, {%1, %2};" : "=l"(a) : "f"(a0), "f"(a1));

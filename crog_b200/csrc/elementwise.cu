@@ -145,10 +145,11 @@ __global__ void __launch_bounds__(128) stem_conv1_kernel(const float* __restrict
           const float4 w0 = *reinterpret_cast<const float4*>(&sw[k * cout + c0]);
           const float4 w1 = *reinterpret_cast<const float4*>(&sw[k * cout + c0 + 4]);
           const float a = x[ci][ky][kx], c = x[ci][ky][kx + 2];
-          v0[0] = fmaf(a, w0.x, v0[0]); v0[1] = fmaf(a, w0.y, v0[1]); v0[2] = fmaf(a, w0.z, v0[2]); v0[3] = fmaf(a, w0.w, v0[3]);
-          v0[4] = fmaf(a, w1.x, v0[4]); v0[5] = fmaf(a, w1.y, v0[5]); v0[6] = fmaf(a, w1.z, v0[6]); v0[7] = fmaf(a, w1.w, v0[7]);
-          v1[0] = fmaf(c, w0.x, v1[0]); v1[1] = fmaf(c, w0.y, v1[1]); v1[2] = fmaf(c, w0.z, v1[2]); v1[3] = fmaf(c, w0.w, v1[3]);
-          v1[4] = fmaf(c, w1.x, v1[4]); v1[5] = fmaf(c, w1.y, v1[5]); v1[6] = fmaf(c, w1.z, v1[6]); v1[7] = fmaf(c, w1.w, v1[7]);
+          // packed FFMA2: (v[2j], v[2j+1]) += (a, a) * (w[2j], w[2j+1]) — the same two fused multiply-adds, one instruction
+          fma2_bcast(v0[0], v0[1], a, w0.x, w0.y); fma2_bcast(v0[2], v0[3], a, w0.z, w0.w);
+          fma2_bcast(v0[4], v0[5], a, w1.x, w1.y); fma2_bcast(v0[6], v0[7], a, w1.z, w1.w);
+          fma2_bcast(v1[0], v1[1], c, w0.x, w0.y); fma2_bcast(v1[2], v1[3], c, w0.z, w0.w);
+          fma2_bcast(v1[4], v1[5], c, w1.x, w1.y); fma2_bcast(v1[6], v1[7], c, w1.z, w1.w);
         }
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
