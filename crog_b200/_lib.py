@@ -35,6 +35,7 @@ class CrogGemm(C.Structure):
         ("bias2", C.c_void_p), ("residual", C.c_void_p), ("res_ld", C.c_int32), ("residual_relu", C.c_int32),
         ("out", C.c_void_p), ("out_ld", C.c_int32), ("out_dtype", C.c_int32), ("impl", C.c_int32),
         ("out_sample_rows", C.c_int32), ("tile_cfg", C.c_int32),
+        ("a2", C.c_void_p), ("a2_ld", C.c_int32), ("cin2", C.c_int32),
         ("row_stats_out", C.c_void_p), ("row_stats_in", C.c_void_p), ("row_stats_chunks", C.c_int32),
         ("row_stats_width", C.c_int32), ("row_stats_eps", C.c_float),
     ]

@@ -86,6 +86,7 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const CrogGemm g, int n_
 
 int crog_gemm_simt(const CrogGemm* g, cudaStream_t stream) {
   CROG_REQUIRE(g->cin % BK == 0, CROG_E_BADSHAPE, "gemm_simt: cin %d not a multiple of %d", g->cin, BK);
+  CROG_REQUIRE(!g->a2 && g->cin2 == 0, CROG_E_BADSHAPE, "gemm_simt: the second activation operand exists on the tcgen05 path only");
   CROG_REQUIRE(!g->row_stats_out, CROG_E_BADSHAPE, "gemm_simt: the row-statistics producer exists on the tcgen05 path only");
   const int n_tiles = (g->N + BN - 1) / BN;
   const int grid = num_m_tiles(*g, BM) * n_tiles;

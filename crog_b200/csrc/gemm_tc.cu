@@ -74,6 +74,7 @@ struct Cfg {
 
 template <int BN, int STAGES, int NBUF, int MODE, bool CONV3, int EPI_WARPS, bool PAIR>
 __global__ void __launch_bounds__(64 + EPI_WARPS * 32, 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                                   const __grid_constant__ CUtensorMap tmA2,
                                                                    const __grid_constant__ CUtensorMap tmB,
                                                                    const __grid_constant__ CUtensorMap tmOut,
                                                                    const __grid_constant__ CUtensorMap tmRes,
@@ -96,13 +97,14 @@ __global__ void __launch_bounds__(64 + EPI_WARPS * 32, 1) gemm_tc_kernel(const _
 #define tile0 (PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x)       /* both CTAs of a pair walk the same tiles */
 #define tstep (PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x)
   const int kchunks = g.cin / BK;
-  const int num_kb = CONV3 ? 3 : g.taps * kchunks;  // CONV3: one k-block per ky band
+  const int num_kb = CONV3 ? 3 : g.taps * kchunks + g.cin2 / BK;  // CONV3: one k-block per ky band; a2: its chunks follow a's
   const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + STAGES), tfull0 = smem_u32(bars + 2 * STAGES),
                  tempty0 = smem_u32(bars + 2 * STAGES + 2), bres = smem_u32(bars + 2 * STAGES + 4),
                  res0 = smem_u32(bars + 2 * STAGES + 5);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
+    if (g.a2) tma_prefetch_desc(&tmA2);
     tma_prefetch_desc(&tmB);
     if (MODE != MODE_LEGACY) {
       tma_prefetch_desc(&tmOut);
@@ -156,11 +158,13 @@ __global__ void __launch_bounds__(64 + EPI_WARPS * 32, 1) gemm_tc_kernel(const _
             // both CTAs report to the LEADER's full barrier; this CTA stages its own rows of A and its half of the weights
             const uint32_t lfull = mapa_shared(full0 + 8 * s, 0);
             mbar_expect_tx_cluster(lfull, L::A_BYTES + L::B_BYTES);
-            tma_load_2d_pair(sa, &tmA, c0, (int)(tr.row0 + tap_shift(g.taps, tap, g.W)), lfull);
+            if (kb >= g.taps * kchunks) tma_load_2d_pair(sa, &tmA2, (kb - kchunks) * BK, (int)tr.row0, lfull);  // second operand (taps == 1)
+            else tma_load_2d_pair(sa, &tmA, c0, (int)(tr.row0 + tap_shift(g.taps, tap, g.W)), lfull);
             tma_load_2d_pair(sb, &tmB, kb * BK, wrow0 + (int)rank * L::B_ROWS, lfull);
           } else {
             mbar_expect_tx(full0 + 8 * s, L::A_BYTES + L::B_BYTES);
-            tma_load_2d(sa, &tmA, c0, (int)(tr.row0 + tap_shift(g.taps, tap, g.W)), full0 + 8 * s);
+            if (kb >= g.taps * kchunks) tma_load_2d(sa, &tmA2, (kb - kchunks) * BK, (int)tr.row0, full0 + 8 * s);  // second operand (taps == 1)
+            else tma_load_2d(sa, &tmA, c0, (int)(tr.row0 + tap_shift(g.taps, tap, g.W)), full0 + 8 * s);
             tma_load_2d(sb, &tmB, kb * BK, wrow0, full0 + 8 * s);
           }
         }
@@ -556,10 +560,15 @@ int launch(const CrogGemm* g, cudaStream_t stream) {
     CROG_CUDA_OK(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
     attr_set = true; attr_dev = dev;
   }
-  CUtensorMap tmA, tmB, tmOut, tmRes;
-  const long long Ktot = (long long)g->taps * g->cin;
+  CUtensorMap tmA, tmA2, tmB, tmOut, tmRes;
+  const long long Ktot = (long long)g->taps * g->cin + g->cin2;
   int rc = crog_encode_2d(&tmA, g->a, CROG_BF16, (uint64_t)g->cin, (uint64_t)g->a_rows, (uint64_t)g->a_ld, L::A_ROWS);
   if (rc) return rc;
+  tmA2 = tmA;
+  if (g->a2) {
+    rc = crog_encode_2d(&tmA2, g->a2, CROG_BF16, (uint64_t)g->cin2, (uint64_t)g->a_rows, (uint64_t)g->a2_ld, L::A_ROWS);
+    if (rc) return rc;
+  }
   uint64_t wrows = (uint64_t)g->N;
   if (g->w_sample_stride > 0) wrows = (uint64_t)(g->w_sample_stride / Ktot) * (uint64_t)(g->M / g->sample_rows);
   rc = crog_encode_2d(&tmB, g->w, CROG_BF16, (uint64_t)Ktot, wrows, (uint64_t)Ktot, L::B_ROWS);
@@ -587,18 +596,18 @@ int launch(const CrogGemm* g, cudaStream_t stream) {
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
-    CROG_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, STAGES, NBUF, MODE, CONV3, EPI_WARPS, PAIR>, tmA, tmB, tmOut, tmRes, *g, n_tiles, total));
+    CROG_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, STAGES, NBUF, MODE, CONV3, EPI_WARPS, PAIR>, tmA, tmA2, tmB, tmOut, tmRes, *g, n_tiles, total));
     return CROG_OK;
   }
   const int grid = total < g_num_sms ? total : g_num_sms;
-  crog_launch(gemm_tc_kernel<BN, STAGES, NBUF, MODE, CONV3, EPI_WARPS, PAIR>, dim3(grid), dim3(L::NUM_THREADS), L::TOTAL, stream, tmA, tmB, tmOut, tmRes, *g, n_tiles, total);
+  crog_launch(gemm_tc_kernel<BN, STAGES, NBUF, MODE, CONV3, EPI_WARPS, PAIR>, dim3(grid), dim3(L::NUM_THREADS), L::TOTAL, stream, tmA, tmA2, tmB, tmOut, tmRes, *g, n_tiles, total);
   CROG_LAUNCH_OK("gemm_tc");
   return CROG_OK;
 }
 
 template <int MODE>
 int dispatch(const CrogGemm* g, cudaStream_t stream) {
-  const long long Ktot = (long long)g->taps * g->cin;
+  const long long Ktot = (long long)g->taps * g->cin + g->cin2;
   const bool conv3_ok = g->N <= 64 && g->taps == 9 && g->cin == BK && g->w_sample_stride == 0;
   const bool pair_ok = g->w_sample_stride == 0 && g->M > BM;  // shared weights, more than one CTA's worth of rows
   if (g->tile_cfg != CROG_TILE_AUTO) {
@@ -659,6 +668,12 @@ int crog_gemm_tc(const CrogGemm* g, cudaStream_t stream) {
   if (g->w_sample_stride > 0)
     CROG_REQUIRE(g->w_sample_stride % ((long long)g->taps * g->cin) == 0 && g->sample_rows > 0, CROG_E_BADSHAPE,
                  "gemm_tc: per-sample weights need whole rows");
+  if (g->a2) {
+    CROG_REQUIRE(g->taps == 1 && g->cin2 > 0 && g->cin2 % BK == 0 && g->a2_ld % 8 == 0 && aligned16(g->a2) && g->w_sample_stride == 0,
+                 CROG_E_BADSHAPE, "gemm_tc: the second activation operand needs taps == 1, cin2 a multiple of %d, shared weights", BK);
+  } else {
+    CROG_REQUIRE(g->cin2 == 0, CROG_E_BADSHAPE, "gemm_tc: cin2 without a2");
+  }
   if (g->row_stats_out || g->row_stats_in) {
     CROG_REQUIRE(g->in_padded == 0 && g->out_padded == 0 && g->out_sample_rows == 0 && g->w_sample_stride == 0, CROG_E_BADSHAPE,
                  "gemm_tc: folded LayerNorm needs the identity row mapping");

@@ -130,6 +130,9 @@ class ForwardPlan:
         self._keep_all = keep
         self._hold: List[object] = []  # keeps packed weights / descriptors alive
         self.n_launches = 0
+        # bf16 tcgen05 plans merge the last convolution of a stage's first bottleneck with its downsample branch
+        # (CROG_FUSE_DOWNSAMPLE=0: two GEMMs and an identity tensor, as in the fp32 mode)
+        self.fuse_downsample = (precision == "bf16" and gemm_impl != L.IMPL_SIMT and os.environ.get("CROG_FUSE_DOWNSAMPLE", "1") != "0")
         self._side = None
         self._ev = None
         self.gemm_flops = 0
@@ -178,10 +181,15 @@ class ForwardPlan:
              act: int = L.ACT_NONE, residual: Optional[Act] = None, residual_relu: bool = False, addmat=None,
              gate=None, scale2=None, bias2=None, w_sample_stride: int = 0, cin: Optional[int] = None,
              alg_n: Optional[int] = None, alg_cin: Optional[int] = None, out_sample_rows: int = 0, out_row0: int = 0,
-             row_stats_out: Optional[torch.Tensor] = None, row_stats_in: Optional[torch.Tensor] = None, row_stats_width: int = 0):
+             row_stats_out: Optional[torch.Tensor] = None, row_stats_in: Optional[torch.Tensor] = None, row_stats_width: int = 0,
+             a2: Optional[Act] = None):
         g = L.CrogGemm()
         cin = cin if cin is not None else a.C
-        assert w.shape[-1] == taps * cin, (name, tuple(w.shape), taps, cin)
+        cin2 = a2.C if a2 is not None else 0
+        assert w.shape[-1] == taps * cin + cin2, (name, tuple(w.shape), taps, cin, cin2)
+        if a2 is not None:  # second operand contracted after the first (two summed 1x1 convolutions as one GEMM)
+            assert taps == 1 and a2.rows == a.rows and a2.padded == a.padded and (a2.H, a2.W) == (a.H, a.W), name
+            g.a2, g.a2_ld, g.cin2 = a2.ptr, a2.ld, cin2
         g.a, g.a_rows, g.a_ld, g.cin, g.taps, g.dtype = a.ptr, a.rows, a.ld, cin, taps, self.acode
         g.M, g.sample_rows, g.H, g.W = a.rows, a.sample_rows, a.H, a.W
         g.in_padded, g.out_padded = int(a.padded), int(out.padded)
@@ -216,9 +224,9 @@ class ForwardPlan:
         self._add(name, lambda s: L.check(lib.crog_gemm(ref, s)))
         self.gemm_ops.append((name, g, self.ops[-1]))
         rows_eff = a.B * a.H * a.W if a.H > 0 else a.rows
-        self.gemm_flops += 2 * rows_eff * N * taps * cin
+        self.gemm_flops += 2 * rows_eff * N * (taps * cin + cin2)
         # algorithmic FLOPs of the reference op (no channel padding, no halo rows) for roofline accounting
-        self.gemm_alg_flops[name] = 2 * rows_eff * (alg_n or N) * taps * (alg_cin or cin)
+        self.gemm_alg_flops[name] = 2 * rows_eff * (alg_n or N) * (taps * (alg_cin or cin) + cin2)
         if self._keep_all:
             self.keep[name] = out
 
@@ -329,17 +337,28 @@ class ForwardPlan:
             self.resample(p + ".avgpool", t2, t2p, L.RS_AVGPOOL2)
             t2 = t2p
         idt = x
-        if (p + ".downsample.0.weight") in sd:
-            xi = x
-            if stride > 1:
-                xi = self.new(H // 2, W // 2, inpl)
-                self.resample(p + ".downsample.pool", x, xi, L.RS_AVGPOOL2)
+        has_ds = (p + ".downsample.0.weight") in sd
+        xi = x
+        if has_ds and stride > 1:
+            xi = self.new(H // 2, W // 2, inpl)
+            self.resample(p + ".downsample.pool", x, xi, L.RS_AVGPOOL2)
+        out = self.new(t2.H, t2.W, planes * 4)
+        if has_ds and self.fuse_downsample:
+            # out = relu(bn3(conv3(t2)) + bn_d(conv_d(xi))) as ONE contraction over [t2 | xi] (K = planes + inpl) with both
+            # BatchNorm scales folded into the bf16 weights and the two shifts summed: the identity tensor of the first block of
+            # every stage (up to 354 MB written and read back) and one epilogue pass disappear
+            s3, b3 = _bn_fold(sd, p + ".bn3")
+            s_d, b_d = _bn_fold(sd, p + ".downsample.1")
+            wcat = torch.cat([_conv_w(sd[p + ".conv3.weight"]).float() * s3[:, None],
+                              _conv_w(sd[p + ".downsample.0.weight"]).float() * s_d[:, None]], 1)
+            self.gemm(p + ".conv3+downsample", t2, self.wt(wcat), planes * 4, out, bias=self.f32(b3 + b_d), act=RELU, a2=xi)
+            return out
+        if has_ds:
             sc, bi = _bn_fold(sd, p + ".downsample.1")
             idt = self.new(xi.H, xi.W, planes * 4)
             self.gemm(p + ".downsample", xi, self.wt(_conv_w(sd[p + ".downsample.0.weight"])), planes * 4, idt,
                       scale=self.f32(sc), bias=self.f32(bi))
         sc, bi = _bn_fold(sd, p + ".bn3")
-        out = self.new(t2.H, t2.W, planes * 4)
         self.gemm(p + ".conv3", t2, self.wt(_conv_w(sd[p + ".conv3.weight"])), planes * 4, out, scale=self.f32(sc),
                   bias=self.f32(bi), residual=idt, residual_relu=True)
         return out

@@ -101,6 +101,13 @@ typedef struct CrogGemm {
      bias = c) reads them back (row_stats_in, row_stats_chunks pairs per row over row_stats_width values) and applies
      out = acc * rstd_r + (-mu_r rstd_r) * s_n + c_n.  Plain row matrices / compact layouts only (output row ==
      enumerated row). */
+  /* Second activation operand, contracted after the first along K (K = cin + cin2, weights [N, cin + cin2]): fuses two
+     1x1 convolutions that are summed, e.g. the last convolution of a bottleneck and its downsample branch
+     (model/clip.py:44-57: out = relu(bn3(conv3(t)) + bn_d(conv_d(pool(x)))) with both BatchNorm scales folded into the
+     weights).  Same row enumeration as `a`; taps == 1; tcgen05 path only. */
+  const void* a2;
+  int32_t a2_ld;
+  int32_t cin2;
   float* row_stats_out;
   const float* row_stats_in;
   int32_t row_stats_chunks;
