@@ -368,10 +368,13 @@ class ForwardPlan:
         sd, a = self.sd, "backbone.visual.attnpool"
         H, W, E = x4.H, x4.W, x4.C
         T = H * W
+        fuse = self.fuse_downsample  # same trick as the bottlenecks: c_proj(att) + connect(x4) as one GEMM over [att | x4]
         sc, bi = _bn_fold(sd, a + ".connect.1")
-        res = self.new(H, W, 1024)
-        self.gemm(a + ".connect", x4, self.wt(_conv_w(sd[a + ".connect.0.weight"])), 1024, res, scale=self.f32(sc),
-                  bias=self.f32(bi))
+        res = None
+        if not fuse:
+            res = self.new(H, W, 1024)
+            self.gemm(a + ".connect", x4, self.wt(_conv_w(sd[a + ".connect.0.weight"])), 1024, res, scale=self.f32(sc),
+                      bias=self.f32(bi))
         pe = sd[a + ".positional_embedding"].float()
         g = int(round(math.sqrt(pe.shape[0] - 1)))
         pe = pe[1:].reshape(1, g, g, E).permute(0, 3, 1, 2)
@@ -386,8 +389,13 @@ class ForwardPlan:
         att = self.new(0, 0, E, rows=self.B * T)
         self.attention(a + ".attn", qkv.cols(0, E), qkv.cols(E, 2 * E), qkv.cols(2 * E, 3 * E), att, E // 64, T, T)
         c5 = self.new(H, W, 1024)
-        self.gemm(a + ".c_proj", Act(att.t, self.B, H, W, False, E), self.wt(sd[a + ".c_proj.weight"].float()), 1024, c5,
-                  bias=self.f32(sd[a + ".c_proj.bias"]), residual=res, residual_relu=True)
+        if fuse:
+            wcat = torch.cat([sd[a + ".c_proj.weight"].float(), _conv_w(sd[a + ".connect.0.weight"]).float() * sc[:, None]], 1)
+            self.gemm(a + ".c_proj+connect", Act(att.t, self.B, H, W, False, E), self.wt(wcat), 1024, c5,
+                      bias=self.f32(sd[a + ".c_proj.bias"].float() + bi), act=L.ACT_RELU, a2=x4)
+        else:
+            self.gemm(a + ".c_proj", Act(att.t, self.B, H, W, False, E), self.wt(sd[a + ".c_proj.weight"].float()), 1024, c5,
+                      bias=self.f32(sd[a + ".c_proj.bias"]), residual=res, residual_relu=True)
         return c5
 
     def _text(self):

@@ -1,7 +1,5 @@
 mkdir -p gpurun_out
-CROG_FUSE_DOWNSAMPLE=0 python scripts/bf16_err.py 2>&1 | tail -1
-CROG_FUSE_DOWNSAMPLE=1 python scripts/bf16_err.py 2>&1 | tail -1
+python scripts/bf16_err.py 2>&1 | tail -1
 timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
-CROG_FUSE_DOWNSAMPLE=0 python bench.py --steps 30 --no-cpu-baseline --no-e2e > gpurun_out/b0.json 2> gpurun_out/b0.err; python -c "import sys,json; d=json.loads(open('gpurun_out/b0.json').read().strip().splitlines()[-1]); print('unfused', d['value'], d['ms_per_step'], d['roofline']['achieved'], d['clocks']['sm_mhz'])"
 python bench.py --steps 30 --no-cpu-baseline --no-e2e --dump-ops gpurun_out/ops_tuned.txt > gpurun_out/b.json 2> gpurun_out/b.err; python -c "import sys,json; d=json.loads(open('gpurun_out/b.json').read().strip().splitlines()[-1]); print('fused  ', d['value'], d['ms_per_step'], d['roofline']['achieved'], d['clocks']['sm_mhz'])"
-grep -E "downsample" gpurun_out/ops_tuned.txt
+grep -E "attnpool" gpurun_out/ops_tuned.txt

@@ -627,3 +627,32 @@ def test_layernorm_folded_into_gemm():
     ea, eb = relerr(out_a - res, want - res), relerr(out_b - res, want - res)
     assert ea < 1e-2 and eb < 1e-2, (ea, eb)
     assert eb < 1.5 * ea + 1e-3, (ea, eb)  # the fold is as accurate as the separate LayerNorm pass
+
+
+def test_gemm_second_operand_equals_two_gemms():
+    """CrogGemm.a2: out = act([a | a2] [w1 | w2]^T + b) in one launch against the two contractions done separately in fp32
+    (the fused conv3 + downsample of a bottleneck, clip.py:44-57), for a single-CTA and a CTA-pair configuration."""
+    torch.manual_seed(17)
+    M, K1, K2, N = 2704 * 2 + 37, 128, 512, 512
+    dt = torch.bfloat16
+    a1 = (torch.randn(M, K1, device=DEV) * 0.5).to(dt)
+    a2 = (torch.randn(M, K2, device=DEV) * 0.5).to(dt)
+    w = (torch.randn(N, K1 + K2, device=DEV) * (K1 + K2) ** -0.5).to(dt)
+    b = torch.randn(N, device=DEV)
+    want = torch.relu(a1.float() @ w[:, :K1].float().t() + a2.float() @ w[:, K1:].float().t() + b)
+    outs = []
+    for cfg in (L.TILE_AUTO, L.TILE_128x128, L.TILE_PAIR_256x256_E8, L.TILE_128x64):
+        out = torch.zeros(M, N, device=DEV, dtype=dt)
+        g = L.CrogGemm()
+        g.a, g.a_rows, g.a_ld, g.cin, g.taps, g.dtype, g.M = a1.data_ptr(), M, K1, K1, 1, L.BF16, M
+        g.a2, g.a2_ld, g.cin2 = a2.data_ptr(), K2, K2
+        g.w, g.N, g.bias, g.act = w.data_ptr(), N, b.data_ptr(), L.ACT_RELU
+        g.out, g.out_ld, g.out_dtype, g.impl, g.tile_cfg = out.data_ptr(), N, L.BF16, L.IMPL_TCGEN05, cfg
+        L.check(L.lib().crog_gemm(C.byref(g), L.stream_ptr()))
+        torch.cuda.synchronize()
+        assert relerr(out, want) < 4e-3, cfg
+        outs.append(out)
+    assert all(torch.equal(outs[0], o) for o in outs[1:])
+    g.impl = L.IMPL_SIMT  # the CUDA-core path does not implement it and must say so
+    with pytest.raises(L.CrogError):
+        L.check(L.lib().crog_gemm(C.byref(g), L.stream_ptr()))
