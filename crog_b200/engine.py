@@ -103,7 +103,8 @@ class GraspEvaluator:
         Two device staging slots are filled on a copy stream: while batch k runs on the compute stream, batch k+1 is
         already crossing PCIe.  For every batch the decoded grasps / peak counts / J flags are copied back and the
         host waits for them (the caller reads the result of every step); yields ``(n_peaks, grasps, j_flags)`` as
-        pinned CPU tensors that stay valid until the next-but-one iteration."""
+        pinned CPU tensors that stay valid until the next-but-one iteration.  The launches of batch k+1 are enqueued
+        before the host blocks on the results of batch k, so the GPU does not idle while the host hands a result over."""
         dev = self.counters.device
         main = torch.cuda.current_stream(dev)
         if getattr(self, "_copy_stream", None) is None:
@@ -111,8 +112,8 @@ class GraspEvaluator:
             self._slots = [None, None]
             self._ready = [torch.cuda.Event(), torch.cuda.Event()]
             self._free = [torch.cuda.Event(), torch.cuda.Event()]
-            self._done = [torch.cuda.Event(), torch.cuda.Event()]
-            self._hout = [None, None]
+            self._done = [torch.cuda.Event(), torch.cuda.Event(), torch.cuda.Event()]
+            self._hout = [None, None, None]
         it = iter(host_batches)
 
         def prefetch(k):
@@ -132,6 +133,7 @@ class GraspEvaluator:
             return True
 
         k, more = 0, prefetch(0)
+        pending = None  # result slot of the batch whose launches are enqueued but whose results are not handed over yet
         while more:
             s = k & 1
             more = prefetch(k + 1)
@@ -139,14 +141,20 @@ class GraspEvaluator:
             img, word, gt, cnt = self._slots[s]
             _, _, n, grasps, flags = self.step(img, word, gt, cnt)
             self._free[s].record(main)
-            if self._hout[s] is None or self._hout[s][1].shape != grasps.shape:
-                self._hout[s] = [torch.empty(t.shape, dtype=t.dtype).pin_memory() for t in (n, grasps, flags)]
-            for h, d in zip(self._hout[s], (n, grasps, flags)):
+            r = k % 3
+            if self._hout[r] is None or self._hout[r][1].shape != grasps.shape:
+                self._hout[r] = [torch.empty(t.shape, dtype=t.dtype).pin_memory() for t in (n, grasps, flags)]
+            for h, d in zip(self._hout[r], (n, grasps, flags)):
                 h.copy_(d, non_blocking=True)
-            self._done[s].record(main)
-            self._done[s].synchronize()
-            yield tuple(self._hout[s])
+            self._done[r].record(main)
+            if pending is not None:
+                self._done[pending].synchronize()
+                yield tuple(self._hout[pending])
+            pending = r
             k += 1
+        if pending is not None:
+            self._done[pending].synchronize()
+            yield tuple(self._hout[pending])
 
     def reduce(self) -> torch.Tensor:
         import torch.distributed as dist
