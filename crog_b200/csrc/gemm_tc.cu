@@ -60,7 +60,8 @@ struct Cfg {
   static constexpr int BRES_OFF = STAGES * STAGE_BYTES;
   static constexpr int STG_OFF = BRES_OFF + BRES_BYTES;
   static constexpr int BAR_OFF = STG_OFF + EPI_WARPS * STG_WARP;
-  static constexpr int NBARS = 2 * STAGES + 5 + EPI_WARPS * NBUF;  // full[S], empty[S], tfull[2], tempty[2], bres, res[8][NBUF]
+  static constexpr int NACC = EPI_WARPS / 4 < 2 ? 2 : EPI_WARPS / 4;  // TMEM accumulator buffers: one per epilogue group, at least two
+  static constexpr int NBARS = 2 * STAGES + 2 * NACC + 1 + EPI_WARPS * NBUF;  // full[S], empty[S], tfull[NACC], tempty[NACC], bres, res[EPI][NBUF]
   // per epilogue group: this tile's scale / bias slice, double buffered by tile parity ([2][scale | bias][BN] floats);
   // configurations whose operand ring leaves no room for it (long contractions, where the epilogue hides under the
   // mainloop anyway) keep reading scale / bias through the read-only cache
@@ -68,7 +69,8 @@ struct Cfg {
   static constexpr int SB_OFF = ((BAR_OFF + NBARS * 8 + 16 + 15) / 16) * 16;
   static constexpr bool SB = SB_OFF + SB_BYTES + 1024 <= 227 * 1024;
   static constexpr int TOTAL = SB ? SB_OFF + SB_BYTES + 1024 : BAR_OFF + NBARS * 8 + 16 + 1024;   // + tmem slot + alignment slack
-  static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
+  static constexpr int TMEM_COLS = NACC * BN <= 32 ? 32 : (NACC * BN <= 64 ? 64 : (NACC * BN <= 128 ? 128 : (NACC * BN <= 256 ? 256 : 512)));
+  static_assert(NACC * BN <= 512, "accumulator buffers exceed the 512 TMEM columns");
   static_assert(NBUF >= 2 && STG_WARP >= 32 * PITCH, "staging too small");
 };
 
@@ -99,8 +101,8 @@ __global__ void __launch_bounds__(64 + EPI_WARPS * 32, 1) gemm_tc_kernel(const _
   const int kchunks = g.cin / BK;
   const int num_kb = CONV3 ? 3 : g.taps * kchunks + g.cin2 / BK;  // CONV3: one k-block per ky band; a2: its chunks follow a's
   const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + STAGES), tfull0 = smem_u32(bars + 2 * STAGES),
-                 tempty0 = smem_u32(bars + 2 * STAGES + 2), bres = smem_u32(bars + 2 * STAGES + 4),
-                 res0 = smem_u32(bars + 2 * STAGES + 5);
+                 tempty0 = smem_u32(bars + 2 * STAGES + L::NACC), bres = smem_u32(bars + 2 * STAGES + 2 * L::NACC),
+                 res0 = smem_u32(bars + 2 * STAGES + 2 * L::NACC + 1);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -112,7 +114,7 @@ __global__ void __launch_bounds__(64 + EPI_WARPS * 32, 1) gemm_tc_kernel(const _
     }
     // pair: the leader's full barrier collects one arrive(+expect_tx) per CTA, its tempty the epilogue threads of both
     for (int s = 0; s < STAGES; ++s) { mbar_init(full0 + 8 * s, PAIR ? 2 : 1); mbar_init(empty0 + 8 * s, 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(tfull0 + 8 * s, 1); mbar_init(tempty0 + 8 * s, (PAIR ? 2 : 1) * 4 * 32); }
+    for (int s = 0; s < L::NACC; ++s) { mbar_init(tfull0 + 8 * s, 1); mbar_init(tempty0 + 8 * s, (PAIR ? 2 : 1) * 4 * 32); }
     for (int s = 0; s < EPI_WARPS * NBUF; ++s) mbar_init(res0 + 8 * s, 1);
     mbar_init(bres, 1);
     fence_barrier_init();
@@ -176,8 +178,8 @@ __global__ void __launch_bounds__(64 + EPI_WARPS * 32, 1) gemm_tc_kernel(const _
       int kbg = 0, i = 0;
       if constexpr (CONV3) mbar_wait(bres, 0);
       for (int tile = tile0; tile < total_tiles; tile += tstep, ++i) {
-        const int as = i & 1;
-        mbar_wait(tempty0 + 8 * as, ((i >> 1) & 1) ^ 1);  // epilogue group `as` has drained this accumulator buffer
+        const int as = i % L::NACC;
+        mbar_wait(tempty0 + 8 * as, ((i / L::NACC) & 1) ^ 1);  // epilogue group `as` has drained this accumulator buffer
         tc_fence_after();
         const uint32_t tacc = tmem_base + as * BN;
         if constexpr (CONV3) {
@@ -247,7 +249,8 @@ __global__ void __launch_bounds__(64 + EPI_WARPS * 32, 1) gemm_tc_kernel(const _
         for (int u = 0; u < (2 * BN + 127) / 128; ++u)
           if (gt + u * 128 < 2 * BN) sbt[gt + u * 128] = v[u];
         if (grp == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
-        else asm volatile("bar.sync 2, 128;" ::: "memory");
+        else if (grp == 1) asm volatile("bar.sync 2, 128;" ::: "memory");
+        else asm volatile("bar.sync 3, 128;" ::: "memory");
       } else {
         mbar_wait(tfull_bar, tfull_parity);
       }
@@ -292,13 +295,13 @@ __global__ void __launch_bounds__(64 + EPI_WARPS * 32, 1) gemm_tc_kernel(const _
       for (int i = grp;; i += GROUPS) {
         const int tile = tile0 + i * tstep;
         if (tile >= total_tiles) break;
-        const int buf = i & 1;
+        const int buf = i % L::NACC;
         const uint32_t tfull = tfull0 + 8 * buf, tempty = tempty0 + 8 * buf;
         const int n0 = (tile % n_tiles) * BN, row0 = (tile / n_tiles) * MT + (int)rank * BM;
         RowMap m = map_row(g, (long long)row0 + q * 32 + lane, g.M);
         load_row_stats(g, m);
         const int nvc = min(NCH, (g.N - n0 + CW - 1) / CW);  // chunks with at least one real column
-        const float* sbt = stage_scale_bias(i / GROUPS, n0, tfull, (i >> 1) & 1);
+        const float* sbt = stage_scale_bias(i / GROUPS, n0, tfull, (i / L::NACC) & 1);
         tc_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN;
         for (int c = 0; c < nvc; ++c) {
@@ -422,7 +425,7 @@ __global__ void __launch_bounds__(64 + EPI_WARPS * 32, 1) gemm_tc_kernel(const _
       for (int i = grp;; i += GROUPS) {
         const int tile = tile0 + i * tstep;
         if (tile >= total_tiles) break;
-        const int buf = i & 1;
+        const int buf = i % L::NACC;
         const uint32_t tfull = tfull0 + 8 * buf, tempty = tempty0 + 8 * buf;
         const int n_t = tile % n_tiles, m_t = tile / n_tiles;
         TileRows tr = tile_rows(g, m_t, MT);
@@ -435,7 +438,7 @@ __global__ void __launch_bounds__(64 + EPI_WARPS * 32, 1) gemm_tc_kernel(const _
 #pragma unroll
         for (int p = 0; p < PASSES; ++p) orow[p] = __shfl_sync(0xffffffffu, my_orow, p * RPP + rsub);
         const int nvs = min(NSUB, (g.N - n0 + SUB - 1) / SUB);
-        const float* sbt = stage_scale_bias(i / GROUPS, n0, tfull, (i >> 1) & 1);
+        const float* sbt = stage_scale_bias(i / GROUPS, n0, tfull, (i / L::NACC) & 1);
         tc_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN;
         for (int sbi = 0; sbi < nvs; ++sbi) {
@@ -631,6 +634,7 @@ int dispatch(const CrogGemm* g, cudaStream_t stream) {
         return launch<128, 6, 2, MODE, false, 8, true>(g, stream);
       case CROG_TILE_128x64: return launch<64, 5, 3, MODE>(g, stream);
       case CROG_TILE_128x128_S3: return launch<128, 3, 3, MODE>(g, stream);
+      case CROG_TILE_128x128_E12: return launch<128, 3, 2, MODE, false, 12>(g, stream);
       case CROG_TILE_CONV3:
         CROG_REQUIRE(conv3_ok, CROG_E_BADSHAPE, "gemm_tc: CONV3 tiles need a shared 3x3 kernel with cin == 64 and N <= 64");
         return launch<64, 5, 2, MODE, true>(g, stream);

@@ -652,7 +652,7 @@ class ForwardPlan:
                 g.tile_cfg = L.TILE_AUTO
                 base = clock(fn)
                 best_cfg, best_us = L.TILE_AUTO, base
-                for cfg_id in range(1, L.TILE_COUNT):
+                for cfg_id in range(1, min(L.TILE_COUNT, int(os.environ.get("CROG_AUTOTUNE_MAX_CFG", L.TILE_COUNT - 1)) + 1)):
                     g.tile_cfg = cfg_id
                     if lib.crog_gemm(C.byref(g), s) != 0:
                         continue  # configuration does not apply to this shape

@@ -127,7 +127,9 @@ enum {
   CROG_TILE_128x128_S3 = 9,     /* one CTA, 128 x 128 tiles, 3 operand stages, two epilogue groups, scale / bias of the tile
                                    staged in shared memory (the 4-stage ring of CROG_TILE_128x128 leaves no room for it):
                                    the default for short contractions, where the epilogue is the pace */
-  CROG_TILE_COUNT = 10
+  CROG_TILE_128x128_E12 = 10,   /* one CTA, 128 x 128 tiles, 3 stages, THREE epilogue groups (12 warps, three TMEM accumulators,
+                                   2 staging buffers per warp): more warps per scheduler for epilogue-bound layers */
+  CROG_TILE_COUNT = 11
 };
 int crog_gemm(const CrogGemm* g, void* stream);
 
