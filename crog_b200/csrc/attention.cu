@@ -116,6 +116,89 @@ __global__ void __launch_bounds__(QB) attention_kernel(const T* __restrict__ q, 
   }
 }
 
+
+// Small attention (text tower: L <= 77 queries and keys, 8 heads; clip.py:258-262): one CTA per (sample, head), every
+// score and every output element computed by its own thread instead of one thread walking a whole query row
+// (the streaming kernel above keeps 17 of 128 threads busy for ~2700 dependent instructions at L = 17: 41 us per layer,
+// a third of the text tower).  Phase 1: S[i][j] = scale q_i . k_j for all visible pairs; phase 2: row softmax by one
+// warp per row; phase 3: o[i][d..d+3] = sum_j P[i][j] v[j][d..d+3].  fp32 throughout; K rows padded against bank conflicts.
+constexpr int SM_T = 96;      // max tokens
+constexpr int SM_KP = HD + 4;  // padded K row (floats)
+template <typename T>
+__global__ void __launch_bounds__(256) attention_small_kernel(const T* __restrict__ q, int ldq, const T* __restrict__ k, int ldk,
+                                                              const T* __restrict__ v, int ldv, T* __restrict__ o, int ldo, int Tq,
+                                                              int Tk, float scale, int causal, const int64_t* __restrict__ pad_word) {
+  extern __shared__ __align__(16) float sm[];
+  float* Qs = sm;                          // [Tq][HD]
+  float* Ks = Qs + Tq * HD;                // [Tk][SM_KP]
+  float* Vs = Ks + Tk * SM_KP;             // [Tk][HD]
+  float* Ss = Vs + Tk * HD;                // [Tq][Tk + 1]
+  pdl_launch();
+  pdl_wait();
+  const int b = blockIdx.y, h = blockIdx.x, tid = threadIdx.x, SP = Tk + 1;
+  for (int i = tid; i < Tq * (HD / 8); i += 256) {
+    const int r = i / (HD / 8), d8 = (i % (HD / 8)) * 8;
+    float t[8];
+    load8(q + ((long long)b * Tq + r) * ldq + h * HD + d8, t);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) Qs[r * HD + d8 + j] = t[j] * scale;
+  }
+  for (int i = tid; i < Tk * (HD / 8); i += 256) {
+    const int r = i / (HD / 8), d8 = (i % (HD / 8)) * 8;
+    float tk[8], tv[8];
+    load8(k + ((long long)b * Tk + r) * ldk + h * HD + d8, tk);
+    load8(v + ((long long)b * Tk + r) * ldv + h * HD + d8, tv);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { Ks[r * SM_KP + d8 + j] = tk[j]; Vs[r * HD + d8 + j] = tv[j]; }
+  }
+  __syncthreads();
+  for (int p = tid; p < Tq * Tk; p += 256) {
+    const int i = p / Tk, j = p - i * Tk;
+    const bool dead = (causal && j > i) || (pad_word && pad_word[(long long)b * Tk + j] == 0);
+    float d0 = 0.f, d1 = 0.f;
+    if (!dead) {
+      const float4* qa = reinterpret_cast<const float4*>(Qs + i * HD);
+      const float4* ka = reinterpret_cast<const float4*>(Ks + j * SM_KP);
+#pragma unroll
+      for (int d = 0; d < HD / 4; d += 2) {
+        const float4 a = qa[d], c = ka[d], a2 = qa[d + 1], c2 = ka[d + 1];
+        d0 = fmaf(a.x, c.x, d0); d1 = fmaf(a.y, c.y, d1); d0 = fmaf(a.z, c.z, d0); d1 = fmaf(a.w, c.w, d1);
+        d0 = fmaf(a2.x, c2.x, d0); d1 = fmaf(a2.y, c2.y, d1); d0 = fmaf(a2.z, c2.z, d0); d1 = fmaf(a2.w, c2.w, d1);
+      }
+    }
+    Ss[i * SP + j] = dead ? -INFINITY : d0 + d1;
+  }
+  __syncthreads();
+  for (int i = tid >> 5; i < Tq; i += 8) {  // one warp per row
+    const int lane = tid & 31;
+    float m = -INFINITY;
+    for (int j = lane; j < Tk; j += 32) m = fmaxf(m, Ss[i * SP + j]);
+    m = warp_max(m);
+    float sum = 0.f;
+    for (int j = lane; j < Tk; j += 32) {
+      const float pj = __expf(Ss[i * SP + j] - m);  // -inf -> 0
+      Ss[i * SP + j] = pj;
+      sum += pj;
+    }
+    sum = warp_sum(sum);
+    if (lane == 0) Ss[i * SP + Tk] = 1.f / sum;
+  }
+  __syncthreads();
+  for (int p = tid; p < Tq * (HD / 4); p += 256) {
+    const int i = p / (HD / 4), d4 = (p % (HD / 4)) * 4;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int jn = causal ? min(Tk, i + 1) : Tk;
+    for (int j = 0; j < jn; ++j) {
+      const float pj = Ss[i * SP + j];
+      const float4 vv = *reinterpret_cast<const float4*>(Vs + j * HD + d4);
+      acc.x = fmaf(pj, vv.x, acc.x); acc.y = fmaf(pj, vv.y, acc.y); acc.z = fmaf(pj, vv.z, acc.z); acc.w = fmaf(pj, vv.w, acc.w);
+    }
+    const float inv = Ss[i * SP + Tk];
+    T* op = o + ((long long)b * Tq + i) * ldo + h * HD + d4;
+    store4(op, acc.x * inv, acc.y * inv, acc.z * inv, acc.w * inv);
+  }
+}
+
 }  // namespace
 
 int crog_attention_tc(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, void* o, int ldo, int B, int heads,
@@ -134,6 +217,23 @@ extern "C" int crog_attention(const void* q, int32_t ldq, const void* k, int32_t
   // query on CUDA cores).  The causal text attention (L <= 77 queries) stays on CUDA cores.
   if (dtype == CROG_BF16 && !causal && (Tk >= 128 || (Tq >= 128 && !getenv("CROG_ATTN_CROSS_SIMT"))))
     return crog_attention_tc(q, ldq, k, ldk, v, ldv, o, ldo, B, heads, Tq, Tk, scale, (const int64_t*)pad_word, s);
+  if (Tq <= SM_T && Tk <= SM_T && !getenv("CROG_ATTN_NO_SMALL")) {  // text tower (and any other short sequence)
+    const size_t smem = ((size_t)Tq * HD + (size_t)Tk * SM_KP + (size_t)Tk * HD + (size_t)Tq * (Tk + 1)) * sizeof(float);
+    static bool attr = false;
+    if (!attr) {
+      const int mx = (SM_T * HD + SM_T * SM_KP + SM_T * HD + SM_T * (SM_T + 1)) * (int)sizeof(float);
+      CROG_CUDA_OK(cudaFuncSetAttribute(attention_small_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+      CROG_CUDA_OK(cudaFuncSetAttribute(attention_small_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+      attr = true;
+    }
+    dim3 g2(heads, B);
+    if (dtype == CROG_F32)
+      crog_launch(attention_small_kernel<float>, g2, dim3(256), smem, s, (const float*)q, ldq, (const float*)k, ldk, (const float*)v, ldv, (float*)o, ldo, Tq, Tk, scale, causal, pad_word);
+    else
+      crog_launch(attention_small_kernel<bf16>, g2, dim3(256), smem, s, (const bf16*)q, ldq, (const bf16*)k, ldk, (const bf16*)v, ldv, (bf16*)o, ldo, Tq, Tk, scale, causal, pad_word);
+    CROG_LAUNCH_OK("attention_small");
+    return CROG_OK;
+  }
   dim3 grid((Tq + QB - 1) / QB, heads, B);
   if (dtype == CROG_F32)
     crog_launch(attention_kernel<float>, grid, dim3(QB), 0, s, (const float*)q, ldq, (const float*)k, ldk, (const float*)v, ldv, (float*)o, ldo, Tq, Tk, scale, causal, pad_word);
