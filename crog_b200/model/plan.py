@@ -124,6 +124,8 @@ class ForwardPlan:
         self.acode = L.dtype_code(self.adt)
         self.impl = gemm_impl
         self.ops: List[Callable[[int], None]] = []
+        self.op_side: set = set()
+        self.op_after: Dict[int, List[int]] = {}
         self.op_names: List[str] = []
         self.op_launches: List[int] = []  # kernel launches per recorded op (profiles/launch_list.py joins ncu rows on it)
         self.keep: Dict[str, Act] = {}
@@ -132,8 +134,11 @@ class ForwardPlan:
         self.n_launches = 0
         # bf16 tcgen05 plans merge the last convolution of a stage's first bottleneck with its downsample branch
         # (CROG_FUSE_DOWNSAMPLE=0: two GEMMs and an identity tensor, as in the fp32 mode)
+        self.side_helpers = os.environ.get("CROG_SIDE_HELPERS", "1") != "0"
         self.fuse_downsample = (precision == "bf16" and gemm_impl != L.IMPL_SIMT and os.environ.get("CROG_FUSE_DOWNSAMPLE", "1") != "0")
         self._side = None
+        self._side2 = None
+        self._sev = {}
         self._ev = None
         self.gemm_flops = 0
         self.gemm_alg_flops: Dict[str, int] = {}
@@ -170,11 +175,20 @@ class ForwardPlan:
         self._hold.append(t)
         return t
 
-    def _add(self, name: str, fn: Callable[[int], None], launches: int = 1):
+    def _add(self, name: str, fn: Callable[[int], None], launches: int = 1, side: bool = False, after: Optional[List[int]] = None) -> int:
+        """Record one op; returns its index.  side=True: a small memory-bound helper (pooling / layout copy) off the critical
+        path - run() launches it on a second side stream, where it shares the SMs with the tensor-core kernels of the main
+        stream (it needs no shared memory); after=[indices]: side ops whose results this op reads."""
         self.ops.append(fn)
         self.op_names.append(name)
         self.op_launches.append(launches)
         self.n_launches += launches
+        idx = len(self.ops) - 1
+        if side:
+            self.op_side.add(idx)
+        if after:
+            self.op_after[idx] = list(after)
+        return idx
 
     # ------------------------------------------------------------------ op recorders
     def gemm(self, name: str, a: Act, w: torch.Tensor, N: int, out: Act, taps: int = 1, scale=None, bias=None,
@@ -182,7 +196,7 @@ class ForwardPlan:
              gate=None, scale2=None, bias2=None, w_sample_stride: int = 0, cin: Optional[int] = None,
              alg_n: Optional[int] = None, alg_cin: Optional[int] = None, out_sample_rows: int = 0, out_row0: int = 0,
              row_stats_out: Optional[torch.Tensor] = None, row_stats_in: Optional[torch.Tensor] = None, row_stats_width: int = 0,
-             a2: Optional[Act] = None):
+             a2: Optional[Act] = None, after: Optional[List[int]] = None):
         g = L.CrogGemm()
         cin = cin if cin is not None else a.C
         cin2 = a2.C if a2 is not None else 0
@@ -221,7 +235,7 @@ class ForwardPlan:
         self._hold.extend([g, w, scale, bias, addmat, gate, scale2, bias2])
         lib = self.lib
         ref = C.byref(g)
-        self._add(name, lambda s: L.check(lib.crog_gemm(ref, s)))
+        self._add(name, lambda s: L.check(lib.crog_gemm(ref, s)), after=after)
         self.gemm_ops.append((name, g, self.ops[-1]))
         rows_eff = a.B * a.H * a.W if a.H > 0 else a.rows
         self.gemm_flops += 2 * rows_eff * N * (taps * cin + cin2)
@@ -230,13 +244,14 @@ class ForwardPlan:
         if self._keep_all:
             self.keep[name] = out
 
-    def resample(self, name: str, src: Act, dst: Act, mode: int):
+    def resample(self, name: str, src: Act, dst: Act, mode: int, side: bool = False) -> int:
         lib, code = self.lib, L.dtype_code(src.t.dtype)
         assert src.t.dtype == dst.t.dtype
         a = (src.ptr, src.ld, int(src.padded), dst.ptr, dst.ld, int(dst.padded), src.B, src.H, src.W, src.C, mode, code)
-        self._add(name, lambda s: L.check(lib.crog_resample(*a, s)))
+        idx = self._add(name, lambda s: L.check(lib.crog_resample(*a, s)), side=side and self.side_helpers)
         if self._keep_all:
             self.keep[name] = dst
+        return idx
 
     def layernorm(self, name: str, x: Act, p: str, out: Act, residual: Optional[Act] = None):
         lib = self.lib
@@ -305,6 +320,14 @@ class ForwardPlan:
                 inpl = planes * 4
             feats.append(x)
             self.keep[f"layer{li}"] = x
+            # zero-haloed copies of C3 / C4 for the 3x3 convolutions of the neck: produced on the helper stream as soon
+            # as the stage is done, under the tensor-core work of the following stages
+            if li == 2:
+                self._c3p = self.new(x.H, x.W, x.C, padded=True)
+                self._c3p_idx = self.resample("neck.c3_pad", x, self._c3p, L.RS_COPY, side=True)
+            if li == 3:
+                self._c4p = self.new(x.H, x.W, x.C, padded=True)
+                self._c4p_idx = self.resample("neck.c4_pad", x, self._c4p, L.RS_COPY, side=True)
         c3, c4, x4 = feats[1], feats[2], feats[3]
         c5 = self._attnpool(x4)
         self.keep.update(c3=c3, c4=c4, c5=c5)
@@ -324,6 +347,14 @@ class ForwardPlan:
     def _bottleneck(self, p: str, x: Act, inpl: int, planes: int, stride: int) -> Act:
         sd, RELU = self.sd, L.ACT_RELU
         H, W = x.H, x.W
+        # the pooled input of the downsample branch is only needed by the last GEMM of the block: it is produced on the
+        # helper stream while conv1 / conv2 run
+        has_ds = (p + ".downsample.0.weight") in sd
+        xi, pool_idx = x, None
+        if has_ds and stride > 1:
+            xi = self.new(H // 2, W // 2, inpl)
+            pool_idx = self.resample(p + ".downsample.pool", x, xi, L.RS_AVGPOOL2, side=True)
+        dep = [pool_idx] if pool_idx is not None else None
         sc, bi = _bn_fold(sd, p + ".bn1")
         t1 = self.new(H, W, planes, padded=True)
         self.gemm(p + ".conv1", x, self.wt(_conv_w(sd[p + ".conv1.weight"])), planes, t1, scale=self.f32(sc),
@@ -337,11 +368,6 @@ class ForwardPlan:
             self.resample(p + ".avgpool", t2, t2p, L.RS_AVGPOOL2)
             t2 = t2p
         idt = x
-        has_ds = (p + ".downsample.0.weight") in sd
-        xi = x
-        if has_ds and stride > 1:
-            xi = self.new(H // 2, W // 2, inpl)
-            self.resample(p + ".downsample.pool", x, xi, L.RS_AVGPOOL2)
         out = self.new(t2.H, t2.W, planes * 4)
         if has_ds and self.fuse_downsample:
             # out = relu(bn3(conv3(t2)) + bn_d(conv_d(xi))) as ONE contraction over [t2 | xi] (K = planes + inpl) with both
@@ -351,13 +377,13 @@ class ForwardPlan:
             s_d, b_d = _bn_fold(sd, p + ".downsample.1")
             wcat = torch.cat([_conv_w(sd[p + ".conv3.weight"]).float() * s3[:, None],
                               _conv_w(sd[p + ".downsample.0.weight"]).float() * s_d[:, None]], 1)
-            self.gemm(p + ".conv3+downsample", t2, self.wt(wcat), planes * 4, out, bias=self.f32(b3 + b_d), act=RELU, a2=xi)
+            self.gemm(p + ".conv3+downsample", t2, self.wt(wcat), planes * 4, out, bias=self.f32(b3 + b_d), act=RELU, a2=xi, after=dep)
             return out
         if has_ds:
             sc, bi = _bn_fold(sd, p + ".downsample.1")
             idt = self.new(xi.H, xi.W, planes * 4)
             self.gemm(p + ".downsample", xi, self.wt(_conv_w(sd[p + ".downsample.0.weight"])), planes * 4, idt,
-                      scale=self.f32(sc), bias=self.f32(bi))
+                      scale=self.f32(sc), bias=self.f32(bi), after=dep)
         sc, bi = _bn_fold(sd, p + ".bn3")
         self.gemm(p + ".conv3", t2, self.wt(_conv_w(sd[p + ".conv3.weight"])), planes * 4, out, scale=self.f32(sc),
                   bias=self.f32(bi), residual=idt, residual_relu=True)
@@ -468,18 +494,16 @@ class ForwardPlan:
         f5 = self.new(c5.H, c5.W, fo[2], padded=True)
         self._cbr("neck.f1_v_proj", "neck.f1_v_proj", c5, f5, 1, gate=gate.t, scale2=self.f32(s2), bias2=self.f32(b2))
         H4, W4 = c4.H, c4.W
-        c4p = self.new(H4, W4, c4.C, padded=True)
-        self.resample("neck.c4_pad", c4, c4p, L.RS_COPY)
+        c4p = self._c4p
         cat4 = self.new(H4, W4, fo[1] + fo[2])
-        self._cbr("neck.f2_v_proj", "neck.f2_v_proj", c4p, cat4.cols(0, fo[1]), 9)
+        self._cbr("neck.f2_v_proj", "neck.f2_v_proj", c4p, cat4.cols(0, fo[1]), 9, after=[self._c4p_idx])
         self.resample("neck.f5_up", f5, cat4.cols(fo[1], fo[1] + fo[2]), L.RS_BILINEAR2)
         cat3 = self.new(H4, W4, fo[0] + fo[1])
         f4 = cat3.cols(fo[0], fo[0] + fo[1])
         self._cbr("neck.f2_cat", "neck.f2_cat", cat4, f4, 1)
-        c3p = self.new(c3.H, c3.W, c3.C, padded=True)
-        self.resample("neck.c3_pad", c3, c3p, L.RS_COPY)
+        c3p = self._c3p
         t3 = self.new(c3.H, c3.W, fo[0])
-        self._cbr("neck.f3_v_proj", "neck.f3_v_proj", c3p, t3, 9)
+        self._cbr("neck.f3_v_proj", "neck.f3_v_proj", c3p, t3, 9, after=[self._c3p_idx])
         self.resample("neck.f3_pool", t3, cat3.cols(0, fo[0]), L.RS_AVGPOOL2)
         f3p = self.new(H4, W4, fo[1], padded=True)
         self._cbr("neck.f3_cat", "neck.f3_cat", cat3, f3p, 1)
@@ -691,18 +715,32 @@ class ForwardPlan:
         main = torch.cuda.current_stream()
         if self._side is None:
             self._side = torch.cuda.Stream(device=self.dev)
+            self._side2 = torch.cuda.Stream(device=self.dev)
             self._ev = (torch.cuda.Event(), torch.cuda.Event())
+            self._sev = {i: (torch.cuda.Event(), torch.cuda.Event()) for i in self.op_side}
         t0, t1 = self.text_range
         self._ev[0].record(main)
         self._side.wait_event(self._ev[0])
         for fn in self.ops[t0:t1]:
             fn(self._side.cuda_stream)
         self._ev[1].record(self._side)
-        for fn in self.ops[:t0]:
-            fn(main.cuda_stream)
+
+        def on_main(lo, hi):
+            for i in range(lo, hi):
+                if i in self.op_side:  # helper stream: starts once the main stream has reached this point
+                    self._sev[i][0].record(main)
+                    self._side2.wait_event(self._sev[i][0])
+                    self.ops[i](self._side2.cuda_stream)
+                    self._sev[i][1].record(self._side2)
+                    continue
+                for d in self.op_after.get(i, ()):
+                    if d in self.op_side:
+                        main.wait_event(self._sev[d][1])
+                self.ops[i](main.cuda_stream)
+
+        on_main(0, t0)
         main.wait_event(self._ev[1])
-        for fn in self.ops[t1:]:
-            fn(main.cuda_stream)
+        on_main(t1, len(self.ops))
 
     def run_debug(self):
         """Run op by op with a device sync after each, naming the op that faults."""

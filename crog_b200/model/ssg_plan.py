@@ -35,6 +35,7 @@ class SSGPlan(ForwardPlan):
         self.op_launches = []
         self.n_launches, self.gemm_flops, self.gemm_alg_flops = 0, 0, {}
         self.gemm_ops, self.tile_choice = [], {}
+        self.op_side, self.op_after, self.side_helpers, self.fuse_downsample = set(), {}, False, False
         self._side = self._ev = None
         self.text_range = (0, 0)
         self.sd = {k: v.detach().to(self.dev) for k, v in sd.items()}
