@@ -1,7 +1,6 @@
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
-for rep in 1 2; do
-CROG_SIDE_HELPERS=0 python bench.py --steps 40 --no-cpu-baseline --no-e2e > gpurun_out/b0.json 2> gpurun_out/b0.err; python -c "import sys,json; d=json.loads(open('gpurun_out/b0.json').read().strip().splitlines()[-1]); print('inline ', d['value'], d['ms_per_step'], d['clocks']['sm_mhz'])"
-python bench.py --steps 40 --no-cpu-baseline --no-e2e > gpurun_out/b.json 2> gpurun_out/b.err; python -c "import sys,json; d=json.loads(open('gpurun_out/b.json').read().strip().splitlines()[-1]); print('helpers', d['value'], d['ms_per_step'], d['clocks']['sm_mhz'])"
-done
-tail -3 gpurun_out/b.err
+M=gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active,sm__throughput.avg.pct_of_peak_sustained_elapsed
+CROG_NO_FORK=1 ncu --metrics $M --clock-control none --profile-from-start off --csv --log-file gpurun_out/launches_v5_raw.csv python tests/prof_forward.py 64 gpurun_out/ops_v5.tsv > gpurun_out/prof_fwd.log 2>&1
+tail -1 gpurun_out/prof_fwd.log
+ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv --log-file gpurun_out/bench_launches_raw.csv python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu-baseline --ncu-range > gpurun_out/bench_ncu.json 2> gpurun_out/bench_ncu.err
+wc -l gpurun_out/bench_launches_raw.csv
