@@ -1,6 +1,9 @@
+# One GPU-box validation pass (used with: gpurun --timeout 1500 -- 'bash scripts/gpu_run.sh'):
+# the GPU parity suite, the smoke entry point, the default bench line and the tail micro-benchmark.
 mkdir -p gpurun_out
-M=gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active,sm__throughput.avg.pct_of_peak_sustained_elapsed
-CROG_NO_FORK=1 ncu --metrics $M --clock-control none --profile-from-start off --csv --log-file gpurun_out/launches_v5_raw.csv python tests/prof_forward.py 64 gpurun_out/ops_v5.tsv > gpurun_out/prof_fwd.log 2>&1
-tail -1 gpurun_out/prof_fwd.log
-ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv --log-file gpurun_out/bench_launches_raw.csv python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu-baseline --ncu-range > gpurun_out/bench_ncu.json 2> gpurun_out/bench_ncu.err
-wc -l gpurun_out/bench_launches_raw.csv
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
+python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
+python bench.py > gpurun_out/bench_final.json 2> gpurun_out/bench_final.err
+python -c "import json; d=json.loads(open('gpurun_out/bench_final.json').read().strip().splitlines()[-1]); print('bench', d['value'], d['ms_per_step'], 'e2e', d['e2e']['value'], 'gemm TF/s', d['roofline']['achieved'], d['roofline']['frac'], 'cpu', d['cpu_baseline']['value'], d['clocks'])"
+python bench.py --workload tail > gpurun_out/tail_final.json 2> gpurun_out/tail_final.err
+python -c "import json; d=json.loads(open('gpurun_out/tail_final.json').read().strip().splitlines()[-1]); print('tail', d['ms_per_step'], d['roofline']['frac'], d['stress']['ms'], d['blobs']['parity_spot_check'])"
