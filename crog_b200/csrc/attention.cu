@@ -1,7 +1,11 @@
-// Softmax attention for head_dim 64 (text causal L<=77, attention-pool 169 tokens, decoder
-// self-attention 676 tokens, decoder cross-attention 676 x L with key padding).
-// v1: CUDA-core streaming softmax, one query per thread, K/V tiles of 64 keys staged in shared
-// memory and broadcast to the warp; fp32 math throughout.
+// Softmax attention for head_dim 64 on CUDA cores, and the dispatcher of crog_attention:
+//   * bf16 attentions with >= 128 queries or keys (attention pool, decoder self- and cross-attention) go to the tcgen05
+//     kernel of attention_tc.cu;
+//   * short sequences (the causal text tower, L <= 96) run attention_small_kernel: one CTA per (sample, head), one
+//     thread per score, one warp per softmax row, one thread per output quad;
+//   * everything else (fp32 mode with long sequences) runs the streaming kernel: one query per thread, K/V tiles of
+//     64 keys staged in shared memory and broadcast to the warp.
+// fp32 math throughout.
 #include <stdlib.h>
 
 #include "common.cuh"

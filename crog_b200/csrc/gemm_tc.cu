@@ -5,12 +5,15 @@
 //   warp 0      TMA producer   (cp.async.bulk.tensor 2D, SWIZZLE_128B, mbarrier complete_tx) over a STAGES-deep ring
 //   warp 1      MMA issuer     (tcgen05.mma cta_group::1 kind::f16, M=128, N=BN, K=16) into one of two TMEM
 //                              accumulator buffers, so tile i+1 is being multiplied while tile i drains
-//   warps 2..9  epilogue       two independent groups of four warps; group g drains accumulator buffer g (tiles
-//                              i = g, g+2, ...), so two tiles are in flight in the epilogue and no barrier ever
-//                              joins more than one warp.  A warp owns 32 accumulator rows (its TMEM lane quarter)
-//                              and walks the tile's columns in 128-byte chunks:
+//   warps 2..   epilogue       EPI_WARPS / 4 independent groups of four warps (one, two or three); group g drains
+//                              accumulator buffer g (tiles i = g, g + G, ...), so G tiles are in flight in the
+//                              epilogue.  A warp owns 32 accumulator rows (its TMEM lane quarter) and walks the tile's
+//                              columns in 128-byte chunks.  The tile's scale / bias slice is staged in shared memory
+//                              once per tile by the group (named barrier) and applied as packed FFMA2; the residual
+//                              add is FADD2, ReLU on bf16 outputs is applied to the packed pairs.
 //     TMA epilogue   (output rows == enumerated rows: every token matrix, compact->compact and padded->padded
-//                    convolutions)  tcgen05.ld -> registers (thread = row) -> +addmat, scale/bias, act, gate ->
+//                    convolutions)  tcgen05.ld -> registers (thread = row) -> +addmat, scale/bias (or the row-affine
+//                    form of a folded LayerNorm), act, gate -> optional per-row (sum, sum^2) partials ->
 //                    (+ residual chunk that a TMA load prefetched into the staging buffer NBUF-1 chunks ahead) ->
 //                    packed into the SWIZZLE_128B staging tile -> one cp.async.bulk.tensor store per chunk.
 //                    Halo rows of a padded output are written as zeros, which is what they must hold.
@@ -18,7 +21,8 @@
 //                    row-contiguous 16-byte stores with the output row looked up per staged row.
 // The K loop runs over (tap, 64-channel chunk); for a 3x3 convolution on the zero-haloed ("padded") NHWC layout
 // tap t is the same activation matrix shifted by a constant number of rows, so the A tile of every k-step is one plain
-// 2D TMA box at row (row0 + shift_t); rows outside the tensor are zero-filled by TMA.
+// 2D TMA box at row (row0 + shift_t); rows outside the tensor are zero-filled by TMA.  A second activation operand
+// (CrogGemm.a2) continues the K loop after the first one's chunks: two summed 1x1 convolutions as one contraction.
 #include <stdlib.h>
 
 #include "tc_common.cuh"
