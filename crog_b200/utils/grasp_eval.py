@@ -18,6 +18,7 @@ import torch
 from .. import _lib as L
 
 _ws_cache = {}
+MAX_PREDS = 32  # predictions per sample one crog_jaccard call scores (MAXK in csrc/tail.cu)
 
 
 def _dev():
@@ -186,19 +187,25 @@ def calculate_jacquard_index(grasp_preds, grasp_targets, iou_threshold=0.25):
     preds = np.asarray(grasp_preds, dtype=np.float64).reshape(-1, 5)
     is_np = isinstance(grasp_targets, np.ndarray)
     tg = np.asarray(grasp_targets, dtype=np.float64)
-    K = max(preds.shape[0], 1)
-    g = torch.zeros((1, K, 5), dtype=torch.float64, device=dev)
-    if preds.shape[0]:
-        g[0, :preds.shape[0]] = torch.from_numpy(preds).to(dev)
-    n = torch.tensor([preds.shape[0]], dtype=torch.int32, device=dev)
     t = torch.from_numpy(np.ascontiguousarray(tg[None, :, :6] if tg.shape[1] >= 6 else np.pad(tg, ((0, 0), (0, 6 - tg.shape[1])))[None])).to(dev)
     cnt = torch.tensor([tg.shape[0]], dtype=torch.int32, device=dev)
-    flags = jacquard_batched(g, n, t, cnt)
-    edited = t[0].cpu().numpy()
-    if is_np and grasp_targets.dtype.kind == "f":
+    hit = 0
+    # the device kernel scores at most MAX_PREDS predictions per call; longer lists go in chunks (max over chunks = max over
+    # all pairs; the target edit is idempotent)
+    for p0 in range(0, max(preds.shape[0], 1), MAX_PREDS):
+        chunk = preds[p0:p0 + MAX_PREDS]
+        K = max(chunk.shape[0], 1)
+        g = torch.zeros((1, K, 5), dtype=torch.float64, device=dev)
+        if chunk.shape[0]:
+            g[0, :chunk.shape[0]] = torch.from_numpy(chunk).to(dev)
+        n = torch.tensor([chunk.shape[0]], dtype=torch.int32, device=dev)
+        flags = jacquard_batched(g, n, t, cnt)
+        hit |= int(flags[0, 1].item())
+    if is_np:  # the reference edits any ndarray in place, in the array's own dtype
+        edited = t[0].cpu().numpy()
         grasp_targets[:, 2] = edited[:, 2]
         grasp_targets[:, 3] = edited[:, 3]
-    return int(flags[0, 1].item())
+    return hit
 
 
 # ======================================================================= SSG post-processing (BASELINE config 4)

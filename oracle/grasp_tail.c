@@ -5,8 +5,10 @@
  * two can be checked against each other.  Third-party semantics restated
  * (absent from /root/reference): scikit-image 0.20.0 peak_local_max / draw.polygon,
  * scipy 1.9.1 maximum_filter, opencv 4.7.0 boxPoints, numpy 1.24.3 promotion
- * (SURVEY.md Appendix A).  PARITY UNPINNED for the scikit-image parts (no reference
- * tests / vectors exist); see oracle/grasp_tail.py header for what is pinned.
+ * (SURVEY.md Appendix A).  PINNED (round 2) against the reference's own lines
+ * 289-374 executed by oracle/make_golden_tail.py (tests/golden/tail_cases.npz) and
+ * against OpenCV / scipy cross-checks; the two scikit-image internals that stay
+ * unverifiable offline are listed in oracle/grasp_tail.py's header.
  *
  * Also used as bench.py's cpu_baseline ("port") for the tail micro-benchmark.
  *

@@ -13,12 +13,27 @@ under /root/reference (environment.yml:49,61,75,76):
 
 so this file restates their published algorithms.
 
-PARITY PINNING STATUS: **parity unpinned** for the scikit-image parts — the reference
-has no tests or golden vectors for this path and scikit-image is not installable
-here.  What *is* pinned (tests/test_oracle_tail.py): the two upstream docstring
-known-answer vectors (A.6), ``cv2.boxPoints`` of the installed OpenCV bit-for-bit,
-``scipy.ndimage.maximum_filter`` for the 5x5 max filter, and agreement between this
-numpy restatement and the independent plain-C restatement in oracle/grasp_tail.c.
+PARITY PINNING STATUS (round 2): **pinned against the reference's own code executed here**, with two third-party
+internals left that cannot be executed offline.
+
+Pinned (oracle/make_golden_tail.py -> tests/golden/tail_cases.npz, re-checked by tests/test_oracle_tail.py):
+  * the reference's OWN lines utils/grasp_eval.py:289-374 run unmodified (real cv2.boxPoints, x/y transposition,
+    rr<640 / cc<480 filters, area[cc, rr] canvas, calculate_max_iou, in-place target edit) next to this file on 60
+    config-5 maps (blobs + stress, K = 1 / 5 / 9), 1600 rectangle pairs and 48 prediction/GT sets: peaks, rows, pixel
+    counts, IoU floats, J flags and edited targets are equal;
+  * ``polygon`` == {p : cv2.pointPolygonTest(quad, p) >= 0} (exact integer test of the installed OpenCV) on 10 000 random
+    truncated boxPoints quadrilaterals of non-zero area;
+  * the single greedy spacing pass == skimage's batched cKDTree ``ensure_spacing`` written out literally with scipy
+    (oracle/skimage_literal.py) on plateau-heavy maps, K in {1, 5, 40, 400, inf};
+  * ``cv2.boxPoints`` bit-for-bit, ``scipy.ndimage.maximum_filter`` for the 5x5 filter, the two upstream docstring
+    vectors, and agreement with the independent plain-C restatement oracle/grasp_tail.c.
+NOT verifiable without a scikit-image 0.20.0 install (restated from the published source):
+  1. skimage/_shared/_geometry point_in_polygon on ZERO-AREA quadrilaterals (w or h truncating to a doubled segment):
+     O'Rourke's crossing test keeps only the end points there, OpenCV keeps the whole segment; this file follows the
+     published skimage rule.  (Non-degenerate quads are covered by the OpenCV cross-check.)
+  2. that peak_local_max 0.20.0 really is maximum_filter(mode='nearest') + ``image > threshold`` + border width
+     = min_distance + ``argsort(-intensity, kind='stable')`` + ensure_spacing(min_split_size=50, max_split_size=2000)
+     as restated in skimage_literal.py — i.e. the *transcription* of that control flow, not its consequences.
 
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline/reference arm may
 import this file.
