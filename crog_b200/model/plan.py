@@ -339,6 +339,8 @@ class ForwardPlan:
         self._dynamic_weights(state32)
         self.text_range = (t_begin, len(self.ops))  # independent of the image tower: may run on a forked stream
         fq = self._neck(c3, c4, c5)
+        if not cfg.use_contrastive:
+            self.keep["fq_neck"] = fq  # (with a decoder this buffer is its in-place fp32 residual stream)
         if cfg.use_contrastive:
             fq = self._decoder(fq, wordfeat)
             self.keep["fq_dec"] = fq

@@ -59,8 +59,11 @@ def build_reference(cfg):
     return ref
 
 
-def run_case(tag, word_len, batch, mode, seed_w):
-    cfg = synth.default_cfg(word_len=word_len)
+def run_case(tag, word_len, batch, mode, seed_w, **cfg_over):
+    """cfg_over: the ablation switches of config/OCID-VLG/crog_multiple_r50_wo_contrastive.yaml (use_contrastive=False:
+    no TransformerDecoder, model/crog.py:27-39,70-72) and ..._wo_grasps.yaml (use_grasp_masks=False: the mask-only
+    ``Projector`` of model/layers.py:135-173, eval return ``(pred, mask)``, model/crog.py:115-133)."""
+    cfg = synth.default_cfg(word_len=word_len, **cfg_over)
     ref = build_reference(cfg)
     sd = synth.make_state_dict(cfg, seed=seed_w, mode=mode)
     ref_sd = ref.state_dict()
@@ -72,6 +75,8 @@ def run_case(tag, word_len, batch, mode, seed_w):
     t0 = time.time()
     with torch.no_grad():
         (r_maps, _) = ref(img, word)
+        if torch.is_tensor(r_maps):  # mask-only ablation returns the bare prediction
+            r_maps = (r_maps,)
         # intermediates straight from the reference sub-modules
         c3, c4, c5 = ref.backbone.encode_image(img)
         wfeat, state = ref.backbone.encode_text(word)
@@ -83,11 +88,14 @@ def run_case(tag, word_len, batch, mode, seed_w):
                      ("word", wfeat, inter["word"]), ("state", state, inter["state"]),
                      ("fq_neck", fq, inter["fq_neck"])]:
         errs[nm] = float((a - b).abs().max())
-    for i, nm in enumerate(("mask", "qua", "sin", "cos", "wid")):
+    assert len(r_maps) == len(o_maps) == (5 if cfg.use_grasp_masks else 1)
+    for i, nm in enumerate(("mask", "qua", "sin", "cos", "wid")[:len(r_maps)]):
         errs[nm] = float((r_maps[i] - o_maps[i]).abs().max())
     print(tag, "ref fwd %.2fs" % t_ref, {k: "%.2e" % v for k, v in errs.items()})
-    # the restatement must agree with the reference to fp32 round-off (1e-4 abs on O(10) values)
-    assert all(v <= 1e-4 for v in errs.values()), errs
+    # the restatement must agree with the reference to fp32 round-off: 1e-4 abs on logits of range +-16; the decoder-less
+    # ablation feeds the projector un-normalised features (logits up to +-104), so the bar scales with the range
+    rng_scale = max(1.0, max(float(m.abs().max()) for m in r_maps) / 16.0)
+    assert all(v <= 1e-4 * rng_scale for v in errs.values()), (errs, rng_scale)
     post = O.postprocess(r_maps, (416, 416))
     out = {
         "word_len": np.int64(word_len), "batch": np.int64(batch), "seed_w": np.int64(seed_w),
@@ -95,9 +103,12 @@ def run_case(tag, word_len, batch, mode, seed_w):
         "state": state.numpy(), "word_feat": wfeat.numpy(),
         "c5_sample": c5[:, ::16].numpy(), "c4_sample": c4[:, ::64].numpy(), "c3_sample": c3[:, ::64, ::2, ::2].numpy(),
         "fq_neck_sample": fq[:, ::16].numpy(),
-        "fq_dec_sample": inter["fq_dec"][:, ::16].numpy(),
-        "post_qua_rowsum": post[1].sum(-1).numpy(),
     }
+    if cfg.use_contrastive:
+        out["fq_dec_sample"] = inter["fq_dec"][:, ::16].numpy()
+    if cfg.use_grasp_masks:
+        out["post_qua_rowsum"] = post[1].sum(-1).numpy()
+    out["use_contrastive"], out["use_grasp_masks"] = np.bool_(cfg.use_contrastive), np.bool_(cfg.use_grasp_masks)
     path = os.path.join(ROOT, "tests", "golden", f"model_{tag}.npz")
     os.makedirs(os.path.dirname(path), exist_ok=True)
     np.savez_compressed(path, mode=np.array(mode), **out)
@@ -108,3 +119,5 @@ if __name__ == "__main__":
     torch.set_num_threads(os.cpu_count())
     run_case("L17_perturbed", 17, 2, "perturbed", 0)
     run_case("L20_init", 20, 1, "init", 0)
+    run_case("L17_wo_contrastive", 17, 1, "perturbed", 0, use_contrastive=False)
+    run_case("L17_wo_grasps", 17, 1, "perturbed", 0, use_grasp_masks=False)

@@ -65,6 +65,44 @@ def test_forward_fp32_matches_reference_golden(golden_dir, tag):
     assert np.abs(plan.keep["c5"].interior().cpu().numpy()[:, ::16] - g["c5_sample"]).max() <= 1e-3
 
 
+@pytest.mark.parametrize("tag,over", [("L17_wo_contrastive", {"use_contrastive": False}), ("L17_wo_grasps", {"use_grasp_masks": False})])
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_ablation_configs_match_reference_golden(golden_dir, tag, over, precision):
+    """The two ablation switches of the reference (model/crog.py:25-45): no TransformerDecoder
+    (crog_multiple_r50_wo_contrastive.yaml) and the mask-only Projector (..._wo_grasps.yaml, model/layers.py:135-173),
+    against goldens of the unmodified reference.  fp32: 1e-3 max-abs on logits of range +-16, scaled with the range for the
+    decoder-less model whose un-normalised features give logits up to +-104; bf16: the stated rel-L2 <= 5e-2 per map."""
+    from crog_b200.model import CROG
+
+    g = np.load(os.path.join(golden_dir, f"model_{tag}.npz"))
+    Lw, B = int(g["word_len"]), int(g["batch"])
+    cfg = synth.default_cfg(Lw, **over)
+    sd = synth.make_state_dict(cfg, int(g["seed_w"]), str(g["mode"]))
+    model = CROG(cfg, precision=precision)
+    model.load_state_dict(sd, strict=True)
+    model = model.cuda()
+    img, word = synth.make_inputs(B, Lw)
+    out, tgt = model(img.cuda(), word.cuda())
+    torch.cuda.synchronize()
+    if cfg.use_grasp_masks:
+        assert isinstance(out, tuple) and len(out) == 5 and len(tgt) == 5
+        got = torch.stack([m[:, 0] for m in out], 1).cpu().numpy()
+    else:  # eval return of the mask-only model is (pred, mask), model/crog.py:133
+        assert torch.is_tensor(out) and tgt is None
+        got = out.cpu().numpy()
+    ref = g["maps"]
+    assert got.shape == ref.shape
+    if precision == "fp32":
+        scale = max(1.0, float(np.abs(ref).max()) / 16.0)
+        assert np.abs(got - ref).max() <= 1e-3 * scale, (np.abs(got - ref).max(), scale)
+        if not cfg.use_contrastive:  # the FPN output survives (no decoder updates it in place): reference's neck(...) slice
+            fq = model.plan_for(B, 416).keep["fq_neck"].interior().cpu().numpy()
+            assert np.abs(fq[:, ::16] - g["fq_neck_sample"]).max() <= 1e-3
+    else:
+        rel = max(np.linalg.norm(got[:, i] - ref[:, i]) / np.linalg.norm(ref[:, i]) for i in range(ref.shape[1]))
+        assert rel <= 5e-2, rel
+
+
 def test_forward_bf16_tcgen05_tolerance(golden_dir):
     g = np.load(os.path.join(golden_dir, "model_L17_perturbed.npz"))
     Lw, B = 17, 2

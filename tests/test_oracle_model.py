@@ -35,3 +35,21 @@ def test_restatement_matches_reference_golden(golden_dir, tag):
     assert np.abs(inter["fq_dec"][:, ::16].numpy() - g["fq_dec_sample"]).max() <= 1e-4
     post = O.postprocess(maps, (416, 416))
     assert np.abs(post[1].sum(-1).numpy() - g["post_qua_rowsum"]).max() <= 1e-2
+
+
+@pytest.mark.parametrize("tag,over", [("L17_wo_contrastive", {"use_contrastive": False}), ("L17_wo_grasps", {"use_grasp_masks": False})])
+def test_restatement_matches_reference_golden_ablations(golden_dir, tag, over):
+    """config/OCID-VLG/crog_multiple_r50_wo_contrastive.yaml / ..._wo_grasps.yaml shapes (model/crog.py:25-45)."""
+    g = np.load(os.path.join(golden_dir, f"model_{tag}.npz"))
+    L, B = int(g["word_len"]), int(g["batch"])
+    cfg = synth.default_cfg(L, **over)
+    sd = synth.make_state_dict(cfg, int(g["seed_w"]), str(g["mode"]))
+    assert not over.get("use_contrastive", True) == (not any(k.startswith("decoder") for k in sd))
+    img, word = synth.make_inputs(B, L)
+    torch.set_num_threads(os.cpu_count())
+    maps, inter = O.crog_forward(sd, cfg, img, word, keep=True)
+    got = torch.stack([m[:, 0] for m in maps], 1).numpy()
+    assert got.shape == g["maps"].shape and got.shape[1] == (5 if cfg.use_grasp_masks else 1)
+    scale = max(1.0, float(np.abs(g["maps"]).max()) / 16.0)  # the decoder-less logits reach +-104
+    assert np.abs(got - g["maps"]).max() <= 1e-4 * scale
+    assert np.abs(inter["fq_neck"][:, ::16].numpy() - g["fq_neck_sample"]).max() <= 1e-4
