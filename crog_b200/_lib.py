@@ -52,7 +52,7 @@ SIGNATURES = {
     "crog_stem_conv1": (C.c_int, [_P, _I, _I, _I, _P, _P, _P, _I, _P, _I, _I, _P]),
     "crog_layernorm": (C.c_int, [_P, _I, _P, _P, _P, _P, _I, _L, _I, _F, _P]),
     "crog_layernorm_chain": (C.c_int, [_P, _I, _P, _P, _P, _P, _P, _P, _P, _I, _L, _I, _F, _P]),
-    "crog_embed_tokens": (C.c_int, [_P, _P, _P, _P, _I, _I, _I, _P]),
+    "crog_embed_tokens": (C.c_int, [_P, _P, _P, _P, _I, _I, _I, _I, _P]),
     "crog_gather_eot": (C.c_int, [_P, _P, _I, _P, _I, _I, _I, _I, _P]),
     "crog_attention": (C.c_int, [_P, _I, _P, _I, _P, _I, _P, _I, _I, _I, _I, _I, _F, _I, _P, _I, _P]),
     "crog_dynw_fold": (C.c_int, [_P, _I, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P]),

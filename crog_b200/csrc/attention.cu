@@ -223,12 +223,13 @@ extern "C" int crog_attention(const void* q, int32_t ldq, const void* k, int32_t
     return crog_attention_tc(q, ldq, k, ldk, v, ldv, o, ldo, B, heads, Tq, Tk, scale, (const int64_t*)pad_word, s);
   if (Tq <= SM_T && Tk <= SM_T && !getenv("CROG_ATTN_NO_SMALL")) {  // text tower (and any other short sequence)
     const size_t smem = ((size_t)Tq * HD + (size_t)Tk * SM_KP + (size_t)Tk * HD + (size_t)Tq * (Tk + 1)) * sizeof(float);
-    static bool attr = false;
-    if (!attr) {
+    static DeviceOnce once;
+    int dev_;
+    if (once.need(&dev_)) {
       const int mx = (SM_T * HD + SM_T * SM_KP + SM_T * HD + SM_T * (SM_T + 1)) * (int)sizeof(float);
       CROG_CUDA_OK(cudaFuncSetAttribute(attention_small_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
       CROG_CUDA_OK(cudaFuncSetAttribute(attention_small_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
-      attr = true;
+      once.done(dev_);
     }
     dim3 g2(heads, B);
     if (dtype == CROG_F32)

@@ -267,10 +267,11 @@ __global__ void __launch_bounds__(256, 2) attention_tc_kernel(const __grid_const
 
 int crog_attention_tc(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, void* o, int ldo, int B, int heads,
                       int Tq, int Tk, float scale, const int64_t* pad_word, cudaStream_t stream) {
-  static bool attr = false;
-  if (!attr) {
+  static DeviceOnce once;
+  int dev_;
+  if (once.need(&dev_)) {
     CROG_CUDA_OK(cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL));
-    attr = true;
+    once.done(dev_);
   }
   CUtensorMap tmQ, tmK, tmV;
   int rc = crog_encode_2d_bf16(&tmQ, q, (uint64_t)heads * HD, (uint64_t)B * Tq, (uint64_t)ldq, QT);

@@ -5,6 +5,8 @@
 #include <stdint.h>
 #include <stdio.h>
 
+#include <atomic>
+
 #include "../../include/crog_b200.h"
 
 typedef __nv_bfloat16 bf16;
@@ -25,6 +27,22 @@ void crog_set_error(const char* fmt, ...);
     cudaError_t e__ = (expr);                                                        \
     if (e__ != cudaSuccess) CROG_FAIL(CROG_E_CUDA, "%s: %s", #expr, cudaGetErrorString(e__)); \
   } while (0)
+
+// Kernel function attributes (dynamic shared memory opt-in, carve-out) are PER DEVICE.  One bit per device ordinal, set
+// after the attributes have been applied on that device; safe against concurrent host threads (two threads may both apply
+// the same attributes once, which is harmless).  Usage:
+//   static DeviceOnce once; int dev; if (once.need(&dev)) { cudaFuncSetAttribute(...); once.done(dev); }
+struct DeviceOnce {
+  std::atomic<unsigned long long> mask{0};
+  bool need(int* dev) const {
+    *dev = 0;
+    if (cudaGetDevice(dev) != cudaSuccess) return true;
+    return *dev >= 64 || !((mask.load(std::memory_order_acquire) >> *dev) & 1ull);
+  }
+  void done(int dev) {
+    if (dev < 64) mask.fetch_or(1ull << dev, std::memory_order_release);
+  }
+};
 #define CROG_LAUNCH_OK(name)                                                        \
   do {                                                                               \
     cudaError_t e__ = cudaGetLastError();                                            \

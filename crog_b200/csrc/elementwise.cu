@@ -268,11 +268,15 @@ __global__ void layernorm_chain_kernel(const TI* __restrict__ x, const float* __
 
 // ------------------------------------------------------------------ text embedding / EOT gather
 __global__ void embed_kernel(const int64_t* __restrict__ word, const float* __restrict__ emb, const float* __restrict__ pos,
-                             float* __restrict__ out, int B, int L, int D) {
+                             float* __restrict__ out, int B, int L, int D, int vocab) {
   pdl_launch();
   pdl_wait();
   const int row = blockIdx.x, l = row % L;
   const long long id = word[row];
+  if (id < 0 || id >= vocab) {  // nn.Embedding's device-side assert (clip.py:440): fail loudly, never read out of bounds
+    if (threadIdx.x == 0) printf("crog_embed_tokens: token id %lld at row %d outside [0, %d)\n", id, row, vocab);
+    __trap();
+  }
   for (int c = threadIdx.x * 4; c < D; c += blockDim.x * 4) {
     const float4 e = *reinterpret_cast<const float4*>(emb + id * D + c);
     const float4 p = *reinterpret_cast<const float4*>(pos + (long long)l * D + c);
@@ -554,10 +558,11 @@ extern "C" int crog_layernorm_chain(const void* x, int32_t x_dtype, const float*
 }
 
 extern "C" int crog_embed_tokens(const int64_t* word, const float* emb, const float* pos, float* out, int32_t B, int32_t L,
-                                 int32_t D, void* stream) {
+                                 int32_t D, int32_t vocab, void* stream) {
   CROG_REQUIRE(D % 4 == 0, CROG_E_BADSHAPE, "embed: D %% 4");
+  CROG_REQUIRE(vocab > 0, CROG_E_BADSHAPE, "embed: vocab > 0");
   if (B * L == 0) return CROG_OK;
-  crog_launch(embed_kernel, dim3(B * L), dim3(128), 0, (cudaStream_t)stream, word, emb, pos, out, B, L, D);
+  crog_launch(embed_kernel, dim3(B * L), dim3(128), 0, (cudaStream_t)stream, word, emb, pos, out, B, L, D, vocab);
   CROG_LAUNCH_OK("embed");
   return CROG_OK;
 }

@@ -558,14 +558,12 @@ template <int BN, int STAGES, int NBUF, int MODE, bool CONV3 = false, int EPI_WA
 int launch(const CrogGemm* g, cudaStream_t stream) {
   using L = Cfg<BN, STAGES, NBUF, CONV3, EPI_WARPS, PAIR>;
   static_assert(L::TOTAL <= 227 * 1024, "shared memory budget");
-  static bool attr_set = false;  // per-process; device attribute is re-set cheaply if another device is used
-  static int attr_dev = -1;
+  static DeviceOnce once;  // function attributes are per device (one static per template instantiation)
   int dev = 0;
-  CROG_CUDA_OK(cudaGetDevice(&dev));
-  if (!attr_set || attr_dev != dev) {
+  if (once.need(&dev) || g_num_sms == 0) {
     CROG_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES, NBUF, MODE, CONV3, EPI_WARPS, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
     CROG_CUDA_OK(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
-    attr_set = true; attr_dev = dev;
+    once.done(dev);
   }
   CUtensorMap tmA, tmA2, tmB, tmOut, tmRes;
   const long long Ktot = (long long)g->taps * g->cin + g->cin2;

@@ -492,11 +492,12 @@ extern "C" int crog_ssg_fast_nms(const float* cls, const int32_t* keep, const fl
   unsigned long long* cand = (unsigned long long*)workspace;
   int* cand_keep = (int*)(cand + (size_t)ncls * top_k);
   int* cand_n = cand_keep + (size_t)ncls * top_k;
-  static bool attr = false;
-  if (!attr) {
+  static DeviceOnce once;
+  int dev_;
+  if (once.need(&dev_)) {
     CROG_CUDA_OK(cudaFuncSetAttribute(ssg_nms_class_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, NMS_CAP * 8));
     CROG_CUDA_OK(cudaFuncSetAttribute(ssg_nms_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MRG_CAP * 8));
-    attr = true;
+    once.done(dev_);
   }
   ssg_nms_class_kernel<<<ncls, NMS_T, NMS_CAP * 8, s>>>(cls, keep, boxes, N, num_classes, top_k, iou_thr, cand, cand_keep, cand_n);
   CROG_LAUNCH_OK("ssg_nms_class");

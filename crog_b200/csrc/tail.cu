@@ -740,12 +740,13 @@ extern "C" int crog_detect_grasps(const float* q, const float* sin_m, const floa
   int* flags = (int*)(ws + (((int64_t)B * nb * nw * SEG_BYTES + 15) / 16) * 16);
   const size_t smem_lists = (size_t)nw * (CAPW + TSEL) * 8;
   const size_t smem_fast = (size_t)SCAN_NST * SCAN_R * W * 4 + smem_lists + 2 * SCAN_NST * 8;
-  static bool attr = false;
-  if (!attr) {
+  static DeviceOnce once;
+  int dev_;
+  if (once.need(&dev_)) {
     CROG_CUDA_OK(cudaFuncSetAttribute(peak_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       SCAN_NST * SCAN_R * 8 * STRIP * 4 + 8 * (CAPW + TSEL) * 8 + 2 * SCAN_NST * 8));
     CROG_CUDA_OK(cudaFuncSetAttribute(peak_scan_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * (CAPW + TSEL) * 8));
-    attr = true;
+    once.done(dev_);
   }
   if (W % 4 == 0 && (long long)H * W >= 2 && !getenv("CROG_SCAN_GENERIC")) peak_scan_kernel<<<dim3(nb, B), (nw + 1) * 32, smem_fast, s>>>(q, H, W, threshold, nw, band, ws);
   else peak_scan_generic_kernel<<<dim3(nb, B), nw * 32, smem_lists, s>>>(q, H, W, threshold, nw, band, ws);
@@ -773,11 +774,12 @@ extern "C" int crog_jaccard(const double* grasps, const int32_t* n_peaks, int32_
   CROG_REQUIRE((inter == nullptr) == (uni == nullptr), CROG_E_BADSHAPE, "jaccard: inter/uni must both be given or both NULL");
   if (B == 0) return CROG_OK;
   const size_t smem = (size_t)K * TG_MAXROWS * TG_WORDS * 4;
-  static bool attr = false;
-  if (!attr) {
+  static DeviceOnce once_j;
+  int dev_j;
+  if (once_j.need(&dev_j)) {
     CROG_CUDA_OK(cudaFuncSetAttribute(jaccard_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MAXK * TG_MAXROWS * TG_WORDS * 4));
     CROG_CUDA_OK(cudaFuncSetAttribute(jaccard_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    attr = true;
+    once_j.done(dev_j);
   }
   jaccard_kernel<<<B, JT, smem, (cudaStream_t)stream>>>(grasps, n_peaks, K, gt, gt_count, Mmax, inter, uni, j_flags,
                                                         (long long*)counters, edit_gt);

@@ -73,12 +73,36 @@ class GraspEvaluator:
         flags = GE.jacquard_batched(grasps, n, gt, gt_count, counters=self.counters)
         return {"post": post, "maps": inv, "iou": iou, "peaks": peaks, "n_peaks": n, "grasps": grasps, "j_flags": flags}
 
-    def summary(self):
-        """crog_engine.py:535-556: mean mask IoU, Pr@50..90 and J@1 / J@K over everything seen so far (this rank)."""
+    def gathered_iou(self) -> Optional[torch.Tensor]:
+        """Per-sample mask IoU of every rank, concatenated in rank order — the reference's ``concat_all_gather(iou_list)``
+        (utils/misc.py:47-59, engine/crog_engine.py:269).  Unlike the reference's fixed-shape all_gather, ragged shards
+        (shard_range gives the low ranks one sample more) are handled by gathering the counts first."""
+        import torch.distributed as dist
+
+        if not self.iou_list:
+            return None
+        iou = torch.cat(self.iou_list)
+        if not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1):
+            return iou
+        world = dist.get_world_size()
+        n = torch.tensor([iou.numel()], dtype=torch.int64, device=iou.device)
+        counts = [torch.zeros_like(n) for _ in range(world)]
+        dist.all_gather(counts, n)
+        counts = [int(c.item()) for c in counts]
+        pad = torch.zeros(max(counts), dtype=iou.dtype, device=iou.device)
+        pad[:iou.numel()] = iou
+        parts = [torch.zeros_like(pad) for _ in range(world)]
+        dist.all_gather(parts, pad)
+        return torch.cat([p[:c] for p, c in zip(parts, counts)])
+
+    def summary(self, gather: bool = True):
+        """crog_engine.py:535-556: mean mask IoU, Pr@50..90 and J@1 / J@K over everything seen so far.  With ``gather`` and
+        an initialised process group the IoU list is all-gathered over ranks first, as the reference does
+        (crog_engine.py:269); the J counters are whatever ``reduce()`` has made of them (per rank until it is called)."""
         j1, jk = self.j_index()
         out = {"J@1": j1, f"J@{self.K}": jk, "n": 0, "IoU": float("nan"), "Pr": {}}
-        if self.iou_list:
-            iou = torch.cat(self.iou_list)
+        iou = self.gathered_iou() if gather else (torch.cat(self.iou_list) if self.iou_list else None)
+        if iou is not None:
             out["n"], out["IoU"] = int(iou.numel()), float(iou.mean().item())
             for t in range(5, 10):
                 thr = torch.arange(0.5, 1.0, 0.1)[t - 5].item()  # the reference's float32 thresholds (crog_engine.py:541)
@@ -96,10 +120,17 @@ class GraspEvaluator:
         return post, peaks, n, grasps, flags
 
     @torch.no_grad()
-    def stream(self, host_batches):
+    def stream(self, host_batches, letterbox=None, original: bool = False):
         """End-to-end evaluation over HOST batches with the input copies hidden behind the previous batch's compute.
 
         ``host_batches`` yields ``(img, word, gt, gt_count)`` CPU tensors (pinned memory for truly asynchronous copies).
+        ``img`` is either the float32 network input [B,3,S,S] or — with ``letterbox = (mat, mat_inv, (ori_h, ori_w))``
+        from ``utils.warp.get_transform_mat`` — the raw uint8 RGB camera frames [B,ori_h,ori_w,3]: they cross PCIe as
+        bytes (0.92 MB instead of 2.08 MB per sample) and the letterbox + normalisation of utils/dataset.py:843-866 runs
+        on the device (``crog_preprocess_u8``, bit-exact with OpenCV).  ``original=True`` additionally decodes at the
+        original image size after the inverse letterbox (``step_original``, the reference's real evaluation loop,
+        engine/crog_engine.py:386-556) instead of at the network resolution.
+
         Two device staging slots are filled on a copy stream: while batch k runs on the compute stream, batch k+1 is
         already crossing PCIe.  For every batch the decoded grasps / peak counts / J flags are copied back and the
         host waits for them (the caller reads the result of every step); yields ``(n_peaks, grasps, j_flags)`` as
@@ -114,6 +145,9 @@ class GraspEvaluator:
             self._free = [torch.cuda.Event(), torch.cuda.Event()]
             self._done = [torch.cuda.Event(), torch.cuda.Event(), torch.cuda.Event()]
             self._hout = [None, None, None]
+            self._affine = {}
+        if original and letterbox is None:
+            raise RuntimeError("stream(original=True) needs letterbox=(mat, mat_inv, ori_size)")
         it = iter(host_batches)
 
         def prefetch(k):
@@ -132,6 +166,14 @@ class GraspEvaluator:
                 self._ready[s].record(self._copy_stream)
             return True
 
+        def affine(mat, B):
+            key = (id(mat), B)
+            if key not in self._affine:
+                if len(self._affine) > 8:
+                    self._affine.clear()
+                self._affine[key] = WP.device_affine(mat, B, dev)
+            return self._affine[key]
+
         k, more = 0, prefetch(0)
         pending = None  # result slot of the batch whose launches are enqueued but whose results are not handed over yet
         while more:
@@ -139,7 +181,17 @@ class GraspEvaluator:
             more = prefetch(k + 1)
             main.wait_event(self._ready[s])
             img, word, gt, cnt = self._slots[s]
-            _, _, n, grasps, flags = self.step(img, word, gt, cnt)
+            if img.dtype == torch.uint8:
+                if letterbox is None:
+                    raise RuntimeError("uint8 frames need letterbox=(mat, mat_inv, ori_size)")
+                S = self.model.cfg.input_size
+                buf = self.model.input_buffer(img.shape[0], S) if hasattr(self.model, "input_buffer") else None
+                img = WP.preprocess_images(img, affine(letterbox[0], img.shape[0]), (S, S), out=buf)
+            if original:
+                r_ = self.step_original(img, word, gt, cnt, affine(letterbox[1], img.shape[0]), letterbox[2])
+                n, grasps, flags = r_["n_peaks"], r_["grasps"], r_["j_flags"]
+            else:
+                _, _, n, grasps, flags = self.step(img, word, gt, cnt)
             self._free[s].record(main)
             r = k % 3
             if self._hout[r] is None or self._hout[r][1].shape != grasps.shape:

@@ -13,6 +13,8 @@ through ``load_state_dict`` (random init otherwise).
 from __future__ import annotations
 
 import os
+import threading
+from collections import OrderedDict
 from typing import Dict, Optional, Tuple
 
 import torch
@@ -60,16 +62,50 @@ class CROG(nn.Module):
                 mod.register_buffer(leaf, t)
             else:
                 mod.register_parameter(leaf, nn.Parameter(t, requires_grad=False))
-        self._plans: Dict[Tuple, object] = {}
+        # Plans own their activation buffers (about 95 MB per sample at 416x416): the cache is a small LRU, a batch smaller
+        # than a cached plan's runs on that plan (samples are independent end to end), and `prepare()` moves plan build +
+        # tile autotune + graph capture out of the first forward.  The dicts are shared by DataParallel replicas (shallow
+        # __dict__ copies), so they are keyed by device and guarded by one lock.
+        self.max_plans = int(os.environ.get("CROG_MAX_PLANS", "2"))
+        self._plans: "OrderedDict[Tuple, object]" = OrderedDict()
         self._graphs: Dict[Tuple, object] = {}
+        self._lock = threading.RLock()
         self.register_load_state_dict_post_hook(lambda module, incompatible: module.invalidate())
         self.eval()
 
     # ------------------------------------------------------------------ weight / plan management
     def invalidate(self):
         """Drop packed weights and captured graphs (call after changing parameters in place)."""
-        self._plans.clear()
-        self._graphs.clear()
+        with self._lock:
+            self._plans.clear()
+            self._graphs.clear()
+
+    def __getstate__(self):
+        # plans / graphs / the lock are per-process run-time state: a pickled or deep-copied module starts without them
+        d = dict(self.__dict__)
+        d["_plans"], d["_graphs"], d["_lock"] = OrderedDict(), {}, None
+        return d
+
+    def __setstate__(self, state):
+        super().__setstate__(state)
+        self._lock = threading.RLock()
+
+    def _full_state(self) -> Dict[str, torch.Tensor]:
+        """``state_dict()`` that also works on a ``torch.nn.DataParallel`` replica, whose ``_parameters`` are empty (the
+        per-device copies are plain attributes, torch/nn/parallel/replicate.py): walk the name table with getattr."""
+        out = {}
+        for s_ in crog_tensor_specs(self.cfg):
+            m = self
+            parts = s_.name.split(".")
+            for p_ in parts[:-1]:
+                m = m._modules[p_]
+            t = m._parameters.get(parts[-1])
+            if t is None:
+                t = m._buffers.get(parts[-1])
+            if t is None:
+                t = getattr(m, parts[-1])
+            out[s_.name] = t.detach()
+        return out
 
     def load_state_dict(self, state_dict, strict: bool = True, **kw):
         # reference checkpoints are saved from DataParallel/DDP (test_crog.py:70,79): accept "module." keys
@@ -100,21 +136,56 @@ class CROG(nn.Module):
             self.invalidate()
         return self
 
-    def plan_for(self, batch: int, size: int, keep: bool = False):
+    def _device(self) -> torch.device:
+        m = self._modules["backbone"]
+        t = m._parameters.get("text_projection")
+        return (t if t is not None else getattr(m, "text_projection")).device
+
+    def plan_for(self, batch: int, size: int, keep: bool = False, exact: bool = True):
+        """The execution plan serving ``batch`` samples of ``size`` x ``size``.  ``exact=False`` accepts a cached plan of a
+        larger batch (the smallest one): a dataloader's ragged last batch then costs neither 95 MB/sample of new buffers
+        nor a tile autotune; it runs in the first rows of the big plan."""
         from .plan import ForwardPlan
 
-        dev = self.backbone.text_projection.device
+        dev = self._device()
         if dev.type != "cuda":
             raise L.CrogError("crog_b200.CROG.forward needs the module on a CUDA device (sm_100a); no CPU fallback exists")
-        key = (batch, size, self.precision, self.gemm_impl, keep, dev.index)
-        plan = self._plans.get(key)
-        if plan is None:
-            with torch.cuda.device(dev):
-                plan = ForwardPlan(self.state_dict(), self.cfg, batch, self.precision, dev, size, self.gemm_impl, keep)
-                if self.autotune and os.environ.get("CROG_AUTOTUNE", "1") != "0":
-                    plan.autotune()
-            self._plans[key] = plan
+        with self._lock:
+            key = (batch, size, self.precision, self.gemm_impl, keep, dev.index)
+            plan = self._plans.get(key)
+            if plan is None and not exact:
+                fits = [k for k in self._plans if k[1:] == key[1:] and k[0] > batch]
+                if fits:
+                    key = min(fits)
+                    plan = self._plans[key]
+            if plan is None:
+                with torch.cuda.device(dev):
+                    plan = ForwardPlan(self._full_state(), self.cfg, batch, self.precision, dev, size, self.gemm_impl, keep)
+                    if self.autotune and os.environ.get("CROG_AUTOTUNE", "1") != "0":
+                        plan.autotune()
+                self._plans[key] = plan
+                per_dev = [k for k in self._plans if k[-1] == dev.index]
+                while len(per_dev) > max(self.max_plans, 1):  # least recently used plan of this device goes, with its graph
+                    old = per_dev.pop(0)
+                    self._graphs.pop(id(self._plans.pop(old)), None)
+            self._plans.move_to_end(key)
         return plan
+
+    def prepare(self, batch: int, size: Optional[int] = None):
+        """Build the plan for ``batch`` (weight packing, buffer allocation, per-layer tile autotune: about 2 s at batch 64)
+        and capture its CUDA graph now, instead of inside the first ``forward``.  Call once with the largest batch the
+        loader yields; smaller batches reuse that plan."""
+        plan = self.plan_for(batch, size or self.cfg.input_size)
+        with torch.cuda.device(plan.dev):
+            self._run(plan)
+            torch.cuda.synchronize()
+        return self
+
+    def input_buffer(self, batch: int, size: Optional[int] = None) -> torch.Tensor:
+        """The float32 [B,3,S,S] tensor the plan for this batch reads.  A producer on the same stream (e.g.
+        ``utils.warp.preprocess_images(..., out=model.input_buffer(B))``) can fill it in place and pass it to ``forward``,
+        which then skips its 2 MB-per-sample device-to-device input copy."""
+        return self.plan_for(batch, size or self.cfg.input_size, exact=False).img[:batch]
 
     # ------------------------------------------------------------------ forward
     @torch.no_grad()
@@ -127,12 +198,13 @@ class CROG(nn.Module):
         if word.dim() != 2 or word.shape[0] != img.shape[0] or word.shape[1] != self.cfg.word_len:
             raise RuntimeError(f"expected word of shape [{img.shape[0]},{self.cfg.word_len}], got {tuple(word.shape)}")
         B, S = img.shape[0], img.shape[-1]
-        plan = self.plan_for(B, S)
+        plan = self.plan_for(B, S, exact=False)
         with torch.cuda.device(plan.dev):
-            plan.img.copy_(img, non_blocking=True)
-            plan.word.copy_(word, non_blocking=True)
+            if img.data_ptr() != plan.img.data_ptr():  # input_buffer(): the producer wrote the plan's input in place
+                plan.img[:B].copy_(img, non_blocking=True)
+            plan.word[:B].copy_(word, non_blocking=True)  # rows >= B keep an earlier batch: independent samples, results unused
             self._run(plan)
-            out = plan.out.clone()
+            out = plan.out[:, :B].clone()
         maps = tuple(out[i] for i in range(plan.NH))
         if self.use_grasp_masks:
             return maps, (mask, grasp_qua_mask, grasp_sin_mask, grasp_cos_mask, grasp_wid_mask)
@@ -145,10 +217,13 @@ class CROG(nn.Module):
         key = id(plan)
         g = self._graphs.get(key)
         if g is None:
-            plan.run()  # eager warm-up: sets kernel attributes, faults surface here with op context
-            torch.cuda.synchronize()
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
-                plan.run()
-            self._graphs[key] = g
+            with self._lock:  # one capture at a time (DataParallel replicas run forward from worker threads)
+                g = self._graphs.get(key)
+                if g is None:
+                    plan.run()  # eager warm-up: sets kernel attributes, faults surface here with op context
+                    torch.cuda.synchronize()
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g, capture_error_mode="thread_local"):
+                        plan.run()
+                    self._graphs[key] = g
         g.replay()

@@ -434,7 +434,7 @@ class ForwardPlan:
         rows = B * Lt
         x = self.new(0, 0, D, dtype=torch.float32, rows=rows)
         emb, pos = self.f32(sd["backbone.token_embedding.weight"]), self.f32(sd["backbone.positional_embedding"])
-        a = (self.word.data_ptr(), emb.data_ptr(), pos.data_ptr(), x.ptr, B, Lt, D)
+        a = (self.word.data_ptr(), emb.data_ptr(), pos.data_ptr(), x.ptr, B, Lt, D, emb.shape[0])
         self._add("text.embed", lambda s: L.check(lib.crog_embed_tokens(*a, s)))
         h = self.new(0, 0, D, rows=rows)
         qkv = self.new(0, 0, 3 * D, rows=rows)

@@ -269,3 +269,43 @@ def make_ssg_output_dict(cfg, n_confident: int = 8, seed: int = 6, proto_hw: int
     # make the quality channel of the confident instances peaky enough to pass threshold_abs = 0.4 after smoothing
     return {"anchors": anchors.view(-1).tolist(), "protos": protos.unsqueeze(0), "cls_pred": torch.softmax(logits, -1).unsqueeze(0),
             "box_pred": box.unsqueeze(0), "ins_coef_pred": coef.unsqueeze(0), "grasp_coef_pred": gcoef.unsqueeze(0)}
+
+
+# ====================================================================== one seeded GLOBAL batch (multi-GPU J gate)
+def make_global_samples(lo: int, hi: int, word_len: int, size: int = 416, max_gt: int = 64, base_seed: int = 9000):
+    """Samples [lo, hi) of ONE seeded global batch.  Sample i depends on ``base_seed + i`` only, so every rank of every
+    world size produces the same bytes for it: the J counters summed over 1, 2, 4 or 8 shards must be identical
+    (shards from crog_b200.engine.shard_range).  Returns (img, word, gt, gt_count)."""
+    imgs, words, gts, cnts = [], [], [], []
+    for i in range(lo, hi):
+        img, word = make_inputs(1, word_len, size, seed_img=base_seed + 3 * i, seed_txt=base_seed + 3 * i + 1)
+        gt, cnt = make_gt_rects(1, max_gt, seed=base_seed + 3 * i + 2, size=size)
+        imgs.append(img); words.append(word); gts.append(gt); cnts.append(cnt)
+    return torch.cat(imgs), torch.cat(words), np.concatenate(gts), np.concatenate(cnts)
+
+
+def plant_gt_near_predictions(gt: np.ndarray, cnt: np.ndarray, grasps: np.ndarray, n_peaks: np.ndarray, lo: int,
+                              base_seed: int = 9000) -> np.ndarray:
+    """Random-init weights put the predicted grasps nowhere near random ground truth (J@1 = 0 is a poor parity witness).
+    Overwrites GT row 0 of about half the samples with a rectangle near the sample's own top-1 prediction and of another
+    quarter near its 3rd prediction (J@5 hit without a J@1 hit), jittered by a per-sample seeded RNG, so that both outcomes
+    of both counters occur.  A deterministic function of (sample index, the sample's decoded grasps)."""
+    gt = gt.copy()
+    for b in range(gt.shape[0]):
+        rng = np.random.default_rng(base_seed + 7919 * (lo + b))
+        u = rng.random()
+        k = 0 if u < 0.5 else (2 if u < 0.75 else -1)
+        if k < 0 or n_peaks[b] <= k:
+            continue
+        x, y, w, _, a = grasps[b, k]
+        gt[b, 0] = [x + rng.uniform(-6, 6), y + rng.uniform(-6, 6), min(max(w + rng.uniform(-12, 12), 4.0), 130.0),
+                    rng.uniform(10, 40), a + rng.uniform(-22, 22), 1.0]
+    return gt
+
+
+def make_frames_u8(batch: int, h: int = 480, w: int = 640, seed: int = 11) -> torch.Tensor:
+    """OCID-VLG sized camera frames: uint8 RGB [B, h, w, 3] (smooth blobs + noise; content is irrelevant to throughput)."""
+    g = torch.Generator().manual_seed(seed)
+    base = torch.rand((batch, h // 16, w // 16, 3), generator=g).permute(0, 3, 1, 2)
+    up = torch.nn.functional.interpolate(base, size=(h, w), mode="bilinear", align_corners=False).permute(0, 2, 3, 1)
+    return (up * 200 + torch.rand((batch, h, w, 3), generator=g) * 55).clamp(0, 255).to(torch.uint8).contiguous()

@@ -69,8 +69,25 @@ def invert_affine(M) -> np.ndarray:
     return M
 
 
+class DeviceAffine:
+    """Affine matrices already inverted (invert_affine) and resident on the device as [B,6] float64: what the kernels
+    consume.  Build once with ``device_affine(mats, B, dev)`` and pass it wherever ``mats`` is accepted, so a streaming
+    loop does not pay a host inversion + pageable H2D copy (a stream synchronisation) per batch."""
+
+    def __init__(self, t: torch.Tensor):
+        self.t = t
+
+
+def device_affine(mats, B: int, dev) -> DeviceAffine:
+    return DeviceAffine(_minv_tensor(mats, B, torch.device(dev)))
+
+
 def _minv_tensor(mats, B: int, dev) -> torch.Tensor:
     """One 2x3 matrix (shared) or B of them, as the caller would pass to cv2.warpAffine -> device [B,6] float64."""
+    if isinstance(mats, DeviceAffine):
+        if mats.t.shape != (B, 6) or mats.t.device != dev:
+            raise RuntimeError(f"DeviceAffine of shape {tuple(mats.t.shape)} on {mats.t.device} does not fit batch {B} on {dev}")
+        return mats.t
     if torch.is_tensor(mats):
         mats = mats.detach().cpu().numpy()
     m = np.asarray(mats, dtype=np.float64)
@@ -106,9 +123,10 @@ def warp_affine_cubic(src: torch.Tensor, mats, dsize: Tuple[int, int], border_va
 
 
 def preprocess_images(img_u8: torch.Tensor, mats, input_size: Tuple[int, int] = (416, 416),
-                      mean: Sequence[float] = CLIP_MEAN, std: Sequence[float] = CLIP_STD) -> torch.Tensor:
+                      mean: Sequence[float] = CLIP_MEAN, std: Sequence[float] = CLIP_STD, out: torch.Tensor = None) -> torch.Tensor:
     """utils/dataset.py:843-866 for a batch of equally sized images: img_u8 [B,Ho,Wo,3] uint8 RGB CUDA, ``mats`` the
-    forward letterbox matrices (``get_transform_mat(...)[0]``) -> [B,3,H,W] float32 normalised."""
+    forward letterbox matrices (``get_transform_mat(...)[0]``) -> [B,3,H,W] float32 normalised (written into ``out`` when
+    given, e.g. ``CROG.input_buffer(B)`` so the forward reads it in place)."""
     import ctypes as C
 
     lib = L.lib()
@@ -119,7 +137,10 @@ def preprocess_images(img_u8: torch.Tensor, mats, input_size: Tuple[int, int] = 
     B, Ho, Wo, _ = img_u8.shape
     Sh, Sw = int(input_size[0]), int(input_size[1])
     minv = _minv_tensor(mats, B, dev)
-    out = torch.empty((B, 3, Sh, Sw), dtype=torch.float32, device=dev)
+    if out is None:
+        out = torch.empty((B, 3, Sh, Sw), dtype=torch.float32, device=dev)
+    elif tuple(out.shape) != (B, 3, Sh, Sw) or out.dtype != torch.float32 or not out.is_contiguous() or out.device != dev:
+        raise RuntimeError(f"out must be a contiguous float32 [{B},3,{Sh},{Sw}] tensor on {dev}")
     border = (C.c_double * 3)(*[float(np.float64(m) * 255) for m in CLIP_MEAN])  # dataset.py:860
     mean32 = torch.tensor(list(mean), dtype=torch.float32).numpy()
     std32 = torch.tensor(list(std), dtype=torch.float32).numpy()

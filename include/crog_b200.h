@@ -161,9 +161,11 @@ int crog_layernorm_chain(const void* x, int32_t x_dtype, const float* g1, const 
                          float* y, const float* g2, const float* b2, void* z, int32_t z_dtype, int64_t rows,
                          int32_t D, float eps, void* stream);
 
-/* Token embedding + positional embedding (clip.py:440-443): out[b*L+l] = emb[word[b,l]] + pos[l], fp32. */
+/* Token embedding + positional embedding (clip.py:440-443): out[b*L+l] = emb[word[b,l]] + pos[l], fp32.
+ * `vocab` = rows of emb; an id outside [0, vocab) is a device-side assertion failure (message + trap), as with the
+ * reference's nn.Embedding on CUDA — never a silent out-of-bounds read. */
 int crog_embed_tokens(const int64_t* word, const float* emb, const float* pos, float* out, int32_t B,
-                      int32_t L, int32_t D, void* stream);
+                      int32_t L, int32_t D, int32_t vocab, void* stream);
 /* EOT gather (clip.py:450-451): out[b] = x[b*L + argmax_l word[b,l]]. */
 int crog_gather_eot(const int64_t* word, const void* x, int32_t x_dtype, void* out, int32_t out_dtype,
                     int32_t B, int32_t L, int32_t D, void* stream);

@@ -220,7 +220,7 @@ def test_embed_gather_cast_split():
     word = word.to(DEV)
     emb, pos = _rand(49408, D, seed=24), _rand(77, D, seed=25)
     x = torch.zeros(B * Lt, D, device=DEV)
-    L.check(lib.crog_embed_tokens(word.data_ptr(), emb.data_ptr(), pos.data_ptr(), x.data_ptr(), B, Lt, D, L.stream_ptr()))
+    L.check(lib.crog_embed_tokens(word.data_ptr(), emb.data_ptr(), pos.data_ptr(), x.data_ptr(), B, Lt, D, emb.shape[0], L.stream_ptr()))
     torch.cuda.synchronize()
     assert torch.equal(x.view(B, Lt, D), emb[word] + pos[:Lt])
     eot = torch.zeros(B, D, device=DEV, dtype=BF)

@@ -217,3 +217,44 @@ def test_engine_stream_matches_step():
     for (n1, g1, f1), (n2, g2, f2) in zip(want, got):
         assert torch.equal(n1, n2) and torch.equal(g1, g2) and torch.equal(f1, f2)
     assert torch.equal(ev1.counters.cpu(), ev2.counters.cpu())
+
+
+def test_ragged_batch_reuses_big_plan_and_lru_bound():
+    """A batch smaller than a prepared plan runs in that plan's first rows (no new buffers, no autotune) with bit-identical
+    per-sample results; the plan cache is a bounded LRU; prepare() moves build + autotune + graph capture out of forward."""
+    Lw = 17
+    cfg, sd, model = _build(Lw, "perturbed", "bf16")
+    model.prepare(4)
+    assert len(model._plans) == 1 and len(model._graphs) == 1
+    img, word = synth.make_inputs(4, Lw)
+    full, _ = model(img.cuda(), word.cuda())
+    part, _ = model(img[:3].cuda(), word[:3].cuda())  # ragged last batch of a loader
+    assert len(model._plans) == 1, "the 3-sample batch must reuse the 4-sample plan"
+    assert all(p.shape[0] == 3 and torch.equal(p, f[:3]) for p, f in zip(part, full))
+    # in-place input: a producer fills model.input_buffer(B) and forward skips its device-to-device copy
+    buf = model.input_buffer(2)
+    buf.copy_(img[1:3].cuda())
+    two, _ = model(buf, word[1:3].cuda())
+    assert all(torch.equal(t, f[1:3]) for t, f in zip(two, full))
+    # LRU: at most max_plans plans per device stay alive
+    model.max_plans = 2
+    model.autotune = False
+    for b in (5, 6, 7):
+        model.plan_for(b, 416)
+    assert len(model._plans) == 2 and sorted(k[0] for k in model._plans) == [6, 7]
+    assert len(model._graphs) == 0  # the evicted 4-sample plan took its captured graph with it
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs (torch.nn.DataParallel replicas)")
+def test_dataparallel_two_gpus_matches_single():
+    """INTEGRATION.md's ``torch.nn.DataParallel(model).cuda()`` (reference test_crog.py:70) with two visible devices: every
+    replica builds its own per-device plan from attribute-held parameter copies; results equal the single-GPU run."""
+    Lw = 17
+    cfg, sd, model = _build(Lw, "perturbed", "bf16")
+    img, word = synth.make_inputs(4, Lw)
+    single, _ = model(img.cuda(), word.cuda())
+    dp = torch.nn.DataParallel(model, device_ids=[0, 1])
+    multi, _ = dp(img.cuda(), word.cuda())
+    torch.cuda.synchronize()
+    assert all(torch.equal(a.cpu(), b.cpu()) for a, b in zip(single, multi))
+    assert {k[-1] for k in model._plans} == {0, 1}
