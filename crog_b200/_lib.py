@@ -12,6 +12,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 SO_PATH = os.environ.get("CROG_B200_SO") or os.path.join(_HERE, "lib", "libcrog_b200.so")  # override: A/B of two builds
 
+ABI_VERSION = 4  # crog_abi_version() of the library these signatures were written for
 F32, BF16 = 0, 1
 ACT_NONE, ACT_RELU, ACT_QUICKGELU, ACT_TANH = 0, 1, 2, 3
 IMPL_AUTO, IMPL_SIMT, IMPL_TCGEN05 = 0, 1, 2
@@ -38,6 +39,7 @@ class CrogGemm(C.Structure):
         ("a2", C.c_void_p), ("a2_ld", C.c_int32), ("cin2", C.c_int32),
         ("row_stats_out", C.c_void_p), ("row_stats_in", C.c_void_p), ("row_stats_chunks", C.c_int32),
         ("row_stats_width", C.c_int32), ("row_stats_eps", C.c_float),
+        ("max_ctas", C.c_int32), ("tap_mask", C.c_int32),
     ]
 
 
@@ -49,7 +51,7 @@ SIGNATURES = {
     "crog_check_device": (C.c_int, []),
     "crog_gemm": (C.c_int, [C.POINTER(CrogGemm), _P]),
     "crog_resample": (C.c_int, [_P, _I, _I, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
-    "crog_stem_conv1": (C.c_int, [_P, _I, _I, _I, _P, _P, _P, _I, _P, _I, _I, _P]),
+    "crog_stem_conv1": (C.c_int, [_P, _I, _I, _I, _P, _P, _P, _I, _P, _I, _I, _I, _P]),
     "crog_layernorm": (C.c_int, [_P, _I, _P, _P, _P, _P, _I, _L, _I, _F, _P]),
     "crog_layernorm_chain": (C.c_int, [_P, _I, _P, _P, _P, _P, _P, _P, _P, _I, _L, _I, _F, _P]),
     "crog_embed_tokens": (C.c_int, [_P, _P, _P, _P, _I, _I, _I, _I, _P]),
@@ -71,7 +73,7 @@ SIGNATURES = {
     "crog_ssg_nms_workspace_bytes": (C.c_int64, [_I, _I]),
     "crog_ssg_fast_nms": (C.c_int, [_P, _P, _P, _I, _I, _F, _I, _I, _F, _P, _P, _P, _P, _P, _P]),
     "crog_ssg_detect": (C.c_int, [_P, _P, _P, _I, _I, _F, _F, _I, _I, _F, _P, _P, _P, _P, _P, _P, _P, _P]),
-    "crog_ssg_masks": (C.c_int, [_P, _I, _I, _I, _P, _P, _P, _P, _P, _I, _P, _P, _I, _I, _I, _P]),
+    "crog_ssg_masks": (C.c_int, [_P, _I, _I, _I, _P, _P, _P, _P, _P, _I, _P, _P, _I, _I, _I, _I, _P]),
     "crog_gaussian": (C.c_int, [_P, _P, _P, _I, _I, _I, _P, _I, _P, _I, _I, _P]),
     "crog_warp_affine_cubic_f32": (C.c_int, [_P, _I, _I, _I, _I, _P, _P, _I, _I, _F, _P]),
     "crog_preprocess_u8": (C.c_int, [_P, _I, _I, _I, _P, _P, _I, _I, _P, _P, _P, _P]),
@@ -90,6 +92,10 @@ def load() -> C.CDLL:
             raise CrogError(f"{SO_PATH} is missing: run `python -m crog_b200.build` (or __graft_entry__.build()). "
                             "crog_b200 has no CPU or PyTorch fallback.")
         lib = C.CDLL(SO_PATH)
+        lib.crog_abi_version.restype = C.c_int
+        if lib.crog_abi_version() != ABI_VERSION:  # a stale build would be called with shifted arguments
+            raise CrogError(f"{SO_PATH} has ABI version {lib.crog_abi_version()}, this package binds version {ABI_VERSION}: "
+                            "rebuild with `python -m crog_b200.build`")
         for name, (res, args) in SIGNATURES.items():
             fn = getattr(lib, name)  # AttributeError if the .so does not export a declared symbol
             fn.restype = res

@@ -99,7 +99,8 @@ __global__ void __launch_bounds__(256) resample_kernel(const T* __restrict__ in,
 template <typename T>
 __global__ void __launch_bounds__(128) stem_conv1_kernel(const float* __restrict__ img, int B, int Hin, int Win,
                                                           const float* __restrict__ w, const float* __restrict__ scale,
-                                                          const float* __restrict__ bias, int cout, T* __restrict__ out, int out_ld) {
+                                                          const float* __restrict__ bias, int cout, T* __restrict__ out, int out_ld,
+                                                          int pairs) {
   extern __shared__ __align__(16) float sw[];  // [27][cout] + scale + bias
   pdl_launch();  // the weights below are constants of the plan: staging them overlaps the predecessor's tail
   for (int i = threadIdx.x; i < 27 * cout; i += blockDim.x) {
@@ -157,9 +158,15 @@ __global__ void __launch_bounds__(128) stem_conv1_kernel(const float* __restrict
       v0[j] = fmaxf(v0[j] * sc + bi, 0.f);
       v1[j] = fmaxf(v1[j] * sc + bi, 0.f);
     }
-    T* o = out + pix_row(b, oy, ox, OH, OW, 1) * out_ld + c0;
-    store8(o, v0);
-    if (ox + 1 < OW) store8(o + out_ld, v1);
+    if (pairs) {  // pixel-pair layout: this thread's two pixels are one row of the zero-haloed [OH+2, OW/2+2] grid
+      T* o = out + ((long long)(b * (OH + 2) + oy + 1) * (OWP + 2) + oxp + 1) * out_ld + c0;
+      store8(o, v0);
+      store8(o + cout, v1);
+    } else {
+      T* o = out + pix_row(b, oy, ox, OH, OW, 1) * out_ld + c0;
+      store8(o, v0);
+      if (ox + 1 < OW) store8(o + out_ld, v1);
+    }
   }
 }
 
@@ -503,16 +510,18 @@ extern "C" int crog_resample(const void* in, int32_t in_ld, int32_t in_padded, v
 }
 
 extern "C" int crog_stem_conv1(const float* img, int32_t B, int32_t Hin, int32_t Win, const float* w, const float* scale,
-                               const float* bias, int32_t cout, void* out, int32_t out_ld, int32_t out_dtype, void* stream) {
+                               const float* bias, int32_t cout, void* out, int32_t out_ld, int32_t out_dtype, int32_t pixel_pairs,
+                               void* stream) {
   CROG_REQUIRE(Hin % 2 == 0 && Win % 2 == 0 && out_ld % 8 == 0 && cout <= out_ld && cout % 8 == 0, CROG_E_BADSHAPE, "stem_conv1: bad shape");
+  CROG_REQUIRE(!pixel_pairs || (Win % 4 == 0 && 2 * cout <= out_ld), CROG_E_BADSHAPE, "stem_conv1: the pixel-pair layout needs an even output width and out_ld >= 2*cout");
   const long long total = (long long)B * (Hin / 2) * ((Win / 2 + 1) / 2) * (cout / 8);  // (pixel pair, 8-channel group) threads
   if (total == 0) return CROG_OK;
   const int g = grid_for(total, 128);
   const size_t sm = (size_t)(29 * cout) * sizeof(float);
   if (out_dtype == CROG_F32)
-    crog_launch(stem_conv1_kernel<float>, dim3(g), dim3(128), sm, (cudaStream_t)stream, img, B, Hin, Win, w, scale, bias, cout, (float*)out, out_ld);
+    crog_launch(stem_conv1_kernel<float>, dim3(g), dim3(128), sm, (cudaStream_t)stream, img, B, Hin, Win, w, scale, bias, cout, (float*)out, out_ld, pixel_pairs);
   else
-    crog_launch(stem_conv1_kernel<bf16>, dim3(g), dim3(128), sm, (cudaStream_t)stream, img, B, Hin, Win, w, scale, bias, cout, (bf16*)out, out_ld);
+    crog_launch(stem_conv1_kernel<bf16>, dim3(g), dim3(128), sm, (cudaStream_t)stream, img, B, Hin, Win, w, scale, bias, cout, (bf16*)out, out_ld, pixel_pairs);
   CROG_LAUNCH_OK("stem_conv1");
   return CROG_OK;
 }

@@ -187,6 +187,8 @@ __global__ void __launch_bounds__(64 + EPI_WARPS * 32, 1) gemm_tc_kernel(const _
         tc_fence_after();
         const uint32_t tacc = tmem_base + as * BN;
         if constexpr (CONV3) {
+          const uint32_t tmask = g.tap_mask ? (uint32_t)g.tap_mask : 0x1ffu;
+          uint32_t acc_on = 0;  // 0 until the tile's first MMA has been issued
           for (int ky = 0; ky < 3; ++ky, ++kbg) {
             const int s = kbg % STAGES, it = kbg / STAGES;
             mbar_wait(full0 + 8 * s, it & 1);
@@ -194,6 +196,7 @@ __global__ void __launch_bounds__(64 + EPI_WARPS * 32, 1) gemm_tc_kernel(const _
             const uint32_t sa = smem_u32(smem + s * L::STAGE_BYTES);
 #pragma unroll
             for (int kx = 0; kx < 3; ++kx) {
+              if (!((tmask >> (ky * 3 + kx)) & 1u)) continue;  // tap not contracted (its weights are zero)
               // rows [kx, kx + 128) of the band: the SWIZZLE_128B XOR is a function of the absolute shared address
               // (descriptor base_offset = 0), so a start address moved by whole 128-byte rows still reads the
               // pattern TMA wrote (verified on B200: tests/test_gpu_kernels.py::test_conv3x3_padded)
@@ -201,7 +204,8 @@ __global__ void __launch_bounds__(64 + EPI_WARPS * 32, 1) gemm_tc_kernel(const _
               const uint64_t db = make_sdesc(smem_u32(smem + L::BRES_OFF + (ky * 3 + kx) * L::B_BYTES));
 #pragma unroll
               for (int k = 0; k < BK / UMMA_K; ++k)
-                tc_mma_bf16(tacc, da + (uint64_t)(k * UMMA_K * 2 / 16), db + (uint64_t)(k * UMMA_K * 2 / 16), idesc, (ky | kx | k) != 0);
+                tc_mma_bf16(tacc, da + (uint64_t)(k * UMMA_K * 2 / 16), db + (uint64_t)(k * UMMA_K * 2 / 16), idesc, acc_on | (uint32_t)k);
+              acc_on = 1;
             }
             tc_commit(empty0 + 8 * s);
           }
@@ -594,7 +598,8 @@ int launch(const CrogGemm* g, cudaStream_t stream) {
   if (total == 0) return CROG_OK;
   if constexpr (PAIR) {
     // one cluster of two CTAs (an SM pair of one TPC) per tile stream
-    const int pairs = total < g_num_sms / 2 ? total : g_num_sms / 2;
+    int pairs = total < g_num_sms / 2 ? total : g_num_sms / 2;
+    if (g->max_ctas > 0 && pairs > g->max_ctas / 2) pairs = g->max_ctas / 2 > 0 ? g->max_ctas / 2 : 1;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(2 * pairs); cfg.blockDim = dim3(L::NUM_THREADS); cfg.dynamicSmemBytes = L::TOTAL; cfg.stream = stream;
     cudaLaunchAttribute at[1];
@@ -604,7 +609,8 @@ int launch(const CrogGemm* g, cudaStream_t stream) {
     CROG_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, STAGES, NBUF, MODE, CONV3, EPI_WARPS, PAIR>, tmA, tmA2, tmB, tmOut, tmRes, *g, n_tiles, total));
     return CROG_OK;
   }
-  const int grid = total < g_num_sms ? total : g_num_sms;
+  int grid = total < g_num_sms ? total : g_num_sms;
+  if (g->max_ctas > 0 && grid > g->max_ctas) grid = g->max_ctas;
   crog_launch(gemm_tc_kernel<BN, STAGES, NBUF, MODE, CONV3, EPI_WARPS, PAIR>, dim3(grid), dim3(L::NUM_THREADS), L::TOTAL, stream, tmA, tmA2, tmB, tmOut, tmRes, *g, n_tiles, total);
   CROG_LAUNCH_OK("gemm_tc");
   return CROG_OK;

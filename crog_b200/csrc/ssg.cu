@@ -371,7 +371,7 @@ __global__ void __launch_bounds__(256) ssg_lowres_kernel(const float* __restrict
 // planes [P][h][w] -> [P][oh][ow]; planes whose bit is set in bin_mask (by plane % planes_per_det) are thresholded > 0.5.
 __global__ void __launch_bounds__(256) bilinear_crop_kernel(const float* __restrict__ in, int h, int w, float* __restrict__ out, int oh,
                                                             int ow, int S, const int* __restrict__ n_planes, int planes_per_det,
-                                                            uint32_t bin_mask) {
+                                                            uint32_t bin_mask, int det_stride) {
   const int pl = blockIdx.z;
   if (n_planes && pl >= *n_planes * planes_per_det) return;
   const int ox = blockIdx.x * blockDim.x + threadIdx.x, oy = blockIdx.y;
@@ -384,8 +384,8 @@ __global__ void __launch_bounds__(256) bilinear_crop_kernel(const float* __restr
   const float v = hy * (hx * __ldg(src + y0 * w + x0) + lx * __ldg(src + y0 * w + x1)) + ly * (hx * __ldg(src + y1 * w + x0) + lx * __ldg(src + y1 * w + x1));
   const int d = pl / planes_per_det, k = pl % planes_per_det;
   const bool bin = (bin_mask >> k) & 1u;
-  // output is map-major: [planes_per_det][gridDim.z / planes_per_det detections][oh][ow], so each map type is one contiguous batch
-  out[(((long long)k * (gridDim.z / planes_per_det) + d) * oh + oy) * ow + ox] = bin ? (v > 0.5f ? 1.f : 0.f) : v;
+  // output is map-major: [planes_per_det][det_stride detections][oh][ow], so each map type is one contiguous batch
+  out[(((long long)k * det_stride + d) * oh + oy) * ow + ox] = bin ? (v > 0.5f ? 1.f : 0.f) : v;
 }
 
 // ------------------------------------------------------------------ Gaussian (sigma = 2 -> 17 taps), float64 accumulation, float32 per pass
@@ -518,15 +518,17 @@ extern "C" int crog_ssg_detect(const float* cls, const float* box, const float* 
 
 extern "C" int crog_ssg_masks(const float* protos, int32_t h, int32_t w, int32_t num_protos, const float* coef, const float* gcoef,
                               const float* boxes, const int32_t* det_anchor, const int32_t* det_n, int32_t max_det, float* lowres,
-                              float* out, int32_t out_h, int32_t out_w, int32_t resize_to, void* stream) {
+                              float* out, int32_t out_det_stride, int32_t out_h, int32_t out_w, int32_t resize_to, void* stream) {
   CROG_REQUIRE(num_protos % 4 == 0 && num_protos <= 256 && aligned16(protos), CROG_E_BADSHAPE, "ssg_masks: num_protos %d", num_protos);
   CROG_REQUIRE(out_h <= resize_to && out_w <= resize_to && max_det * 5 <= 65535, CROG_E_BADSHAPE, "ssg_masks: bad output extent");
+  if (out_det_stride <= 0) out_det_stride = max_det;
+  CROG_REQUIRE(max_det >= 1, CROG_E_BADSHAPE, "ssg_masks: max_det");
   cudaStream_t s = (cudaStream_t)stream;
   dim3 g1((h * w + 255) / 256, max_det);
   ssg_lowres_kernel<<<g1, 256, 5 * num_protos * sizeof(float), s>>>(protos, h, w, num_protos, coef, gcoef, boxes, det_anchor, det_n, lowres);
   CROG_LAUNCH_OK("ssg_lowres");
   dim3 g2((out_w + 255) / 256, out_h, max_det * 5);
-  bilinear_crop_kernel<<<g2, 256, 0, s>>>(lowres, h, w, out, out_h, out_w, resize_to, det_n, 5, 1u);
+  bilinear_crop_kernel<<<g2, 256, 0, s>>>(lowres, h, w, out, out_h, out_w, resize_to, det_n, 5, 1u, out_det_stride);
   CROG_LAUNCH_OK("ssg_resize");
   return CROG_OK;
 }

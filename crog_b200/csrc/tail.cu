@@ -75,7 +75,7 @@ __device__ void warp_select_top(unsigned long long* list, int n, int keep, unsig
 // only feed their neighbours through shuffles, so no lane needs extra halo loads.  Rows are software-pipelined five at a
 // time (the next five float4 loads are in flight while the current five are processed).
 __global__ void __launch_bounds__(256, 2) peak_scan_generic_kernel(const float* __restrict__ q, int H, int W, float thr, int nwarps,
-                                                                int BAND, uint8_t* __restrict__ ws) {
+                                                                int BAND, int tsel, uint8_t* __restrict__ ws) {
   extern __shared__ unsigned long long s_lists[];  // [warps][CAPW + TSEL]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp >= nwarps) return;
@@ -145,10 +145,10 @@ __global__ void __launch_bounds__(256, 2) peak_scan_generic_kernel(const float* 
         const bool k2 = owner && ctr.z == vm.z && ctr.z > thr && c0 + 2 < W - 2;
         const bool k3 = owner && ctr.w == vm.w && ctr.w > thr && c0 + 3 < W - 2;
         if (__ballot_sync(0xffffffffu, k0 | k1 | k2 | k3)) {
-          if (count + 128 > CAPW) {  // make room: keep the best TSEL so far
+          if (count + 128 > CAPW) {  // make room: keep the best tsel so far
             __syncwarp();
-            warp_select_top(list, count, TSEL, top, lane);
-            count = TSEL; truncated = 1;
+            warp_select_top(list, count, tsel, top, lane);
+            count = tsel; truncated = 1;
           }
           const uint32_t lt = (1u << lane) - 1u;
           const bool kk[4] = {k0, k1, k2, k3};
@@ -166,13 +166,13 @@ __global__ void __launch_bounds__(256, 2) peak_scan_generic_kernel(const float* 
     for (int u = 0; u < 5; ++u) cur[u] = nxt[u];
   }
   __syncwarp();
-  if (count > TSEL) { warp_select_top(list, count, TSEL, top, lane); count = TSEL; truncated = 1; }
+  if (count > tsel) { warp_select_top(list, count, tsel, top, lane); count = tsel; truncated = 1; }
   nonconst = __any_sync(0xffffffffu, nonconst);
   uint8_t* seg = ws + ((long long)(b * nbands + band) * nwarps + warp) * SEG_BYTES;
   if (lane == 0) {
     SegHeader h;
     h.count = count; h.truncated = truncated;
-    h.worst_kept = truncated ? list[TSEL - 1] : 0ull;
+    h.worst_kept = truncated ? list[tsel - 1] : 0ull;
     h.nonconst = nonconst; h.pad[0] = h.pad[1] = h.pad[2] = 0;
     *reinterpret_cast<SegHeader*>(seg) = h;
   }
@@ -193,8 +193,14 @@ __global__ void __launch_bounds__(256, 2) peak_scan_generic_kernel(const float* 
 //  * Per lane-row (4 pixels): one LDS.128, four shuffles, six FMNMX3 for the horizontal maxima, eight for the
 //    vertical ones, eight compares, one vote.
 //  * The "trivial image" rule (A.1 step 2) costs nothing unless the map's four probe pixels are equal (TRACK).
+//  * Density independence: a warp keeps only its best `tsel` keys in the end, so once it has selected them for the first
+//    time (after tsel + SEL_SLACK candidates) the worst kept key is a running cut that can only rise: later candidates
+//    below it are dropped by one float compare instead of being appended and selected away (they could never survive the
+//    final selection, so the segment written out is unchanged).  On iid-uniform maps, where 4 % of all pixels are 5x5
+//    maxima above the threshold, the appends decay like tsel / candidates seen and the scan stays a streaming kernel.
 constexpr int SCAN_R = 5;    // rows per stage (= ring length, so ring slots are compile-time)
 constexpr int SCAN_NST = 4;  // stages
+constexpr int SEL_SLACK = 64; // candidates a warp appends beyond its tsel kept keys before it selects again
 
 __device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -205,8 +211,10 @@ template <bool TRACK>
 __device__ __forceinline__ void scan_rows(const float* stage0, uint32_t full0, uint32_t empty0, int W, int row0, int nrows, int y0,
                                           int y1, int ccol, int c0, bool owner, float tx, float ty, float tz, float tw, float p0,
                                           int lane, unsigned long long* list, unsigned long long* top, int& count,
-                                          int& truncated, int& nonconst) {
+                                          int& truncated, int& nonconst, const int tsel) {
   const float NEG = -INFINITY;
+  unsigned long long cut = 0ull;  // worst kept key after the latest selection (0: nothing dropped yet)
+  float cutv = NEG;
   float4 raw[5], hm[5];
 #pragma unroll
   for (int u = 0; u < 5; ++u) { raw[u] = make_float4(NEG, NEG, NEG, NEG); hm[u] = raw[u]; }
@@ -238,23 +246,37 @@ __device__ __forceinline__ void scan_rows(const float* stage0, uint32_t full0, u
         const float vy = max3(max3(hm[0].y, hm[1].y, hm[2].y), hm[3].y, hm[4].y);
         const float vz = max3(max3(hm[0].z, hm[1].z, hm[2].z), hm[3].z, hm[4].z);
         const float vw = max3(max3(hm[0].w, hm[1].w, hm[2].w), hm[3].w, hm[4].w);
-        const bool k0 = a0 && ctr.x == vx, k1 = a1 && ctr.y == vy;
-        const bool k2 = a2 && ctr.z == vz, k3 = a3 && ctr.w == vw;
+        // (values equal to the cut's pass here; the exact 64-bit key comparison follows in the append path)
+        const bool k0 = a0 && ctr.x == vx && ctr.x >= cutv, k1 = a1 && ctr.y == vy && ctr.y >= cutv;
+        const bool k2 = a2 && ctr.z == vz && ctr.z >= cutv, k3 = a3 && ctr.w == vw && ctr.w >= cutv;
         if (__any_sync(0xffffffffu, k0 | k1 | k2 | k3)) {
-          if (count + 128 > CAPW) {  // make room: keep the best TSEL so far
-            __syncwarp();
-            warp_select_top(list, count, TSEL, top, lane);
-            count = TSEL; truncated = 1;
-          }
-          const uint32_t lt = (1u << lane) - 1u;
-          const bool kk[4] = {k0, k1, k2, k3};
-          const float cv[4] = {ctr.x, ctr.y, ctr.z, ctr.w};
+          // exact filter on the 64-bit keys (value, then row-major index): a candidate that ties the cut's value but
+          // comes later in the map is below the cut, so a plateau at the top value stops appending after tsel entries
           const int rc = row0 + idx - 2;
+          const float cv[4] = {ctr.x, ctr.y, ctr.z, ctr.w};
+          unsigned long long key[4];
+          bool keep[4] = {k0, k1, k2, k3};
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            const uint32_t m = __ballot_sync(0xffffffffu, kk[j]);
-            if (kk[j]) list[count + __popc(m & lt)] = make_key(cv[j], rc * W + c0 + j);
-            count += __popc(m);
+            key[j] = make_key(cv[j], rc * W + c0 + j);
+            keep[j] = keep[j] && key[j] > cut;
+          }
+          if (__any_sync(0xffffffffu, keep[0] | keep[1] | keep[2] | keep[3])) {
+            if (count + 128 > CAPW || count >= tsel + SEL_SLACK) {  // keep the best tsel so far; their worst is the new cut
+              __syncwarp();
+              warp_select_top(list, count, tsel, top, lane);
+              count = tsel; truncated = 1;
+              cut = list[tsel - 1];
+              cutv = key_val(cut);
+            }
+            const uint32_t lt = (1u << lane) - 1u;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const bool kp = keep[j] && key[j] > cut;
+              const uint32_t m = __ballot_sync(0xffffffffu, kp);
+              if (kp) list[count + __popc(m & lt)] = key[j];
+              count += __popc(m);
+            }
           }
         }
       }
@@ -266,7 +288,7 @@ __device__ __forceinline__ void scan_rows(const float* stage0, uint32_t full0, u
 
 // blockDim = (nwarps + 1) * 32: warps 0..nwarps-1 consume, warp nwarps produces.
 __global__ void __launch_bounds__(288) peak_scan_kernel(const float* __restrict__ q, int H, int W, float thr, int nwarps, int BAND,
-                                                        uint8_t* __restrict__ ws) {
+                                                        int tsel, uint8_t* __restrict__ ws) {
   extern __shared__ __align__(128) uint8_t s_raw[];
   float* stage0 = reinterpret_cast<float*>(s_raw);                                            // [SCAN_NST][SCAN_R][W]
   unsigned long long* s_lists = reinterpret_cast<unsigned long long*>(s_raw + (size_t)SCAN_NST * SCAN_R * W * 4);  // [warps][CAPW + TSEL]
@@ -318,16 +340,16 @@ __global__ void __launch_bounds__(288) peak_scan_kernel(const float* __restrict_
   const int ccol = min(max(c0, 0), W - 4);
   int nonconst = track ? 0 : 1;
   int count = 0, truncated = 0;
-  if (track) scan_rows<true>(stage0, full0, empty0, W, row0, nrows, y0, y1, ccol, c0, owner, tx, ty, tz, tw, p0, lane, list, top, count, truncated, nonconst);
-  else scan_rows<false>(stage0, full0, empty0, W, row0, nrows, y0, y1, ccol, c0, owner, tx, ty, tz, tw, p0, lane, list, top, count, truncated, nonconst);
+  if (track) scan_rows<true>(stage0, full0, empty0, W, row0, nrows, y0, y1, ccol, c0, owner, tx, ty, tz, tw, p0, lane, list, top, count, truncated, nonconst, tsel);
+  else scan_rows<false>(stage0, full0, empty0, W, row0, nrows, y0, y1, ccol, c0, owner, tx, ty, tz, tw, p0, lane, list, top, count, truncated, nonconst, tsel);
   __syncwarp();
-  if (count > TSEL) { warp_select_top(list, count, TSEL, top, lane); count = TSEL; truncated = 1; }
+  if (count > tsel) { warp_select_top(list, count, tsel, top, lane); count = tsel; truncated = 1; }
   nonconst = __any_sync(0xffffffffu, nonconst);
   uint8_t* seg = ws + ((long long)(b * nbands + band) * nwarps + warp) * SEG_BYTES;
   if (lane == 0) {
     SegHeader h;
     h.count = count; h.truncated = truncated;
-    h.worst_kept = truncated ? list[TSEL - 1] : 0ull;
+    h.worst_kept = truncated ? list[tsel - 1] : 0ull;
     h.nonconst = nonconst; h.pad[0] = h.pad[1] = h.pad[2] = 0;
     *reinterpret_cast<SegHeader*>(seg) = h;
   }
@@ -748,8 +770,13 @@ extern "C" int crog_detect_grasps(const float* q, const float* sin_m, const floa
     CROG_CUDA_OK(cudaFuncSetAttribute(peak_scan_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * (CAPW + TSEL) * 8));
     once.done(dev_);
   }
-  if (W % 4 == 0 && (long long)H * W >= 2 && !getenv("CROG_SCAN_GENERIC")) peak_scan_kernel<<<dim3(nb, B), (nw + 1) * 32, smem_fast, s>>>(q, H, W, threshold, nw, band, ws);
-  else peak_scan_generic_kernel<<<dim3(nb, B), nw * 32, smem_lists, s>>>(q, H, W, threshold, nw, band, ws);
+  // keys kept per warp segment: strict 5x5 maxima are >= 3 apart, so without ties the answer is the global top K and
+  // K + 1 kept keys per segment already prove it; 2K + 2 leaves room for tie-induced rejections before a map is flagged
+  // for the exact sweep.  Fewer kept keys = cheaper selections and a tighter running cut.
+  static const int tsel_env = getenv("CROG_SCAN_TSEL") ? atoi(getenv("CROG_SCAN_TSEL")) : 0;
+  const int tsel = tsel_env > 0 ? max(1, min(tsel_env, TSEL)) : max(8, min(2 * K + 2, TSEL));
+  if (W % 4 == 0 && (long long)H * W >= 2 && !getenv("CROG_SCAN_GENERIC")) peak_scan_kernel<<<dim3(nb, B), (nw + 1) * 32, smem_fast, s>>>(q, H, W, threshold, nw, band, tsel, ws);
+  else peak_scan_generic_kernel<<<dim3(nb, B), nw * 32, smem_lists, s>>>(q, H, W, threshold, nw, band, tsel, ws);
   CROG_LAUNCH_OK("peak_scan");
   peak_select_kernel<<<(B + 3) / 4, 128, 0, s>>>(sin_m, cos_m, wid, B, H, W, K, nb * nw, ws, flags, peaks, n_peaks, grasps);
   CROG_LAUNCH_OK("peak_select");

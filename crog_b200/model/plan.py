@@ -136,13 +136,20 @@ class ForwardPlan:
         # (CROG_FUSE_DOWNSAMPLE=0: two GEMMs and an identity tensor, as in the fp32 mode)
         self.side_helpers = os.environ.get("CROG_SIDE_HELPERS", "1") != "0"
         self.fuse_downsample = (precision == "bf16" and gemm_impl != L.IMPL_SIMT and os.environ.get("CROG_FUSE_DOWNSAMPLE", "1") != "0")
+        # bf16 tcgen05 plans store the two 32-channel stem tensors as pixel pairs (CROG_STEM_PAIRS=0: channel-padded rows)
+        self.stem_pairs = (precision == "bf16" and gemm_impl != L.IMPL_SIMT and os.environ.get("CROG_STEM_PAIRS", "1") != "0")
+        # SMs the text tower's persistent GEMMs may occupy while it runs beside the image front (0: no partition)
+        self.text_sms = int(os.environ.get("CROG_TEXT_SMS", "16")) if precision == "bf16" and gemm_impl != L.IMPL_SIMT else 0
+        self.front_end = 0  # ops [0, front_end) are the image front (stem, layer1, layer2) that overlaps the text tower
         self._side = None
         self._side2 = None
         self._sev = {}
         self._ev = None
         self.gemm_flops = 0
         self.gemm_alg_flops: Dict[str, int] = {}
+        self.gemm_alg_bytes: Dict[str, int] = {}  # operands read once + result written once (no padding, no halo, no re-reads)
         self.gemm_ops: List[tuple] = []  # (name, descriptor, launch fn) of every GEMM, for the plan-time tile autotuner
+        self.gemm_index: Dict[int, object] = {}  # op index -> descriptor
         self.tile_choice: Dict[str, tuple] = {}  # name -> (tile_cfg, us, heuristic us) once autotune() has run
         sd = {k: v.detach().to(self.dev) for k, v in sd.items()}
         self.sd = sd
@@ -196,8 +203,10 @@ class ForwardPlan:
              gate=None, scale2=None, bias2=None, w_sample_stride: int = 0, cin: Optional[int] = None,
              alg_n: Optional[int] = None, alg_cin: Optional[int] = None, out_sample_rows: int = 0, out_row0: int = 0,
              row_stats_out: Optional[torch.Tensor] = None, row_stats_in: Optional[torch.Tensor] = None, row_stats_width: int = 0,
-             a2: Optional[Act] = None, after: Optional[List[int]] = None):
+             a2: Optional[Act] = None, after: Optional[List[int]] = None, tap_mask: int = 0,
+             alg_flops: Optional[int] = None, alg_bytes: Optional[int] = None):
         g = L.CrogGemm()
+        g.tap_mask = tap_mask
         cin = cin if cin is not None else a.C
         cin2 = a2.C if a2 is not None else 0
         assert w.shape[-1] == taps * cin + cin2, (name, tuple(w.shape), taps, cin, cin2)
@@ -235,12 +244,20 @@ class ForwardPlan:
         self._hold.extend([g, w, scale, bias, addmat, gate, scale2, bias2])
         lib = self.lib
         ref = C.byref(g)
-        self._add(name, lambda s: L.check(lib.crog_gemm(ref, s)), after=after)
+        idx = self._add(name, lambda s: L.check(lib.crog_gemm(ref, s)), after=after)
         self.gemm_ops.append((name, g, self.ops[-1]))
+        self.gemm_index[idx] = g
         rows_eff = a.B * a.H * a.W if a.H > 0 else a.rows
         self.gemm_flops += 2 * rows_eff * N * (taps * cin + cin2)
         # algorithmic FLOPs of the reference op (no channel padding, no halo rows) for roofline accounting
-        self.gemm_alg_flops[name] = 2 * rows_eff * (alg_n or N) * (taps * (alg_cin or cin) + cin2)
+        self.gemm_alg_flops[name] = alg_flops if alg_flops is not None else 2 * rows_eff * (alg_n or N) * (taps * (alg_cin or cin) + cin2)
+        esz = a.t.element_size()
+        w_copies = (a.rows // a.sample_rows) if w_sample_stride > 0 else 1
+        self.gemm_alg_bytes[name] = (rows_eff * ((alg_cin or cin) + cin2) * esz + w_copies * (alg_n or N) * (taps * (alg_cin or cin) + cin2) * esz
+                                     + rows_eff * (alg_n or N) * out.t.element_size()
+                                     + (rows_eff * N * residual.t.element_size() if residual is not None else 0))
+        if alg_bytes is not None:
+            self.gemm_alg_bytes[name] = alg_bytes
         if self._keep_all:
             self.keep[name] = out
 
@@ -294,19 +311,64 @@ class ForwardPlan:
         # 32 channels zero-padded to one 64-channel K chunk
         v = "backbone.visual"
         H1 = S // 2
-        s1 = self.new(H1, H1, 64, padded=True)
-        sc, bi = _bn_fold(sd, v + ".bn1")
-        w1, sc, bi = self.f32(sd[v + ".conv1.weight"]), self.f32(sc), self.f32(bi)
-        a = (self.img.data_ptr(), B, S, S, w1.data_ptr(), sc.data_ptr(), bi.data_ptr(), 32, s1.ptr, s1.ld, self.acode)
-        self._add("stem.conv1", lambda s: L.check(lib.crog_stem_conv1(*a, s)))
-        sc, bi = _bn_fold(sd, v + ".bn2")
-        s2 = self.new(H1, H1, 64, padded=True)
-        self.gemm("stem.conv2", s1, self.wt(_conv_w(sd[v + ".conv2.weight"], 64, 64)), 64, s2, taps=9,
-                  scale=self.f32(_pad_vec(sc, 64, 1.0)), bias=self.f32(_pad_vec(bi, 64, 0.0)), act=RELU, alg_n=32, alg_cin=32)
-        sc, bi = _bn_fold(sd, v + ".bn3")
+        sc1, bi1 = _bn_fold(sd, v + ".bn1")
+        w1, sc1, bi1 = self.f32(sd[v + ".conv1.weight"]), self.f32(sc1), self.f32(bi1)
+        sc2, bi2 = _bn_fold(sd, v + ".bn2")
+        sc3, bi3 = _bn_fold(sd, v + ".bn3")
         s3 = self.new(H1, H1, 64)
-        self.gemm("stem.conv3", s2, self.wt(_conv_w(sd[v + ".conv3.weight"], 64)), 64, s3, taps=9,
-                  scale=self.f32(sc), bias=self.f32(bi), act=RELU, alg_cin=32)
+        esz = 2 if self.adt == torch.bfloat16 else 4
+        npx = B * H1 * H1
+        if self.stem_pairs and H1 % 2 == 0:
+            # PIXEL-PAIR layout for the two 32-channel stem tensors: a row holds two horizontally adjacent pixels (2 x 32
+            # channels = one full 64-channel K chunk, no padding channels), on a zero-haloed [H1+2, H1/2+2] grid.  A 3x3
+            # convolution over pixels is a 3x3 convolution over pairs whose weights place w[o, i, ky, dx] at pair offset ksx
+            # / input parity q / output parity p with dx = 2 ksx + q - p (zero where |dx| > 1):
+            #   conv2 (32 -> 32): one GEMM, N = 64 = 2 parities x 32, K = 9 x 64 - half the rows and half the executed FLOPs
+            #     of the channel-padded form (which contracted 64 x 64 per tap for a 32 x 32 convolution);
+            #   conv3 (32 -> 64): one GEMM per output parity (N = 64) writing its half of the [pixels/2, 128] view of the
+            #     ordinary NHWC output; each parity reaches only two of the three pair offsets, the third tap is masked out
+            #     (6 of 9 taps contracted).
+            Wp = H1 // 2
+            s1 = self.new(H1, Wp, 64, padded=True)
+            a = (self.img.data_ptr(), B, S, S, w1.data_ptr(), sc1.data_ptr(), bi1.data_ptr(), 32, s1.ptr, s1.ld, self.acode, 1)
+            self._add("stem.conv1", lambda s: L.check(lib.crog_stem_conv1(*a, s)))
+            w2, w3 = sd[v + ".conv2.weight"].float(), sd[v + ".conv3.weight"].float()
+
+            def pair_weights(w, parities):
+                co, ci = w.shape[0], w.shape[1]
+                out = torch.zeros((len(parities) * co, 3, 3, 2 * ci), device=w.device)
+                mask = 0
+                for pi, p_ in enumerate(parities):
+                    for q in (0, 1):
+                        for ksx in (-1, 0, 1):
+                            dx = 2 * ksx + q - p_
+                            if abs(dx) <= 1:
+                                out[pi * co:(pi + 1) * co, :, ksx + 1, q * ci:(q + 1) * ci] = w[:, :, :, dx + 1].permute(0, 2, 1)
+                                for ky in range(3):
+                                    mask |= 1 << (ky * 3 + ksx + 1)
+                return out.reshape(len(parities) * co, -1).contiguous(), mask
+
+            w2p, _ = pair_weights(w2, (0, 1))
+            s2 = self.new(H1, Wp, 64, padded=True)
+            self.gemm("stem.conv2", s1, self.wt(w2p), 64, s2, taps=9, scale=self.f32(torch.cat([sc2, sc2])),
+                      bias=self.f32(torch.cat([bi2, bi2])), act=RELU, alg_flops=2 * npx * 32 * 9 * 32,
+                      alg_bytes=npx * 32 * esz * 2 + 32 * 288 * esz)
+            s3v = Act(s3.t.view(-1, 128), B, H1, Wp, False, 128)
+            for p_ in (0, 1):
+                w3p, mask = pair_weights(w3, (p_,))
+                self.gemm(f"stem.conv3.p{p_}", s2, self.wt(w3p), 64, s3v.cols(64 * p_, 64 * p_ + 64), taps=9, scale=self.f32(sc3),
+                          bias=self.f32(bi3), act=RELU, tap_mask=mask, alg_flops=npx * 64 * 9 * 32,
+                          alg_bytes=(npx * 32 * esz + npx * 64 * esz + 64 * 288 * esz) // 2)
+        else:
+            # channel-padded form (fp32 / CUDA-core plans): 32 channels zero-padded to one 64-channel K chunk
+            s1 = self.new(H1, H1, 64, padded=True)
+            a = (self.img.data_ptr(), B, S, S, w1.data_ptr(), sc1.data_ptr(), bi1.data_ptr(), 32, s1.ptr, s1.ld, self.acode, 0)
+            self._add("stem.conv1", lambda s: L.check(lib.crog_stem_conv1(*a, s)))
+            s2 = self.new(H1, H1, 64, padded=True)
+            self.gemm("stem.conv2", s1, self.wt(_conv_w(sd[v + ".conv2.weight"], 64, 64)), 64, s2, taps=9,
+                      scale=self.f32(_pad_vec(sc2, 64, 1.0)), bias=self.f32(_pad_vec(bi2, 64, 0.0)), act=RELU, alg_n=32, alg_cin=32)
+            self.gemm("stem.conv3", s2, self.wt(_conv_w(sd[v + ".conv3.weight"], 64)), 64, s3, taps=9,
+                      scale=self.f32(sc3), bias=self.f32(bi3), act=RELU, alg_cin=32)
         x = self.new(H1 // 2, H1 // 2, 64)
         self.resample("stem.avgpool", s3, x, L.RS_AVGPOOL2)
         self.keep["stem"] = x
@@ -323,6 +385,7 @@ class ForwardPlan:
             # zero-haloed copies of C3 / C4 for the 3x3 convolutions of the neck: produced on the helper stream as soon
             # as the stage is done, under the tensor-core work of the following stages
             if li == 2:
+                self.front_end = len(self.ops)
                 self._c3p = self.new(x.H, x.W, x.C, padded=True)
                 self._c3p_idx = self.resample("neck.c3_pad", x, self._c3p, L.RS_COPY, side=True)
             if li == 3:
@@ -710,10 +773,12 @@ class ForwardPlan:
         """Replay the recorded launches on the current stream.  The text encoder does not depend on the image tower
         until the neck, so it is forked onto a side stream (under CUDA-graph capture this becomes a parallel branch)."""
         if stream is not None or not fork_text or os.environ.get("CROG_NO_FORK"):
+            self._partition(False)
             s = stream if stream is not None else L.stream_ptr()
             for fn in self.ops:
                 fn(s)
             return
+        self._partition(True)
         main = torch.cuda.current_stream()
         if self._side is None:
             self._side = torch.cuda.Stream(device=self.dev)
@@ -743,6 +808,23 @@ class ForwardPlan:
         on_main(0, t0)
         main.wait_event(self._ev[1])
         on_main(t1, len(self.ops))
+
+    def _partition(self, on: bool):
+        """SM budgets of the two concurrent branches.  Persistent GEMM CTAs take most of an SM's shared memory, so the text
+        tower's and the image tower's cannot share an SM: left alone, the two branches mostly serialise.  While the text
+        tower runs (the memory-bound image front: stem, layer1, layer2) its GEMMs get `text_sms` SMs and the front's the
+        rest; a serial replay (per-op timing, autotune, debugging) gives every GEMM the whole GPU.  The descriptors are
+        read at launch time, so a captured graph keeps the budgets it was captured with."""
+        t0, t1 = self.text_range
+        n_sm = torch.cuda.get_device_properties(self.dev).multi_processor_count
+        for i, g in self.gemm_index.items():
+            cap = 0
+            if on and self.text_sms > 0 and t1 > t0:
+                if t0 <= i < t1:
+                    cap = self.text_sms
+                elif i < self.front_end:
+                    cap = n_sm - self.text_sms
+            g.max_ctas = cap
 
     def run_debug(self):
         """Run op by op with a device sync after each, naming the op that faults."""

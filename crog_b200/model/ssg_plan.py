@@ -33,8 +33,9 @@ class SSGPlan(ForwardPlan):
         self.impl = gemm_impl
         self.ops, self.op_names, self.keep, self._keep_all, self._hold = [], [], {}, keep, []
         self.op_launches = []
-        self.n_launches, self.gemm_flops, self.gemm_alg_flops = 0, 0, {}
-        self.gemm_ops, self.tile_choice = [], {}
+        self.n_launches, self.gemm_flops, self.gemm_alg_flops, self.gemm_alg_bytes = 0, 0, {}, {}
+        self.gemm_ops, self.tile_choice, self.gemm_index = [], {}, {}
+        self.text_sms, self.front_end, self.stem_pairs = 0, 0, False
         self.op_side, self.op_after, self.side_helpers, self.fuse_downsample = set(), {}, False, False
         self._side = self._ev = None
         self.text_range = (0, 0)

@@ -315,7 +315,7 @@ def ssg_masks_device(cfg, output_b, boxes, det_anchor, n: int, ori_size):
     n_dev = torch.full((1,), n, dtype=torch.int32, device=dev)
     with torch.cuda.device(dev):
         L.check(lib.crog_ssg_masks(protos.data_ptr(), h, w, npz, coef.data_ptr(), gco.data_ptr(), boxes.data_ptr(),
-                                   det_anchor.data_ptr(), n_dev.data_ptr(), n, lowres.data_ptr(), hr.data_ptr(), ori_h, ori_w, S,
+                                   det_anchor.data_ptr(), n_dev.data_ptr(), n, lowres.data_ptr(), hr.data_ptr(), n, ori_h, ori_w, S,
                                    L.stream_ptr()))
         q = hr[1]
         L.check(lib.crog_gaussian(q.data_ptr(), tmp.data_ptr(), q.data_ptr(), n, ori_h, ori_w, taps.ctypes.data, (len(taps) - 1) // 2,
@@ -363,25 +363,66 @@ def ssg_post_processing(cfg, output_dict, data_dict):
 @torch.no_grad()
 def ssg_post_processing_batched(cfg, output_dict, ori_size=(480, 640)):
     """Device-resident batched form used by the engine / benchmark: the per-image stages of ssg_post_processing for every
-    sample of a batch with ONE host synchronisation (the detection counts), nothing else leaving HBM.
-    Returns a list of per-sample dicts of CUDA tensors: n, cls, boxes, hr [5,n,H,W], n_peaks [n], grasps [n,5,5]."""
+    sample of a batch with ONE host synchronisation (the detection counts) and nothing else leaving HBM.  The detection
+    stage is launched per image into slices of batch-wide buffers; after the counts are known, the masks of all images are
+    assembled into ONE map-major tensor ``[5, sum(n), H, W]`` (each image writes its own instance range), then one
+    Gaussian and one peak decode run over all ``sum(n)`` instance maps.
+    Returns a list of per-sample dicts of CUDA tensors (views): n, cls, boxes, scores, hr [5,n,H,W], n_peaks [n],
+    grasps [n,5,5]."""
+    lib = L.lib()
     protos, cls, box = output_dict["protos"], output_dict["cls_pred"], output_dict["box_pred"]
     coef, gco = output_dict["ins_coef_pred"], output_dict["grasp_coef_pred"]
     dev = protos.device
+    f32c = lambda t: t.to(dev, torch.float32).contiguous()
+    protos, cls, box, coef, gco = f32c(protos), f32c(cls), f32c(box), f32c(coef), f32c(gco)
     anchors = _anchors_dev(output_dict["anchors"], dev)
-    B = protos.shape[0]
-    dets = [_ssg_detect(cfg, cls[b], box[b], anchors) for b in range(B)]
-    counts = torch.cat([d[1] for d in dets]).cpu().tolist()  # the one sync
-    out = []
-    for b in range(B):
-        boxes, _, det_anchor, det_class, det_score, _ = dets[b]
-        n = counts[b]
-        hr = ssg_masks_device(cfg, (protos[b], coef[b], gco[b]), boxes, det_anchor, n, ori_size)
-        if n > 0:
-            _, npk, grasps = detect_grasps_batched(hr[1], hr[2], hr[3], hr[4], 5)
+    B, N, nc = cls.shape
+    h, w, npz = protos.shape[1:]
+    md = int(cfg.max_detections)
+    ori_h, ori_w = int(ori_size[0]), int(ori_size[1])
+    S = max(ori_h, ori_w)
+    ws_bytes = ((int(L.load().crog_ssg_nms_workspace_bytes(nc, int(cfg.top_k))) + 255) // 256) * 256
+    keep = torch.empty((B, N), dtype=torch.int32, device=dev)
+    boxes = torch.empty((B, N, 4), dtype=torch.float32, device=dev)
+    det_n = torch.zeros((B,), dtype=torch.int32, device=dev)
+    det_anchor = torch.empty((B, md), dtype=torch.int32, device=dev)
+    det_class = torch.empty((B, md), dtype=torch.int32, device=dev)
+    det_score = torch.empty((B, md), dtype=torch.float32, device=dev)
+    ws = torch.empty((B, ws_bytes), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        s = L.stream_ptr()
+        for b in range(B):
+            L.check(lib.crog_ssg_detect(cls[b].data_ptr(), box[b].data_ptr(), anchors.data_ptr(), N, nc, float(cfg.nms_score_thre),
+                                        float(cfg.nms_iou_thre), int(cfg.top_k), md, 0.3, keep[b].data_ptr(), boxes[b].data_ptr(),
+                                        det_n[b:].data_ptr(), det_anchor[b].data_ptr(), det_class[b].data_ptr(),
+                                        det_score[b].data_ptr(), ws[b].data_ptr(), s))
+        counts = det_n.cpu().tolist()  # the one sync: output shapes are data dependent, as in the reference
+        offs = [0]
+        for n in counts:
+            offs.append(offs[-1] + n)
+        tot = offs[-1]
+        hr = torch.empty((5, max(tot, 1), ori_h, ori_w), dtype=torch.float32, device=dev)
+        lowres = torch.empty((max(tot, 1), 5, h, w), dtype=torch.float32, device=dev)
+        plane = ori_h * ori_w
+        for b in range(B):
+            if counts[b] == 0:
+                continue
+            # detection stride of the map-major output = tot instances: image b fills instances [offs[b], offs[b] + n_b)
+            L.check(lib.crog_ssg_masks(protos[b].data_ptr(), h, w, npz, coef[b].data_ptr(), gco[b].data_ptr(), boxes[b].data_ptr(),
+                                       det_anchor[b].data_ptr(), det_n[b:].data_ptr(), counts[b], lowres[offs[b]:].data_ptr(),
+                                       hr.data_ptr() + offs[b] * plane * 4, tot, ori_h, ori_w, S, s))
+        if tot > 0:
+            taps = gaussian_taps(2.0)
+            tmp = torch.empty((tot, ori_h, ori_w), dtype=torch.float32, device=dev)
+            L.check(lib.crog_gaussian(hr[1].data_ptr(), tmp.data_ptr(), hr[1].data_ptr(), tot, ori_h, ori_w, taps.ctypes.data,
+                                      (len(taps) - 1) // 2, None, 1, 0, s))
+            _, npk, grasps = detect_grasps_batched(hr[1, :tot], hr[2, :tot], hr[3, :tot], hr[4, :tot], 5)
         else:
             npk = torch.zeros((0,), dtype=torch.int32, device=dev)
             grasps = torch.zeros((0, 5, 5), dtype=torch.float64, device=dev)
-        out.append({"n": n, "cls": det_class[:n] + 1, "boxes": boxes[det_anchor[:n].long()], "scores": det_score[:n], "hr": hr,
-                    "n_peaks": npk, "grasps": grasps})
+    out = []
+    for b in range(B):
+        n, o = counts[b], offs[b]
+        out.append({"n": n, "cls": det_class[b, :n] + 1, "boxes": boxes[b][det_anchor[b, :n].long()], "scores": det_score[b, :n],
+                    "hr": hr[:, o:o + n], "n_peaks": npk[o:o + n], "grasps": grasps[o:o + n]})
     return out

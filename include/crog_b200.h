@@ -113,6 +113,13 @@ typedef struct CrogGemm {
   int32_t row_stats_chunks;
   int32_t row_stats_width;
   float row_stats_eps;
+  int32_t max_ctas;       /* tcgen05 path: upper bound on the persistent grid (0: one CTA per SM).  The forward plan runs the
+                             text tower on a few SMs BESIDE the memory-bound image front: both branches' persistent CTAs
+                             need most of an SM's shared memory, so without disjoint SM budgets they serialise. */
+  int32_t tap_mask;       /* 3x3 convolutions on the resident-weight path: bit (ky*3+kx) set = tap contracted; 0 = all nine.
+                             Masked taps must have zero weights (other tile configurations still contract them): the
+                             pixel-pair stem (two 32-channel pixels per 64-channel row) only reaches two of the three
+                             horizontal pair offsets per output parity. */
 } CrogGemm;
 enum {
   CROG_TILE_AUTO = 0,
@@ -145,10 +152,13 @@ int crog_resample(const void* in, int32_t in_ld, int32_t in_padded, void* out, i
 
 /* Stem conv1: 3x3 stride 2 pad 1 on NCHW fp32 images + folded BN + ReLU, writing the padded
  * NHWC layout (model/clip.py:165-170,208-211). w [cout,3,3,3] fp32. Only channels [0, cout) of the interior pixels are
- * written: halo pixels and the padding channels [cout, out_ld) must already be zero (the caller's zero-initialised buffer). */
+ * written: halo pixels and the padding channels [cout, out_ld) must already be zero (the caller's zero-initialised buffer).
+ * pixel_pairs != 0: the output is the PIXEL-PAIR layout instead: a zero-haloed [B, OH+2, OW/2+2] grid of rows holding two
+ * horizontally adjacent pixels, channels [0,cout) = pixel 2s, [cout, 2*cout) = pixel 2s+1 (needs OW even, out_ld >= 2*cout):
+ * a 32-channel tensor then fills 64-channel (128-byte) rows with no padding channels. */
 int crog_stem_conv1(const float* img, int32_t B, int32_t Hin, int32_t Win, const float* w,
                     const float* scale, const float* bias, int32_t cout, void* out, int32_t out_ld,
-                    int32_t out_dtype, void* stream);
+                    int32_t out_dtype, int32_t pixel_pairs, void* stream);
 
 /* LayerNorm over the last dim (clip.py:226-231, layers.py:288-311): y = LN(x)*g + b, optional
  * out = residual + y (fp32 residual stream).  x_dtype/out_dtype are CROG_F32|CROG_BF16. */
@@ -261,11 +271,12 @@ int crog_ssg_detect(const float* cls, const float* box, const float* anchors, in
                     int32_t* det_n, int32_t* det_anchor, int32_t* det_class, float* det_score, void* workspace, void* stream);
 /* Mask stage (grasp_eval.py:171-194): lowres[d][k] = crop(act_k(protos . coef_k(d))) for k = ins, qua, sin, cos, wid
  * (sigmoid on ins / qua / wid), [max_det, 5, h, w]; out[k][d] = bilinear resize to resize_to^2 (align_corners=False)
- * cropped to [out_h, out_w], map-major [5, max_det, out_h, out_w]; the instance plane is thresholded (> 0.5 -> 1.0).
- * Only the first *det_n detections are written. */
+ * cropped to [out_h, out_w], map-major [5, out_det_stride, out_h, out_w] (out_det_stride <= 0: max_det; a larger stride
+ * lets several images fill disjoint instance ranges of one batch-wide tensor); the instance plane is thresholded
+ * (> 0.5 -> 1.0).  Only the first *det_n (<= max_det) detections are written. */
 int crog_ssg_masks(const float* protos, int32_t h, int32_t w, int32_t num_protos, const float* coef, const float* gcoef,
                    const float* boxes, const int32_t* det_anchor, const int32_t* det_n, int32_t max_det, float* lowres,
-                   float* out, int32_t out_h, int32_t out_w, int32_t resize_to, void* stream);
+                   float* out, int32_t out_det_stride, int32_t out_h, int32_t out_w, int32_t resize_to, void* stream);
 /* skimage.filters.gaussian(map, sigma, preserve_range=True) of grasp_eval.py:198 = scipy.ndimage.gaussian_filter(mode='nearest'):
  * separable (rows first), float64 accumulation in scipy's tap order, float32 result per pass.  weights_host: the 2*radius+1
  * normalised float64 taps (HOST pointer; computed by the caller exactly as scipy does).  Planes smoothed:

@@ -31,7 +31,7 @@ def _rand(*shape, seed=0, scale=1.0):
 
 def test_library_and_device():
     lib = L.lib()
-    assert lib.crog_abi_version() == 3
+    assert lib.crog_abi_version() == L.ABI_VERSION
     assert lib.crog_check_device() == 0
 
 
@@ -145,7 +145,7 @@ def test_stem_conv1(dt):
     out.view(B, S // 2 + 2, S // 2 + 2, 64)[:, :, 0] = 0; out.view(B, S // 2 + 2, S // 2 + 2, 64)[:, :, -1] = 0
     out[:, 32:] = 0  # the padding channels belong to the caller (zero-initialised plan buffer); the kernel never writes them
     L.check(L.lib().crog_stem_conv1(img.data_ptr(), B, S, S, w.data_ptr(), sc.data_ptr(), bi.data_ptr(), 32, out.data_ptr(), 64,
-                                    L.dtype_code(dt), L.stream_ptr()))
+                                    L.dtype_code(dt), 0, L.stream_ptr()))
     torch.cuda.synchronize()
     want = F.relu(F.conv2d(img, w, stride=2, padding=1) * sc.view(1, -1, 1, 1) + bi.view(1, -1, 1, 1))
     got = unpad(out, B, S // 2, S // 2)
@@ -656,3 +656,59 @@ def test_gemm_second_operand_equals_two_gemms():
     g.impl = L.IMPL_SIMT  # the CUDA-core path does not implement it and must say so
     with pytest.raises(L.CrogError):
         L.check(L.lib().crog_gemm(C.byref(g), L.stream_ptr()))
+
+
+# ------------------------------------------------------------------ round 2: SM budgets, masked taps, pixel-pair stem
+@pytest.mark.parametrize("M,N,K,cap", [(1088, 1536, 512, 16), (43264, 256, 1024, 132), (43264, 512, 2048, 30), (300, 64, 64, 1)])
+def test_gemm_grid_cap_is_bit_identical(M, N, K, cap):
+    """CrogGemm.max_ctas only bounds the persistent grid: every tile is computed the same way by whichever CTA gets it."""
+    a, w = _rand(M, K, seed=1).to(BF), _rand(N, K, seed=2, scale=K ** -0.5).to(BF)
+    bias = _rand(N, seed=3)
+    o0, o1 = torch.zeros(M, N, device=DEV, dtype=BF), torch.zeros(M, N, device=DEV, dtype=BF)
+    run_gemm(a, w, N, o0, bias=bias, act=L.ACT_RELU, impl=L.IMPL_TCGEN05)
+    run_gemm(a, w, N, o1, bias=bias, act=L.ACT_RELU, impl=L.IMPL_TCGEN05, max_ctas=cap)
+    assert torch.equal(o0, o1)
+    assert relerr(o0, F.relu(a.float() @ w.float().t() + bias)) < 6e-3
+
+
+def test_conv3_tap_mask_skips_zero_taps():
+    """Resident-weight 3x3 path with tap_mask: the masked taps (zero weights) are not contracted; result == all nine taps."""
+    B, H, W, Cin, Cout = 2, 20, 24, 64, 64
+    x = _rand(B, Cin, H, W, seed=4)
+    wgt = _rand(Cout, Cin, 3, 3, seed=5, scale=(9 * Cin) ** -0.5)
+    for keep_kx in ((0, 1), (1, 2)):
+        wz = wgt.clone()
+        mask = 0
+        for kx in range(3):
+            if kx not in keep_kx:
+                wz[:, :, :, kx] = 0
+            else:
+                for ky in range(3):
+                    mask |= 1 << (ky * 3 + kx)
+        a = pad_nhwc(x, BF)
+        o_all = torch.zeros(B * (H + 2) * (W + 2), Cout, device=DEV, dtype=BF)
+        o_msk = torch.zeros_like(o_all)
+        run_gemm(a, conv_w(wz, BF), Cout, o_all, taps=9, cin=Cin, H=H, W=W, in_padded=True, out_padded=True,
+                 sample_rows=(H + 2) * (W + 2), impl=L.IMPL_TCGEN05)
+        run_gemm(a, conv_w(wz, BF), Cout, o_msk, taps=9, cin=Cin, H=H, W=W, in_padded=True, out_padded=True,
+                 sample_rows=(H + 2) * (W + 2), impl=L.IMPL_TCGEN05, tap_mask=mask)
+        want = F.conv2d(x.to(BF).float(), wz.to(BF).float(), padding=1)
+        assert relerr(unpad(o_msk, B, H, W), want) < 6e-3
+        assert relerr(unpad(o_msk, B, H, W), unpad(o_all, B, H, W)) < 1e-3  # same products, fewer zero terms
+
+
+def test_stem_conv1_pixel_pair_layout():
+    B, S = 2, 64
+    img = _rand(B, 3, S, S, seed=6)
+    w, sc, bi = _rand(32, 3, 3, 3, seed=7, scale=0.3), torch.rand(32, device=DEV) + 0.5, _rand(32, seed=8, scale=0.1)
+    OH, OWp = S // 2, S // 4
+    out = torch.zeros(B * (OH + 2) * (OWp + 2), 64, device=DEV, dtype=BF)
+    L.check(L.lib().crog_stem_conv1(img.data_ptr(), B, S, S, w.data_ptr(), sc.data_ptr(), bi.data_ptr(), 32, out.data_ptr(), 64,
+                                    L.dtype_code(BF), 1, L.stream_ptr()))
+    torch.cuda.synchronize()
+    want = F.relu(F.conv2d(img, w, stride=2, padding=1) * sc.view(1, -1, 1, 1) + bi.view(1, -1, 1, 1))  # B,32,OH,OW
+    grid = out.float().view(B, OH + 2, OWp + 2, 2, 32)
+    got = grid[:, 1:-1, 1:-1].reshape(B, OH, OWp * 2, 32).permute(0, 3, 1, 2)
+    assert maxerr(got, want) < 2e-2
+    halo = grid.clone(); halo[:, 1:-1, 1:-1] = 0
+    assert float(halo.abs().max()) == 0.0

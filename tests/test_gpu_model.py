@@ -258,3 +258,32 @@ def test_dataparallel_two_gpus_matches_single():
     torch.cuda.synchronize()
     assert all(torch.equal(a.cpu(), b.cpu()) for a, b in zip(single, multi))
     assert {k[-1] for k in model._plans} == {0, 1}
+
+
+def test_stem_pixel_pairs_equal_channel_padded_form(monkeypatch):
+    """bf16 plans store the 32-channel stem tensors as pixel pairs (half the rows, no padding channels, 6-of-9-tap conv3);
+    the result must be the channel-padded form's up to fp32 summation order, and the partitioned / serial replays agree."""
+    from crog_b200.model import CROG
+
+    Lw, B = 17, 2
+    cfg = synth.default_cfg(Lw)
+    sd = synth.make_state_dict(cfg, 0, "perturbed")
+    img, word = synth.make_inputs(B, Lw)
+    outs = {}
+    for pairs in ("1", "0"):
+        monkeypatch.setenv("CROG_STEM_PAIRS", pairs)
+        m = CROG(cfg, precision="bf16")
+        m.load_state_dict(sd, strict=True)
+        m = m.cuda()
+        maps, _ = m(img.cuda(), word.cuda())
+        plan = m.plan_for(B, 416)
+        assert plan.stem_pairs == (pairs == "1")
+        outs[pairs] = (plan.keep["stem"].interior().clone(), torch.stack(maps).clone())
+        if pairs == "1":
+            assert "stem.conv3.p1" in plan.op_names and plan.front_end > 0
+            plan.run(stream=torch.cuda.current_stream().cuda_stream)  # serial replay, no SM budgets
+            torch.cuda.synchronize()
+            assert torch.equal(plan.out.cpu(), torch.stack(maps).cpu())
+    stem1, stem0 = outs["1"][0], outs["0"][0]
+    assert float((stem1 - stem0).norm() / stem0.norm()) < 3e-3
+    assert float((outs["1"][1] - outs["0"][1]).norm() / outs["0"][1].norm()) < 2.5e-2

@@ -225,3 +225,32 @@ def test_post_processing_matches_oracle_and_golden():
     # and the decoded grasp positions agree with the reference's on this fixture
     for a, b in zip(got["grasps_top5"], ref["grasps_top5"]):
         assert [(r[0], r[1]) for r in a] == [(r[0], r[1]) for r in b]
+
+
+def test_post_processing_batched_equals_per_image():
+    """ssg_post_processing_batched (one sync, one map-major tensor for all instances of the batch) returns for every image
+    exactly what the per-image drop-in ssg_post_processing returns (same kernels, different launch geometry)."""
+    from crog_b200.utils import grasp_eval as GE
+
+    cfg = synth.ssg_cfg()
+    ods = [synth.make_ssg_output_dict(cfg, n_confident=n, seed=s) for n, s in ((8, 6), (0, 7), (3, 8), (11, 9))]
+    batch = {k: torch.cat([od[k] for od in ods]).cuda() for k in ("protos", "cls_pred", "box_pred", "ins_coef_pred", "grasp_coef_pred")}
+    batch["anchors"] = ods[0]["anchors"]
+    got = GE.ssg_post_processing_batched(cfg, batch, (480, 640))
+    assert len(got) == len(ods)
+    for od, g in zip(ods, got):
+        ref = GE.ssg_post_processing(cfg, {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in od.items()}, {"ori_size": (480, 640)})
+        n = len(ref["cls"])
+        assert g["n"] == n
+        assert np.array_equal(g["cls"].cpu().numpy(), ref["cls"])
+        assert np.array_equal(g["boxes"].cpu().numpy() * np.array([640, 640, 640, 640]), ref["bboxes"])
+        hr = g["hr"].cpu().numpy()
+        assert hr.shape == (5, n, 480, 640)
+        if n == 0:
+            continue
+        assert np.array_equal(hr[0], ref["ins_masks"])
+        assert np.array_equal(hr[1], ref["grasp_masks"][0]) and np.array_equal(hr[4], ref["grasp_masks"][2])
+        npk, gr = g["n_peaks"].cpu().numpy(), g["grasps"].cpu().numpy()
+        for i in range(n):
+            rows = [[r[0], r[1], r[2], 20, r[4]] for r in gr[i, :npk[i]].tolist()]
+            assert rows == ref["grasps_top5"][i]
