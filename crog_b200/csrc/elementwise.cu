@@ -110,11 +110,13 @@ __global__ void __launch_bounds__(128) stem_conv1_kernel(const float* __restrict
   for (int i = threadIdx.x; i < cout; i += blockDim.x) { sw[27 * cout + i] = scale[i]; sw[28 * cout + i] = bias[i]; }
   __syncthreads();
   pdl_wait();
+  // thread = one output pixel pair, ALL channels: the 45 input values (3 channels x 3 rows x 5 columns) are loaded once
+  // and reused by every 8-channel group (a thread per group re-loaded them cout/8 times and ran at a quarter of the
+  // store bandwidth); in the pixel-pair layout a thread's two pixels are one contiguous 2*cout-channel row.
   const int OH = Hin / 2, OW = Win / 2, OWP = (OW + 1) / 2, cgs = cout / 8;
-  const long long total = (long long)B * OH * OWP * cgs;
+  const long long total = (long long)B * OH * OWP;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int cg = (int)(i % cgs);
-    long long t = i / cgs;
+    long long t = i;
     const int oxp = (int)(t % OWP);
     t /= OWP;
     const int oy = (int)(t % OH), b = (int)(t / OH);
@@ -132,40 +134,38 @@ __global__ void __launch_bounds__(128) stem_conv1_kernel(const float* __restrict
           x[ci][ky][kx] = (iy >= 0 && iy < Hin && ix >= 0 && ix < Win) ? __ldg(rowp + ix) : 0.f;
         }
       }
-    float v0[8], v1[8];
+    T* o0 = pairs ? out + ((long long)(b * (OH + 2) + oy + 1) * (OWP + 2) + oxp + 1) * out_ld
+                  : out + pix_row(b, oy, ox, OH, OW, 1) * out_ld;
+    T* o1 = pairs ? o0 + cout : o0 + out_ld;
+    for (int cg = 0; cg < cgs; ++cg) {
+      float v0[8], v1[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { v0[j] = 0.f; v1[j] = 0.f; }
-    const int c0 = cg * 8;
+      for (int j = 0; j < 8; ++j) { v0[j] = 0.f; v1[j] = 0.f; }
+      const int c0 = cg * 8;
 #pragma unroll
-    for (int ci = 0; ci < 3; ++ci)
+      for (int ci = 0; ci < 3; ++ci)
 #pragma unroll
-      for (int ky = 0; ky < 3; ++ky)
+        for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
-        for (int kx = 0; kx < 3; ++kx) {
-          const int k = ci * 9 + ky * 3 + kx;
-          const float4 w0 = *reinterpret_cast<const float4*>(&sw[k * cout + c0]);
-          const float4 w1 = *reinterpret_cast<const float4*>(&sw[k * cout + c0 + 4]);
-          const float a = x[ci][ky][kx], c = x[ci][ky][kx + 2];
-          // packed FFMA2: (v[2j], v[2j+1]) += (a, a) * (w[2j], w[2j+1]) — the same two fused multiply-adds, one instruction
-          fma2_bcast(v0[0], v0[1], a, w0.x, w0.y); fma2_bcast(v0[2], v0[3], a, w0.z, w0.w);
-          fma2_bcast(v0[4], v0[5], a, w1.x, w1.y); fma2_bcast(v0[6], v0[7], a, w1.z, w1.w);
-          fma2_bcast(v1[0], v1[1], c, w0.x, w0.y); fma2_bcast(v1[2], v1[3], c, w0.z, w0.w);
-          fma2_bcast(v1[4], v1[5], c, w1.x, w1.y); fma2_bcast(v1[6], v1[7], c, w1.z, w1.w);
-        }
+          for (int kx = 0; kx < 3; ++kx) {
+            const int k = ci * 9 + ky * 3 + kx;
+            const float4 w0 = *reinterpret_cast<const float4*>(&sw[k * cout + c0]);
+            const float4 w1 = *reinterpret_cast<const float4*>(&sw[k * cout + c0 + 4]);
+            const float a = x[ci][ky][kx], c = x[ci][ky][kx + 2];
+            // packed FFMA2: (v[2j], v[2j+1]) += (a, a) * (w[2j], w[2j+1]) — the same two fused multiply-adds, one instruction
+            fma2_bcast(v0[0], v0[1], a, w0.x, w0.y); fma2_bcast(v0[2], v0[3], a, w0.z, w0.w);
+            fma2_bcast(v0[4], v0[5], a, w1.x, w1.y); fma2_bcast(v0[6], v0[7], a, w1.z, w1.w);
+            fma2_bcast(v1[0], v1[1], c, w0.x, w0.y); fma2_bcast(v1[2], v1[3], c, w0.z, w0.w);
+            fma2_bcast(v1[4], v1[5], c, w1.x, w1.y); fma2_bcast(v1[6], v1[7], c, w1.z, w1.w);
+          }
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float sc = sw[27 * cout + c0 + j], bi = sw[28 * cout + c0 + j];
-      v0[j] = fmaxf(v0[j] * sc + bi, 0.f);
-      v1[j] = fmaxf(v1[j] * sc + bi, 0.f);
-    }
-    if (pairs) {  // pixel-pair layout: this thread's two pixels are one row of the zero-haloed [OH+2, OW/2+2] grid
-      T* o = out + ((long long)(b * (OH + 2) + oy + 1) * (OWP + 2) + oxp + 1) * out_ld + c0;
-      store8(o, v0);
-      store8(o + cout, v1);
-    } else {
-      T* o = out + pix_row(b, oy, ox, OH, OW, 1) * out_ld + c0;
-      store8(o, v0);
-      if (ox + 1 < OW) store8(o + out_ld, v1);
+      for (int j = 0; j < 8; ++j) {
+        const float sc = sw[27 * cout + c0 + j], bi = sw[28 * cout + c0 + j];
+        v0[j] = fmaxf(v0[j] * sc + bi, 0.f);
+        v1[j] = fmaxf(v1[j] * sc + bi, 0.f);
+      }
+      store8(o0 + c0, v0);
+      if (pairs || ox + 1 < OW) store8(o1 + c0, v1);
     }
   }
 }
@@ -514,7 +514,7 @@ extern "C" int crog_stem_conv1(const float* img, int32_t B, int32_t Hin, int32_t
                                void* stream) {
   CROG_REQUIRE(Hin % 2 == 0 && Win % 2 == 0 && out_ld % 8 == 0 && cout <= out_ld && cout % 8 == 0, CROG_E_BADSHAPE, "stem_conv1: bad shape");
   CROG_REQUIRE(!pixel_pairs || (Win % 4 == 0 && 2 * cout <= out_ld), CROG_E_BADSHAPE, "stem_conv1: the pixel-pair layout needs an even output width and out_ld >= 2*cout");
-  const long long total = (long long)B * (Hin / 2) * ((Win / 2 + 1) / 2) * (cout / 8);  // (pixel pair, 8-channel group) threads
+  const long long total = (long long)B * (Hin / 2) * ((Win / 2 + 1) / 2);  // one thread per output pixel pair
   if (total == 0) return CROG_OK;
   const int g = grid_for(total, 128);
   const size_t sm = (size_t)(29 * cout) * sizeof(float);

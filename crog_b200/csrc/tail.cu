@@ -56,19 +56,93 @@ __device__ __forceinline__ unsigned long long warp_max_u64(unsigned long long k)
   return k;
 }
 __device__ __forceinline__ float max3(float a, float b, float c) { return fmaxf(fmaxf(a, b), c); }
+// largest float below x (finite x)
+__device__ __forceinline__ float float_prev(float x) {
+  if (x == 0.f) return -__uint_as_float(1u);
+  const uint32_t u = __float_as_uint(x);
+  return __uint_as_float(x > 0.f ? u - 1u : u + 1u);
+}
 
-// keep the best `keep` keys of list[0..n) (n <= CAPW) at the front, in descending order
-__device__ void warp_select_top(unsigned long long* list, int n, int keep, unsigned long long* top, int lane) {
-  for (int t = 0; t < keep; ++t) {
-    unsigned long long best = 0ull;
-    for (int i = lane; i < n; i += 32) { const unsigned long long k = list[i]; best = k > best ? k : best; }
-    best = warp_max_u64(best);
-    for (int i = lane; i < n; i += 32) if (list[i] == best) list[i] = 0ull;  // keys are unique
-    if (lane == 0) top[t] = best;
-    __syncwarp();
+// ---- warp-wide top-32 selection on 64-bit keys (bitonic networks over the 32 lanes, one key per lane and register).
+// A selection is ~30 dependent shuffle steps (about 1k cycles) instead of `keep` serial arg-max sweeps over the list
+// (about 400 cycles each): short enough to hide inside the scan's 20-row staging slack, so a warp that selects does not
+// stall the CTA's bulk-copy ring.
+__device__ __forceinline__ unsigned long long shfl_xor_u64(unsigned long long k, int m) {
+  return __shfl_xor_sync(0xffffffffu, k, m);
+}
+__device__ __forceinline__ unsigned long long sort32_desc(unsigned long long k, int lane) {
+#pragma unroll
+  for (int size = 2; size <= 32; size <<= 1) {
+#pragma unroll
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      const unsigned long long o = shfl_xor_u64(k, stride);
+      const bool desc = (lane & size) == 0;      // direction of this lane's block (size 32: one descending block)
+      const bool lower = (lane & stride) == 0;
+      const unsigned long long mx = k > o ? k : o, mn = k > o ? o : k;
+      k = (lower == desc) ? mx : mn;
+    }
   }
-  for (int i = lane; i < keep; i += 32) list[i] = top[i];
+  return k;
+}
+// a, b sorted descending over the lanes -> the 32 largest of the 64 keys, sorted descending
+__device__ __forceinline__ unsigned long long merge_top32(unsigned long long a, unsigned long long b, int lane) {
+  const unsigned long long br = shfl_xor_u64(b, 31);  // b reversed
+  unsigned long long t = a > br ? a : br;              // bitonic sequence holding the top 32
+#pragma unroll
+  for (int stride = 16; stride > 0; stride >>= 1) {
+    const unsigned long long o = shfl_xor_u64(t, stride);
+    const bool lower = (lane & stride) == 0;
+    const unsigned long long mx = t > o ? t : o, mn = t > o ? o : t;
+    t = lower ? mx : mn;
+  }
+  return t;
+}
+// keep the best `keep` (<= 32) keys of list[0..n) (n <= CAPW; keys are unique and non-zero) at the front, descending
+__device__ unsigned long long warp_select_top(unsigned long long* list, int n, int keep, unsigned long long* /*scratch*/, int lane) {
+  unsigned long long acc = 0ull;
+  for (int base = 0; base < n; base += 128) {  // four independent 32-key sorts in flight, then a merge tree
+    unsigned long long k0 = base + lane < n ? list[base + lane] : 0ull;
+    unsigned long long k1 = base + 32 + lane < n ? list[base + 32 + lane] : 0ull;
+    unsigned long long k2 = base + 64 + lane < n ? list[base + 64 + lane] : 0ull;
+    unsigned long long k3 = base + 96 + lane < n ? list[base + 96 + lane] : 0ull;
+    k0 = sort32_desc(k0, lane);
+    if (base + 32 < n) {
+      k1 = sort32_desc(k1, lane);
+      k0 = merge_top32(k0, k1, lane);
+      if (base + 64 < n) {
+        k2 = sort32_desc(k2, lane);
+        if (base + 96 < n) { k3 = sort32_desc(k3, lane); k2 = merge_top32(k2, k3, lane); }
+        k0 = merge_top32(k0, k2, lane);
+      }
+    }
+    acc = base == 0 ? k0 : merge_top32(acc, k0, lane);
+  }
   __syncwarp();
+  if (lane < keep) list[lane] = acc;
+  __syncwarp();
+  return acc;  // lane i holds the i-th largest key (0: fewer than i + 1 keys)
+}
+
+// Cold path of the scan (kept out of line so its registers do not count against the streaming loop): keep the best tsel
+// keys, then apply the value cut.  Returns the new list length; *bound rises to cover everything dropped.
+__device__ __noinline__ int select_and_cut(unsigned long long* list, int count, int tsel, int kdist, int lane,
+                                           unsigned long long* bound_io) {
+  unsigned long long bound = *bound_io;
+  const unsigned long long a = warp_select_top(list, count, tsel, nullptr, lane);
+  if (count > tsel) { const unsigned long long w = list[tsel - 1]; bound = w > bound ? w : bound; count = tsel; }
+  // value cut: the kdist-th distinct value among the kept (sorted) keys
+  const uint32_t hv = (uint32_t)(a >> 32), pv = __shfl_up_sync(0xffffffffu, hv, 1);
+  const bool valid = lane < count;
+  const uint32_t mnew = __ballot_sync(0xffffffffu, valid && (lane == 0 || hv != pv));
+  if (__popc(mnew) >= kdist) {
+    const int pos = __fns(mnew, 0, kdist);
+    const uint32_t cvv = __shfl_sync(0xffffffffu, hv, pos);
+    const unsigned long long ck = (unsigned long long)cvv << 32;  // below every key of that value
+    bound = ck > bound ? ck : bound;
+    count = min(count, __popc(__ballot_sync(0xffffffffu, valid && hv >= cvv)));
+  }
+  *bound_io = bound;
+  return count;
 }
 
 // Lanes 1..30 of a warp own 4 columns each (a 120-column strip); lanes 0 and 31 load the 4 columns on either side and
@@ -200,7 +274,7 @@ __global__ void __launch_bounds__(256, 2) peak_scan_generic_kernel(const float* 
 //    maxima above the threshold, the appends decay like tsel / candidates seen and the scan stays a streaming kernel.
 constexpr int SCAN_R = 5;    // rows per stage (= ring length, so ring slots are compile-time)
 constexpr int SCAN_NST = 4;  // stages
-constexpr int SEL_SLACK = 64; // candidates a warp appends beyond its tsel kept keys before it selects again
+constexpr int SEL_SLACK = 64; // keys a warp appends after a selection before it selects again
 
 __device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -209,12 +283,26 @@ __device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void* src, uint
 
 template <bool TRACK>
 __device__ __forceinline__ void scan_rows(const float* stage0, uint32_t full0, uint32_t empty0, int W, int row0, int nrows, int y0,
-                                          int y1, int ccol, int c0, bool owner, float tx, float ty, float tz, float tw, float p0,
+                                          int y1, int ccol, int c0, bool owner, float tx_, float ty_, float tz_, float tw_, float p0,
                                           int lane, unsigned long long* list, unsigned long long* top, int& count,
-                                          int& truncated, int& nonconst, const int tsel) {
+                                          int& truncated, int& nonconst, const int tsel, const int kdist,
+                                          unsigned long long& bound) {
   const float NEG = -INFINITY;
-  unsigned long long cut = 0ull;  // worst kept key after the latest selection (0: nothing dropped yet)
-  float cutv = NEG;
+  // `bound`: every key this warp has dropped so far is below it (0: nothing dropped).  Two sources:
+  //  * a selection that kept the best tsel keys: its worst kept key;
+  //  * the VALUE cut: two candidates closer than the minimum distance are 5x5 maxima inside each other's window, hence
+  //    equal, so the greedy pass only ever rejects a candidate because of an accepted one of the SAME value, and every
+  //    distinct value yields at least one accepted peak.  Once the warp holds kdist = K + 1 distinct values, no
+  //    candidate below the kdist-th of them can be reached before K peaks are accepted: it is dropped unseen (and the
+  //    bound (value, lowest key) never flags a map, because the pass ends above it).
+  // On iid maps (all values distinct) the cut sits at the warp's (K+1)-th best value after the first selection, so only
+  // a few per cent of the later candidates touch the list at all.
+  unsigned long long cut = bound;
+  // per-lane emission thresholds (+inf for columns that may not emit).  After a selection they are raised to just below
+  // the cut's value, so the threshold-first vote below skips every row without a candidate that can still matter: a
+  // dense map (most pixels above the user threshold) then costs what a sparse one costs.
+  float tx = tx_, ty = ty_, tz = tz_, tw = tw_;
+  int next_sel = 16;  // first selection early (establishes the value cut); then see below
   float4 raw[5], hm[5];
 #pragma unroll
   for (int u = 0; u < 5; ++u) { raw[u] = make_float4(NEG, NEG, NEG, NEG); hm[u] = raw[u]; }
@@ -246,35 +334,44 @@ __device__ __forceinline__ void scan_rows(const float* stage0, uint32_t full0, u
         const float vy = max3(max3(hm[0].y, hm[1].y, hm[2].y), hm[3].y, hm[4].y);
         const float vz = max3(max3(hm[0].z, hm[1].z, hm[2].z), hm[3].z, hm[4].z);
         const float vw = max3(max3(hm[0].w, hm[1].w, hm[2].w), hm[3].w, hm[4].w);
-        // (values equal to the cut's pass here; the exact 64-bit key comparison follows in the append path)
-        const bool k0 = a0 && ctr.x == vx && ctr.x >= cutv, k1 = a1 && ctr.y == vy && ctr.y >= cutv;
-        const bool k2 = a2 && ctr.z == vz && ctr.z >= cutv, k3 = a3 && ctr.w == vw && ctr.w >= cutv;
+        // (values equal to the cut's pass the raised thresholds; the exact 64-bit key comparison follows in the append path)
+        const bool k0 = a0 && ctr.x == vx, k1 = a1 && ctr.y == vy;
+        const bool k2 = a2 && ctr.z == vz, k3 = a3 && ctr.w == vw;
         if (__any_sync(0xffffffffu, k0 | k1 | k2 | k3)) {
           // exact filter on the 64-bit keys (value, then row-major index): a candidate that ties the cut's value but
           // comes later in the map is below the cut, so a plateau at the top value stops appending after tsel entries
           const int rc = row0 + idx - 2;
           const float cv[4] = {ctr.x, ctr.y, ctr.z, ctr.w};
-          unsigned long long key[4];
+          const uint32_t lo0 = 0xffffffffu - (uint32_t)(rc * W + c0);  // low key word of column c0 (column j: lo0 - j)
+          uint32_t chi = (uint32_t)(cut >> 32), clo = (uint32_t)cut;
           bool keep[4] = {k0, k1, k2, k3};
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            key[j] = make_key(cv[j], rc * W + c0 + j);
-            keep[j] = keep[j] && key[j] > cut;
+            const uint32_t hi = f2ord(cv[j]);
+            keep[j] = keep[j] && (hi > chi || (hi == chi && lo0 - j > clo));
           }
           if (__any_sync(0xffffffffu, keep[0] | keep[1] | keep[2] | keep[3])) {
-            if (count + 128 > CAPW || count >= tsel + SEL_SLACK) {  // keep the best tsel so far; their worst is the new cut
+            if (count + 128 > CAPW || count >= next_sel) {
               __syncwarp();
-              warp_select_top(list, count, tsel, top, lane);
-              count = tsel; truncated = 1;
-              cut = list[tsel - 1];
-              cutv = key_val(cut);
+              count = select_and_cut(list, count, tsel, kdist, lane, &bound);
+              cut = bound;
+              truncated = bound != 0ull;
+              // a short list means the value cut is active (distinct values): re-select often, each selection tightens the
+              // cut and the appends die out like kdist / candidates seen; a full list (ties) re-selects every SEL_SLACK keys
+              next_sel = count + (count < 16 ? 10 : SEL_SLACK);
+              chi = (uint32_t)(cut >> 32); clo = (uint32_t)cut;
+              if (cut) {  // "value > prev(cutv)" == "value >= cutv": no float lies between the two
+                const float pc = float_prev(key_val(cut));
+                tx = fmaxf(tx, pc); ty = fmaxf(ty, pc); tz = fmaxf(tz, pc); tw = fmaxf(tw, pc);
+              }
             }
             const uint32_t lt = (1u << lane) - 1u;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              const bool kp = keep[j] && key[j] > cut;
+              const uint32_t hi = f2ord(cv[j]);
+              const bool kp = keep[j] && (hi > chi || (hi == chi && lo0 - j > clo));
               const uint32_t m = __ballot_sync(0xffffffffu, kp);
-              if (kp) list[count + __popc(m & lt)] = key[j];
+              if (kp) list[count + __popc(m & lt)] = ((unsigned long long)hi << 32) | (unsigned long long)(lo0 - j);
               count += __popc(m);
             }
           }
@@ -287,8 +384,9 @@ __device__ __forceinline__ void scan_rows(const float* stage0, uint32_t full0, u
 }
 
 // blockDim = (nwarps + 1) * 32: warps 0..nwarps-1 consume, warp nwarps produces.
-__global__ void __launch_bounds__(288) peak_scan_kernel(const float* __restrict__ q, int H, int W, float thr, int nwarps, int BAND,
-                                                        int tsel, uint8_t* __restrict__ ws) {
+template <int MINB>  // resident CTAs per SM the register allocation is held to (2: no spills, 3: more warps in flight)
+__global__ void __launch_bounds__(288, MINB) peak_scan_kernel(const float* __restrict__ q, int H, int W, float thr, int nwarps, int BAND,
+                                                           int tsel, int kdist, uint8_t* __restrict__ ws) {
   extern __shared__ __align__(128) uint8_t s_raw[];
   float* stage0 = reinterpret_cast<float*>(s_raw);                                            // [SCAN_NST][SCAN_R][W]
   unsigned long long* s_lists = reinterpret_cast<unsigned long long*>(s_raw + (size_t)SCAN_NST * SCAN_R * W * 4);  // [warps][CAPW + TSEL]
@@ -316,8 +414,8 @@ __global__ void __launch_bounds__(288) peak_scan_kernel(const float* __restrict_
       const int nst = (nrows + SCAN_R - 1) / SCAN_R;
       for (int k = 0; k < nst; ++k) {
         const int s = k % SCAN_NST;
-        if (k >= SCAN_NST) {  // back off between polls: the producer must not eat the consumers' issue slots
-          while (!mbar_try_wait(empty0 + 8 * s, ((k / SCAN_NST) - 1) & 1)) __nanosleep(200);
+        if (k >= SCAN_NST) {  // parked by the hardware until the consumers free the stage: no issue slots spent polling
+          while (!mbar_try_wait_hint(empty0 + 8 * s, ((k / SCAN_NST) - 1) & 1, 100000u)) {}
         }
         const int rows = min(SCAN_R, nrows - k * SCAN_R);
         const uint32_t bytes = (uint32_t)rows * W * 4;
@@ -340,16 +438,23 @@ __global__ void __launch_bounds__(288) peak_scan_kernel(const float* __restrict_
   const int ccol = min(max(c0, 0), W - 4);
   int nonconst = track ? 0 : 1;
   int count = 0, truncated = 0;
-  if (track) scan_rows<true>(stage0, full0, empty0, W, row0, nrows, y0, y1, ccol, c0, owner, tx, ty, tz, tw, p0, lane, list, top, count, truncated, nonconst, tsel);
-  else scan_rows<false>(stage0, full0, empty0, W, row0, nrows, y0, y1, ccol, c0, owner, tx, ty, tz, tw, p0, lane, list, top, count, truncated, nonconst, tsel);
+  unsigned long long bound = 0ull;
+  if (track) scan_rows<true>(stage0, full0, empty0, W, row0, nrows, y0, y1, ccol, c0, owner, tx, ty, tz, tw, p0, lane, list, top, count, truncated, nonconst, tsel, kdist, bound);
+  else scan_rows<false>(stage0, full0, empty0, W, row0, nrows, y0, y1, ccol, c0, owner, tx, ty, tz, tw, p0, lane, list, top, count, truncated, nonconst, tsel, kdist, bound);
   __syncwarp();
-  if (count > tsel) { warp_select_top(list, count, tsel, top, lane); count = tsel; truncated = 1; }
+  if (count > tsel) {
+    warp_select_top(list, count, tsel, top, lane);
+    const unsigned long long w = list[tsel - 1];
+    bound = w > bound ? w : bound;
+    count = tsel;
+  }
+  truncated = bound != 0ull;
   nonconst = __any_sync(0xffffffffu, nonconst);
   uint8_t* seg = ws + ((long long)(b * nbands + band) * nwarps + warp) * SEG_BYTES;
   if (lane == 0) {
     SegHeader h;
     h.count = count; h.truncated = truncated;
-    h.worst_kept = truncated ? list[tsel - 1] : 0ull;
+    h.worst_kept = bound;
     h.nonconst = nonconst; h.pad[0] = h.pad[1] = h.pad[2] = 0;
     *reinterpret_cast<SegHeader*>(seg) = h;
   }
@@ -765,17 +870,24 @@ extern "C" int crog_detect_grasps(const float* q, const float* sin_m, const floa
   static DeviceOnce once;
   int dev_;
   if (once.need(&dev_)) {
-    CROG_CUDA_OK(cudaFuncSetAttribute(peak_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    CROG_CUDA_OK(cudaFuncSetAttribute(peak_scan_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      SCAN_NST * SCAN_R * 8 * STRIP * 4 + 8 * (CAPW + TSEL) * 8 + 2 * SCAN_NST * 8));
+    CROG_CUDA_OK(cudaFuncSetAttribute(peak_scan_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       SCAN_NST * SCAN_R * 8 * STRIP * 4 + 8 * (CAPW + TSEL) * 8 + 2 * SCAN_NST * 8));
     CROG_CUDA_OK(cudaFuncSetAttribute(peak_scan_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * (CAPW + TSEL) * 8));
     once.done(dev_);
   }
-  // keys kept per warp segment: strict 5x5 maxima are >= 3 apart, so without ties the answer is the global top K and
-  // K + 1 kept keys per segment already prove it; 2K + 2 leaves room for tie-induced rejections before a map is flagged
-  // for the exact sweep.  Fewer kept keys = cheaper selections and a tighter running cut.
+  // keys kept per warp segment.  Strict 5x5 maxima are >= 3 apart, so without ties the answer is the global top K; ties
+  // (plateaus, e.g. a quality map clipped at 1.0) make the greedy pass reject up to 8 candidates per accepted peak, and a
+  // map whose segments kept too few keys to prove the result is flagged for the slow exact sweep.  32 keeps that rare
+  // (measured: 2K + 2 = 12 keys flagged a quarter of the 'blobs' maps - 4.2 ms of exact sweeps per 4096 maps).
   static const int tsel_env = getenv("CROG_SCAN_TSEL") ? atoi(getenv("CROG_SCAN_TSEL")) : 0;
-  const int tsel = tsel_env > 0 ? max(1, min(tsel_env, TSEL)) : max(8, min(2 * K + 2, TSEL));
-  if (W % 4 == 0 && (long long)H * W >= 2 && !getenv("CROG_SCAN_GENERIC")) peak_scan_kernel<<<dim3(nb, B), (nw + 1) * 32, smem_fast, s>>>(q, H, W, threshold, nw, band, tsel, ws);
+  const int tsel = tsel_env > 0 ? max(1, min(tsel_env, TSEL)) : TSEL;
+  static const int occ_env = getenv("CROG_SCAN_OCC") ? atoi(getenv("CROG_SCAN_OCC")) : 0;
+  if (W % 4 == 0 && (long long)H * W >= 2 && !getenv("CROG_SCAN_GENERIC")) {
+    if (occ_env != 3) peak_scan_kernel<2><<<dim3(nb, B), (nw + 1) * 32, smem_fast, s>>>(q, H, W, threshold, nw, band, tsel, K + 1, ws);
+    else peak_scan_kernel<3><<<dim3(nb, B), (nw + 1) * 32, smem_fast, s>>>(q, H, W, threshold, nw, band, tsel, K + 1, ws);
+  }
   else peak_scan_generic_kernel<<<dim3(nb, B), nw * 32, smem_lists, s>>>(q, H, W, threshold, nw, band, tsel, ws);
   CROG_LAUNCH_OK("peak_scan");
   peak_select_kernel<<<(B + 3) / 4, 128, 0, s>>>(sin_m, cos_m, wid, B, H, W, K, nb * nw, ws, flags, peaks, n_peaks, grasps);

@@ -26,6 +26,21 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// try_wait with a suspend-time hint (ns): the hardware parks the thread until the phase completes or the hint expires, so
+// a waiter that expects to wait long (a producer throttled by its consumers) issues one instruction per `hint_ns`
+// instead of spinning — __nanosleep() between polls returned after a few ns on B200 and the poll loop of one lane ate a
+// third of the SM's issue slots (ncu, peak_scan_kernel: 22 % of executed instructions were SYNCS + NANOSLEEP).
+__device__ __forceinline__ bool mbar_try_wait_hint(uint32_t bar, uint32_t parity, uint32_t hint_ns) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity), "r"(hint_ns)
+      : "memory");
+  return ok != 0;
+}
 // Bounded wait: a protocol bug must surface as a launch failure, not as a hung GPU.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;

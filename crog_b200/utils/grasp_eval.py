@@ -97,6 +97,14 @@ def jacquard_batched(grasps: torch.Tensor, n_peaks: Optional[torch.Tensor], gt: 
 
 
 _side_streams = {}
+_pools = {}
+
+
+def _stream_pool(dev, n: int):
+    key = (dev.index, n)
+    if key not in _pools:
+        _pools[key] = [torch.cuda.Stream(device=dev) for _ in range(n)]
+    return _pools[key]
 
 
 def decode_and_score_batched(q: torch.Tensor, sin: torch.Tensor, cos: torch.Tensor, wid: torch.Tensor, gt: torch.Tensor,
@@ -391,11 +399,23 @@ def ssg_post_processing_batched(cfg, output_dict, ori_size=(480, 640)):
     ws = torch.empty((B, ws_bytes), dtype=torch.uint8, device=dev)
     with torch.cuda.device(dev):
         s = L.stream_ptr()
+        # the per-image detection kernels have small grids (one CTA per class): images are independent, so they are spread
+        # over a pool of streams and fill the GPU side by side instead of queueing behind each other
+        main = torch.cuda.current_stream()
+        pool = _stream_pool(dev, min(8, B))
+        fork = torch.cuda.Event()
+        fork.record(main)
+        for st in pool:
+            st.wait_event(fork)
         for b in range(B):
             L.check(lib.crog_ssg_detect(cls[b].data_ptr(), box[b].data_ptr(), anchors.data_ptr(), N, nc, float(cfg.nms_score_thre),
                                         float(cfg.nms_iou_thre), int(cfg.top_k), md, 0.3, keep[b].data_ptr(), boxes[b].data_ptr(),
                                         det_n[b:].data_ptr(), det_anchor[b].data_ptr(), det_class[b].data_ptr(),
-                                        det_score[b].data_ptr(), ws[b].data_ptr(), s))
+                                        det_score[b].data_ptr(), ws[b].data_ptr(), pool[b % len(pool)].cuda_stream))
+        for st in pool:
+            join = torch.cuda.Event()
+            join.record(st)
+            main.wait_event(join)
         counts = det_n.cpu().tolist()  # the one sync: output shapes are data dependent, as in the reference
         offs = [0]
         for n in counts:
