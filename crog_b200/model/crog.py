@@ -24,6 +24,16 @@ from ..spec import crog_tensor_specs
 from .. import _lib as L
 
 
+_capture_streams: Dict[int, torch.cuda.Stream] = {}
+
+
+def _capture_stream(dev: torch.device) -> torch.cuda.Stream:
+    s = _capture_streams.get(dev.index)
+    if s is None:
+        s = _capture_streams[dev.index] = torch.cuda.Stream(device=dev)
+    return s
+
+
 def _holder(root: nn.Module, dotted: str) -> Tuple[nn.Module, str]:
     parts = dotted.split(".")
     m = root
@@ -223,7 +233,9 @@ class CROG(nn.Module):
                     plan.run()  # eager warm-up: sets kernel attributes, faults surface here with op context
                     torch.cuda.synchronize()
                     g = torch.cuda.CUDAGraph()
-                    with torch.cuda.graph(g, capture_error_mode="thread_local"):
+                    # torch.cuda.graph's default capture stream is ONE process-wide stream on whichever device captured
+                    # first; entering it from another device's replica would switch the current device: use our own
+                    with torch.cuda.graph(g, stream=_capture_stream(plan.dev), capture_error_mode="thread_local"):
                         plan.run()
                     self._graphs[key] = g
         g.replay()

@@ -112,6 +112,12 @@ def _pos1d(d_model: int, n: int) -> torch.Tensor:
     return pe
 
 
+def _aligned(t: torch.Tensor) -> torch.Tensor:
+    """Kernels read parameters with 16-byte vector loads.  Tensors from torch's allocator are 256-byte aligned, but a
+    DataParallel replica's parameters are views into one coalesced broadcast buffer and may start on any 4-byte boundary."""
+    return t if t.data_ptr() % 16 == 0 else t.clone()
+
+
 class ForwardPlan:
     def __init__(self, sd: Dict[str, torch.Tensor], cfg, batch: int, precision: str = "bf16",
                  device: Optional[torch.device] = None, input_size: int = 416, gemm_impl: int = L.IMPL_AUTO,
@@ -151,7 +157,7 @@ class ForwardPlan:
         self.gemm_ops: List[tuple] = []  # (name, descriptor, launch fn) of every GEMM, for the plan-time tile autotuner
         self.gemm_index: Dict[int, object] = {}  # op index -> descriptor
         self.tile_choice: Dict[str, tuple] = {}  # name -> (tile_cfg, us, heuristic us) once autotune() has run
-        sd = {k: v.detach().to(self.dev) for k, v in sd.items()}
+        sd = {k: _aligned(v.detach().to(self.dev)) for k, v in sd.items()}
         self.sd = sd
         S = input_size
         assert S % 32 == 0
@@ -173,12 +179,12 @@ class ForwardPlan:
         return Act(t, self.B, H, W, padded, Cc)
 
     def wt(self, t: torch.Tensor) -> torch.Tensor:
-        t = t.to(self.dev, self.adt).contiguous()
+        t = _aligned(t.to(self.dev, self.adt).contiguous())
         self._hold.append(t)
         return t
 
     def f32(self, t: torch.Tensor) -> torch.Tensor:
-        t = t.to(self.dev, torch.float32).contiguous()
+        t = _aligned(t.to(self.dev, torch.float32).contiguous())
         self._hold.append(t)
         return t
 

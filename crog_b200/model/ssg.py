@@ -19,7 +19,7 @@ import torch.nn as nn
 
 from .. import _lib as L
 from ..spec import ssg_tensor_specs
-from .crog import _holder
+from .crog import _capture_stream, _holder
 from .ssg_anchors import make_all_anchors
 
 
@@ -122,7 +122,7 @@ class SSG(nn.Module):
             plan.run()
             torch.cuda.synchronize()
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
+            with torch.cuda.graph(g, stream=_capture_stream(plan.dev)):
                 plan.run()
             self._graphs[id(plan)] = g
         g.replay()

@@ -17,7 +17,7 @@ import torch
 import torch.nn.functional as F
 
 from .. import _lib as L
-from .plan import Act, ForwardPlan, _bn_fold, _conv_w
+from .plan import Act, ForwardPlan, _aligned, _bn_fold, _conv_w
 from .ssg_anchors import fpn_shapes
 
 
@@ -39,7 +39,7 @@ class SSGPlan(ForwardPlan):
         self.op_side, self.op_after, self.side_helpers, self.fuse_downsample = set(), {}, False, False
         self._side = self._ev = None
         self.text_range = (0, 0)
-        self.sd = {k: v.detach().to(self.dev) for k, v in sd.items()}
+        self.sd = {k: _aligned(v.detach().to(self.dev)) for k, v in sd.items()}
         S = cfg.img_size
         self.S = S
         self.rgb = torch.zeros((batch, 3, S, S), device=self.dev, dtype=torch.float32)
