@@ -369,23 +369,33 @@ __global__ void __launch_bounds__(256) ssg_lowres_kernel(const float* __restrict
 
 // ------------------------------------------------------------------ F.interpolate(size=(S,S), bilinear, align_corners=False) + [:oh, :ow] crop
 // planes [P][h][w] -> [P][oh][ow]; planes whose bit is set in bin_mask (by plane % planes_per_det) are thresholded > 0.5.
+constexpr int BC_ROWS = 8;  // output rows per thread: the horizontal source indices / weights are computed once per column
 __global__ void __launch_bounds__(256) bilinear_crop_kernel(const float* __restrict__ in, int h, int w, float* __restrict__ out, int oh,
                                                             int ow, int S, const int* __restrict__ n_planes, int planes_per_det,
                                                             uint32_t bin_mask, int det_stride) {
   const int pl = blockIdx.z;
   if (n_planes && pl >= *n_planes * planes_per_det) return;
-  const int ox = blockIdx.x * blockDim.x + threadIdx.x, oy = blockIdx.y;
+  const int ox = blockIdx.x * blockDim.x + threadIdx.x;
   if (ox >= ow) return;
   const float sc_h = (float)h / (float)S, sc_w = (float)w / (float)S;
-  const float sy = fmaxf(__fsub_rn(__fmul_rn(sc_h, (float)oy + 0.5f), 0.5f), 0.f), sx = fmaxf(__fsub_rn(__fmul_rn(sc_w, (float)ox + 0.5f), 0.5f), 0.f);
-  const int y0 = (int)sy, x0 = (int)sx, y1 = y0 + (y0 < h - 1), x1 = x0 + (x0 < w - 1);
-  const float ly = sy - y0, lx = sx - x0, hy = 1.f - ly, hx = 1.f - lx;
+  const float sx = fmaxf(__fsub_rn(__fmul_rn(sc_w, (float)ox + 0.5f), 0.5f), 0.f);
+  const int x0 = (int)sx, x1 = x0 + (x0 < w - 1);
+  const float lx = sx - x0, hx = 1.f - lx;
   const float* src = in + (long long)pl * h * w;
-  const float v = hy * (hx * __ldg(src + y0 * w + x0) + lx * __ldg(src + y0 * w + x1)) + ly * (hx * __ldg(src + y1 * w + x0) + lx * __ldg(src + y1 * w + x1));
   const int d = pl / planes_per_det, k = pl % planes_per_det;
   const bool bin = (bin_mask >> k) & 1u;
   // output is map-major: [planes_per_det][det_stride detections][oh][ow], so each map type is one contiguous batch
-  out[(((long long)k * det_stride + d) * oh + oy) * ow + ox] = bin ? (v > 0.5f ? 1.f : 0.f) : v;
+  float* dst = out + ((long long)k * det_stride + d) * oh * ow + ox;
+#pragma unroll
+  for (int j = 0; j < BC_ROWS; ++j) {
+    const int oy = blockIdx.y * BC_ROWS + j;
+    if (oy >= oh) break;
+    const float sy = fmaxf(__fsub_rn(__fmul_rn(sc_h, (float)oy + 0.5f), 0.5f), 0.f);
+    const int y0 = (int)sy, y1 = y0 + (y0 < h - 1);
+    const float ly = sy - y0, hy = 1.f - ly;
+    const float v = hy * (hx * __ldg(src + y0 * w + x0) + lx * __ldg(src + y0 * w + x1)) + ly * (hx * __ldg(src + y1 * w + x0) + lx * __ldg(src + y1 * w + x1));
+    dst[(long long)oy * ow] = bin ? (v > 0.5f ? 1.f : 0.f) : v;
+  }
 }
 
 // ------------------------------------------------------------------ Gaussian (sigma = 2 -> 17 taps), float64 accumulation, float32 per pass
@@ -412,6 +422,61 @@ __global__ void __launch_bounds__(256) gaussian_pass_kernel(const float* __restr
   double acc = __dmul_rn(at(0), g.w[r]);
   for (int j = -r; j < 0; ++j) acc = __dadd_rn(acc, __dmul_rn(__dadd_rn(at(j), at(-j)), g.w[j + r]));
   out[base + (long long)y * W + x] = (float)acc;
+}
+
+// Fast forms for a compile-time radius (sigma = 2 -> R = 8): the same per-output operation order as the generic kernel above
+// (so the results are bit-identical), but an output no longer costs 2R + 1 global loads.
+//  * vertical pass: a thread owns one column and GV_TY consecutive rows; the GV_TY + 2R clamped source values sit in
+//    registers and every output reads its window from them (3 loads per output instead of 17, all coalesced);
+//  * horizontal pass: a CTA stages GH_ROWS row segments (+R on either side, edge-replicated) in shared memory with
+//    coalesced loads; a thread then reads its 2R + 1 neighbours from shared memory (consecutive lanes, no conflicts).
+constexpr int GV_TY = 8, GH_ROWS = 4;
+template <int R>
+__global__ void __launch_bounds__(256) gaussian_vert_kernel(const float* __restrict__ in, float* __restrict__ out, int H, int W,
+                                                            const int* __restrict__ n_planes, int plane_stride_sel, int plane_sel, GaussW g) {
+  const int pz = blockIdx.z;
+  if (n_planes && pz >= *n_planes) return;
+  const long long base = ((long long)pz * plane_stride_sel + plane_sel) * H * W;
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y0 = blockIdx.y * GV_TY;
+  if (x >= W) return;
+  const float* src = in + base + x;
+  double v[GV_TY + 2 * R];
+#pragma unroll
+  for (int j = 0; j < GV_TY + 2 * R; ++j) v[j] = (double)__ldg(src + (long long)min(max(y0 - R + j, 0), H - 1) * W);
+#pragma unroll
+  for (int t = 0; t < GV_TY; ++t) {
+    if (y0 + t >= H) break;
+    double acc = __dmul_rn(v[t + R], g.w[R]);
+#pragma unroll
+    for (int j = -R; j < 0; ++j) acc = __dadd_rn(acc, __dmul_rn(__dadd_rn(v[t + R + j], v[t + R - j]), g.w[j + R]));
+    out[base + (long long)(y0 + t) * W + x] = (float)acc;
+  }
+}
+template <int R>
+__global__ void __launch_bounds__(256) gaussian_horz_kernel(const float* __restrict__ in, float* __restrict__ out, int H, int W,
+                                                            const int* __restrict__ n_planes, int plane_stride_sel, int plane_sel, GaussW g) {
+  __shared__ float tile[GH_ROWS][256 + 2 * R];
+  const int pz = blockIdx.z;
+  if (n_planes && pz >= *n_planes) return;
+  const long long base = ((long long)pz * plane_stride_sel + plane_sel) * H * W;
+  const int x0 = blockIdx.x * 256, y0 = blockIdx.y * GH_ROWS;
+  for (int i = threadIdx.x; i < GH_ROWS * (256 + 2 * R); i += 256) {
+    const int rr = i / (256 + 2 * R), cc = i % (256 + 2 * R);
+    const int yy = min(y0 + rr, H - 1), xx = min(max(x0 - R + cc, 0), W - 1);
+    tile[rr][cc] = __ldg(in + base + (long long)yy * W + xx);
+  }
+  __syncthreads();
+  const int x = x0 + threadIdx.x;
+  if (x >= W) return;
+#pragma unroll
+  for (int rr = 0; rr < GH_ROWS; ++rr) {
+    if (y0 + rr >= H) break;
+    const float* t = &tile[rr][threadIdx.x + R];
+    double acc = __dmul_rn((double)t[0], g.w[R]);
+#pragma unroll
+    for (int j = -R; j < 0; ++j) acc = __dadd_rn(acc, __dmul_rn(__dadd_rn((double)t[j], (double)t[-j]), g.w[j + R]));
+    out[base + (long long)(y0 + rr) * W + x] = (float)acc;
+  }
 }
 
 }  // namespace
@@ -527,7 +592,7 @@ extern "C" int crog_ssg_masks(const float* protos, int32_t h, int32_t w, int32_t
   dim3 g1((h * w + 255) / 256, max_det);
   ssg_lowres_kernel<<<g1, 256, 5 * num_protos * sizeof(float), s>>>(protos, h, w, num_protos, coef, gcoef, boxes, det_anchor, det_n, lowres);
   CROG_LAUNCH_OK("ssg_lowres");
-  dim3 g2((out_w + 255) / 256, out_h, max_det * 5);
+  dim3 g2((out_w + 255) / 256, (out_h + BC_ROWS - 1) / BC_ROWS, max_det * 5);
   bilinear_crop_kernel<<<g2, 256, 0, s>>>(lowres, h, w, out, out_h, out_w, resize_to, det_n, 5, 1u, out_det_stride);
   CROG_LAUNCH_OK("ssg_resize");
   return CROG_OK;
@@ -543,6 +608,13 @@ extern "C" int crog_gaussian(const float* in, float* tmp, float* out, int32_t P,
   g.r = r;
   for (int i = 0; i <= 2 * r; ++i) g.w[i] = weights_host[i];
   cudaStream_t s = (cudaStream_t)stream;
+  if (radius == 8 && !getenv("CROG_GAUSSIAN_GENERIC")) {  // sigma = 2, the only radius the reference uses (grasp_eval.py:198)
+    gaussian_vert_kernel<8><<<dim3((W + 255) / 256, (H + GV_TY - 1) / GV_TY, P), 256, 0, s>>>(in, tmp, H, W, n_planes, plane_stride, plane_sel, g);
+    CROG_LAUNCH_OK("gaussian_rows");
+    gaussian_horz_kernel<8><<<dim3((W + 255) / 256, (H + GH_ROWS - 1) / GH_ROWS, P), 256, 0, s>>>(tmp, out, H, W, n_planes, plane_stride, plane_sel, g);
+    CROG_LAUNCH_OK("gaussian_cols");
+    return CROG_OK;
+  }
   dim3 grid((W + 255) / 256, H, P);
   gaussian_pass_kernel<0><<<grid, 256, 0, s>>>(in, tmp, H, W, n_planes, plane_stride, plane_sel, g);
   CROG_LAUNCH_OK("gaussian_rows");
