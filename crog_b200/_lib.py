@@ -76,7 +76,8 @@ SIGNATURES = {
     "crog_ssg_masks": (C.c_int, [_P, _I, _I, _I, _P, _P, _P, _P, _P, _I, _P, _P, _I, _I, _I, _I, _P]),
     "crog_gaussian": (C.c_int, [_P, _P, _P, _I, _I, _I, _P, _I, _P, _I, _I, _P]),
     "crog_warp_affine_cubic_f32": (C.c_int, [_P, _I, _I, _I, _I, _P, _P, _I, _I, _F, _P]),
-    "crog_preprocess_u8": (C.c_int, [_P, _I, _I, _I, _P, _P, _I, _I, _P, _P, _P, _P]),
+    "crog_preprocess_workspace_bytes": (C.c_int64, []),
+    "crog_preprocess_u8": (C.c_int, [_P, _I, _I, _I, _P, _P, _I, _I, _P, _P, _P, _P, _P]),
     "crog_mask_iou": (C.c_int, [_P, _P, _I, _L, _F, _P, _P]),
 }
 

@@ -63,10 +63,19 @@ __device__ __forceinline__ SrcCoord src_coord(const double* __restrict__ M, int 
   return c;
 }
 
-// src [NP][B][Hs][Ws] -> dst [NP][B][h][w]; grid (ceil(w*h/256), B)
+// src [NP][B][Hs][Ws] -> dst [NP][B][h][w]; grid (ceil(w*h/256), B).  The 32 phases' 1-D cubic coefficients are tabulated
+// once per CTA in shared memory (they were ~50 non-contractable float operations per pixel and axis), the 16 weight
+// products are formed once per pixel and reused by every plane.
 __global__ void __launch_bounds__(256) warp_cubic_f32_kernel(const float* __restrict__ src, int NP, int B, int Hs, int Ws,
                                                              const double* __restrict__ minv, float* __restrict__ dst, int h,
                                                              int w, float cv) {
+  __shared__ float ctab[TAB][4];
+  if (threadIdx.x < TAB) {
+    float c4[4];
+    cubic_coeffs(threadIdx.x, c4);
+    ctab[threadIdx.x][0] = c4[0]; ctab[threadIdx.x][1] = c4[1]; ctab[threadIdx.x][2] = c4[2]; ctab[threadIdx.x][3] = c4[3];
+  }
+  __syncthreads();
   const int b = blockIdx.y;
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= h * w) return;
@@ -79,23 +88,30 @@ __global__ void __launch_bounds__(256) warp_cubic_f32_kernel(const float* __rest
     return;
   }
   float vx[4], vy[4];
-  cubic_coeffs(c.ax, vx);
-  cubic_coeffs(c.ay, vy);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) { vx[k] = ctab[c.ax][k]; vy[k] = ctab[c.ay][k]; }
   const bool inside = c.sx >= 0 && c.sx < max(Ws - 3, 0) && c.sy >= 0 && c.sy < max(Hs - 3, 0);
   if (inside) {
-    for (int pl = 0; pl < NP; ++pl) {
-      const float* S = src + ((long long)pl * B + b) * splane + (long long)c.sy * Ws + c.sx;
+    float wgt[16];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) wgt[i * 4 + j] = __fmul_rn(vy[i], vx[j]);
+    const float* S = src + (long long)b * splane + (long long)c.sy * Ws + c.sx;
+    float* D = dst + (long long)b * dplane + p;
+    const long long sstep = (long long)B * splane, dstep = (long long)B * dplane;
+    for (int pl = 0; pl < NP; ++pl, S += sstep, D += dstep) {
       float sum = 0.f;
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const float* R = S + i * Ws;
-        float r = __fmul_rn(__ldg(R), __fmul_rn(vy[i], vx[0]));
-        r = __fadd_rn(r, __fmul_rn(__ldg(R + 1), __fmul_rn(vy[i], vx[1])));
-        r = __fadd_rn(r, __fmul_rn(__ldg(R + 2), __fmul_rn(vy[i], vx[2])));
-        r = __fadd_rn(r, __fmul_rn(__ldg(R + 3), __fmul_rn(vy[i], vx[3])));
+        float r = __fmul_rn(__ldg(R), wgt[i * 4]);
+        r = __fadd_rn(r, __fmul_rn(__ldg(R + 1), wgt[i * 4 + 1]));
+        r = __fadd_rn(r, __fmul_rn(__ldg(R + 2), wgt[i * 4 + 2]));
+        r = __fadd_rn(r, __fmul_rn(__ldg(R + 3), wgt[i * 4 + 3]));
         sum = i == 0 ? r : __fadd_rn(sum, r);
       }
-      dst[((long long)pl * B + b) * dplane + p] = sum;
+      *D = sum;
     }
   } else {
     for (int pl = 0; pl < NP; ++pl) {
@@ -146,11 +162,32 @@ __device__ __forceinline__ void cubic_weights_i16(int ax, int ay, int (&wt)[16])
   }
 }
 
+// OpenCV's BicubicTab_i: the 16 int16 weights of every (ay, ax) phase pair, built on the device by the same routine the
+// per-pixel form used (so the table is bit-identical to it); 32 KB, rebuilt by every crog_preprocess_u8 call (~2 us).
+__global__ void __launch_bounds__(256) cubic_table_i16_kernel(short* __restrict__ tab) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;  // = ay * 32 + ax
+  if (t >= TAB * TAB) return;
+  int wt[16];
+  cubic_weights_i16(t % TAB, t / TAB, wt);
+#pragma unroll
+  for (int k = 0; k < 16; ++k) tab[t * 16 + k] = (short)wt[k];
+}
+
 // img [B][Ho][Wo][3] uint8 (RGB, HWC) -> out [B][3][S][S] float32 normalised; grid (ceil(S*S/256), B)
-__global__ void __launch_bounds__(256) preprocess_u8_kernel(const uint8_t* __restrict__ img, int B, int Ho, int Wo,
+__global__ void __launch_bounds__(256) preprocess_u8_kernel(const short* __restrict__ wtab, const uint8_t* __restrict__ img, int B, int Ho, int Wo,
                                                             const double* __restrict__ minv, float* __restrict__ out, int Sh,
                                                             int Sw, int cv0, int cv1, int cv2, float m0, float m1, float m2,
-                                                            float s0, float s1, float s2) {
+                                                            float s0, float s1, float s2, long long total_bytes) {
+  // the result pixel is an integer 0..255: (v / 255 - mean) / std has 256 possible values per channel, computed once per
+  // CTA with the reference's two IEEE divisions instead of six divisions per pixel
+  __shared__ float lut[3][256];
+  {
+    const float v = __fdiv_rn((float)threadIdx.x, 255.f);
+    lut[0][threadIdx.x] = __fdiv_rn(__fsub_rn(v, m0), s0);
+    lut[1][threadIdx.x] = __fdiv_rn(__fsub_rn(v, m1), s1);
+    lut[2][threadIdx.x] = __fdiv_rn(__fsub_rn(v, m2), s2);
+  }
+  __syncthreads();
   const int b = blockIdx.y;
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= Sh * Sw) return;
@@ -161,9 +198,39 @@ __global__ void __launch_bounds__(256) preprocess_u8_kernel(const uint8_t* __res
   const bool outside = c.sx >= Wo || c.sx + 4 <= 0 || c.sy >= Ho || c.sy + 4 <= 0;
   if (!outside) {
     int wt[16];
-    cubic_weights_i16(c.ax, c.ay, wt);
+    {
+      const int4* e = reinterpret_cast<const int4*>(wtab + (c.ay * TAB + c.ax) * 16);
+      const int4 e0 = __ldg(e), e1 = __ldg(e + 1);
+      const int q[8] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w};
+#pragma unroll
+      for (int k = 0; k < 8; ++k) { wt[2 * k] = (int)(short)(q[k] & 0xffff); wt[2 * k + 1] = q[k] >> 16; }
+    }
     int acc[3] = {cv0 * COEF_SCALE, cv1 * COEF_SCALE, cv2 * COEF_SCALE};
     const uint8_t* S = img + (long long)b * Ho * Wo * 3;
+    // Interior footprint (the common case): the 4 pixels x 3 channels of a footprint row are 12 contiguous bytes.  They are
+    // fetched as four ALIGNED 32-bit words and realigned with funnel shifts - 16 word loads per pixel instead of 48 byte
+    // loads; integer accumulation, so the order of the terms does not matter.  (The window may start up to 3 bytes before
+    // the row's first byte and ends at most 15 bytes after it: it must lie inside the batch's allocation.)
+    const long long off00 = ((long long)b * Ho * Wo + (long long)c.sy * Wo + c.sx) * 3;
+    const bool fast = c.sx >= 0 && c.sx + 3 < Wo && c.sy >= 0 && c.sy + 3 < Ho && (reinterpret_cast<uintptr_t>(img) & 3) == 0 &&
+                      ((off00 + 3LL * 3 * Wo) & ~3LL) + 16 <= total_bytes;
+    if (fast) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const long long off = off00 + (long long)i * Wo * 3;
+        const uint32_t* wp = reinterpret_cast<const uint32_t*>(img + (off & ~3LL));
+        const uint32_t w0 = __ldg(wp), w1 = __ldg(wp + 1), w2 = __ldg(wp + 2), w3 = __ldg(wp + 3);
+        const uint32_t sh = (uint32_t)(off & 3) * 8u;
+        const uint32_t v0 = __funnelshift_r(w0, w1, sh), v1 = __funnelshift_r(w1, w2, sh), v2 = __funnelshift_r(w2, w3, sh);
+        // bytes: v0 = R0 G0 B0 R1, v1 = G1 B1 R2 G2, v2 = B2 R3 G3 B3
+        const int r0 = v0 & 255, g0 = (v0 >> 8) & 255, b0 = (v0 >> 16) & 255, r1 = v0 >> 24;
+        const int g1 = v1 & 255, b1 = (v1 >> 8) & 255, r2 = (v1 >> 16) & 255, g2 = v1 >> 24;
+        const int b2 = v2 & 255, r3 = (v2 >> 8) & 255, g3 = (v2 >> 16) & 255, b3 = v2 >> 24;
+        acc[0] += (r0 - cv0) * wt[i * 4] + (r1 - cv0) * wt[i * 4 + 1] + (r2 - cv0) * wt[i * 4 + 2] + (r3 - cv0) * wt[i * 4 + 3];
+        acc[1] += (g0 - cv1) * wt[i * 4] + (g1 - cv1) * wt[i * 4 + 1] + (g2 - cv1) * wt[i * 4 + 2] + (g3 - cv1) * wt[i * 4 + 3];
+        acc[2] += (b0 - cv2) * wt[i * 4] + (b1 - cv2) * wt[i * 4 + 1] + (b2 - cv2) * wt[i * 4 + 2] + (b3 - cv2) * wt[i * 4 + 3];
+      }
+    } else
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int yy = c.sy + i;
@@ -183,11 +250,9 @@ __global__ void __launch_bounds__(256) preprocess_u8_kernel(const uint8_t* __res
       res[ch] = v < 0 ? 0 : (v > 255 ? 255 : v);
     }
   }
-  const float mean[3] = {m0, m1, m2}, sd[3] = {s0, s1, s2};
   const long long plane = (long long)Sh * Sw;
 #pragma unroll
-  for (int ch = 0; ch < 3; ++ch)
-    out[((long long)b * 3 + ch) * plane + p] = __fdiv_rn(__fsub_rn(__fdiv_rn((float)res[ch], 255.f), mean[ch]), sd[ch]);
+  for (int ch = 0; ch < 3; ++ch) out[((long long)b * 3 + ch) * plane + p] = lut[ch][res[ch]];
 }
 
 // inter/union pixel counts of (pred > thr) vs (target != 0), one CTA row per sample
@@ -226,9 +291,12 @@ extern "C" int crog_warp_affine_cubic_f32(const float* src, int32_t NP, int32_t 
   return CROG_OK;
 }
 
+extern "C" int64_t crog_preprocess_workspace_bytes(void) { return (int64_t)TAB * TAB * 16 * sizeof(short); }
+
 extern "C" int crog_preprocess_u8(const uint8_t* img, int32_t B, int32_t Ho, int32_t Wo, const double* minv, float* out,
                                   int32_t Sh, int32_t Sw, const double* border_rgb, const float* mean, const float* std_,
-                                  void* stream) {
+                                  void* workspace, void* stream) {
+  CROG_REQUIRE(workspace != nullptr && aligned16(workspace), CROG_E_BADALIGN, "preprocess: workspace (crog_preprocess_workspace_bytes) must be 16B aligned");
   CROG_REQUIRE(B >= 0 && Ho >= 1 && Wo >= 1 && Sh >= 1 && Sw >= 1, CROG_E_BADSHAPE, "preprocess: bad shape");
   CROG_REQUIRE(B <= 65535 && Ho < 32768 && Wo < 32768, CROG_E_BADSHAPE, "preprocess: size limits");
   if (B == 0) return CROG_OK;
@@ -237,9 +305,12 @@ extern "C" int crog_preprocess_u8(const uint8_t* img, int32_t B, int32_t Ho, int
     double r = nearbyint(border_rgb[i]);
     cv[i] = r < 0 ? 0 : (r > 255 ? 255 : (int)r);
   }
+  cubic_table_i16_kernel<<<(TAB * TAB + 255) / 256, 256, 0, (cudaStream_t)stream>>>((short*)workspace);
+  CROG_LAUNCH_OK("cubic_table_i16");
   dim3 grid((unsigned)(((long long)Sh * Sw + 255) / 256), (unsigned)B);
-  preprocess_u8_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(img, B, Ho, Wo, minv, out, Sh, Sw, cv[0], cv[1], cv[2], mean[0],
-                                                               mean[1], mean[2], std_[0], std_[1], std_[2]);
+  preprocess_u8_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const short*)workspace, img, B, Ho, Wo, minv, out, Sh, Sw, cv[0], cv[1], cv[2], mean[0],
+                                                               mean[1], mean[2], std_[0], std_[1], std_[2],
+                                                               (long long)B * Ho * Wo * 3);
   CROG_LAUNCH_OK("preprocess_u8");
   return CROG_OK;
 }

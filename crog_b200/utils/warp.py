@@ -21,6 +21,7 @@ import torch
 
 from .. import _lib as L
 
+_pre_ws = {}
 CLIP_MEAN = (0.48145466, 0.4578275, 0.40821073)
 CLIP_STD = (0.26862954, 0.26130258, 0.27577711)
 
@@ -145,9 +146,12 @@ def preprocess_images(img_u8: torch.Tensor, mats, input_size: Tuple[int, int] = 
     mean32 = torch.tensor(list(mean), dtype=torch.float32).numpy()
     std32 = torch.tensor(list(std), dtype=torch.float32).numpy()
     cm, cs = (C.c_float * 3)(*mean32.tolist()), (C.c_float * 3)(*std32.tolist())
+    ws = _pre_ws.get(dev.index)
+    if ws is None:  # OpenCV's 32 x 32 table of int16 bicubic weight sets; the call rebuilds it on the stream (ordered)
+        ws = _pre_ws[dev.index] = torch.empty(int(L.load().crog_preprocess_workspace_bytes()), dtype=torch.uint8, device=dev)
     with torch.cuda.device(dev):
         L.check(lib.crog_preprocess_u8(img_u8.data_ptr(), B, Ho, Wo, minv.data_ptr(), out.data_ptr(), Sh, Sw, border, cm, cs,
-                                       L.stream_ptr()))
+                                       ws.data_ptr(), L.stream_ptr()))
     return out
 
 

@@ -294,9 +294,11 @@ int crog_warp_affine_cubic_f32(const float* src, int32_t NP, int32_t B, int32_t 
                                float* dst, int32_t h, int32_t w, float border_value, void* stream);
 /* utils/dataset.py:843-866: cv2.warpAffine(img_u8, mat, input_size, INTER_CUBIC, borderValue=border_rgb) then
  * .float().div_(255.).sub_(mean).div_(std): img [B][Ho][Wo][3] uint8 RGB -> out [B][3][Sh][Sw] fp32.  minv as above;
- * border_rgb (3 doubles), mean, std_ (3 floats each) are HOST pointers.  Bit-exact (int16 fixed-point weights). */
+ * border_rgb (3 doubles), mean, std_ (3 floats each) are HOST pointers.  Bit-exact (int16 fixed-point weights).
+ * workspace: crog_preprocess_workspace_bytes() device bytes (OpenCV's 32 x 32 table of int16 weight sets, rebuilt by the call). */
+int64_t crog_preprocess_workspace_bytes(void);
 int crog_preprocess_u8(const uint8_t* img, int32_t B, int32_t Ho, int32_t Wo, const double* minv, float* out, int32_t Sh,
-                       int32_t Sw, const double* border_rgb, const float* mean, const float* std_, void* stream);
+                       int32_t Sw, const double* border_rgb, const float* mean, const float* std_, void* workspace, void* stream);
 /* engine/crog_engine.py:500-501,515-518: per sample pixel counts of (pred > thr) & (target != 0) and (pred > thr) |
  * (target != 0): counts [B,2] int64 = {inter, union} (zeroed by the call). */
 int crog_mask_iou(const float* pred, const float* target, int32_t B, int64_t n, float thr, int64_t* counts, void* stream);
