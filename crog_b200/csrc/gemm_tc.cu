@@ -47,17 +47,27 @@ enum { MODE_LEGACY = 0, MODE_TMA_BF16 = 1, MODE_TMA_F32 = 2 };
 // TMEM receives its own 128 x BN accumulator.  Per CTA and k-block that is 32 KB written + 32 KB read from shared
 // memory instead of 48 + 48: at full tensor rate 125 B/clk instead of 187 B/clk against a 128 B/clk shared-memory port,
 // which is what caps the single-CTA 128 x 256 tile at ~67 % tensor utilisation.
-template <int BN, int STAGES, int NBUF, bool CONV3, int EPI_WARPS, bool PAIR = false>
+// BAND (3x3 convolutions on the zero-haloed layout, any cin, streamed weights): the activation operand is staged as one
+// (BM + 2)-row BAND per (ky, 64-channel chunk) in its own ring of STAGES slots, and the three kx taps read it through
+// row-shifted descriptor views (as CONV3 does), while the weight tiles stream through a second ring of NBST slots, one
+// per (ky, kx, chunk).  The big 3x3 convolutions are bound by the L2 -> SM fabric (the launch list shows 11.3 TB/s of TMA
+// traffic into the SMs for proj.vis.3, the measured cap is ~6300 B/clk = 12 TB/s at 1.9 GHz): fetching every activation
+// row once per ky instead of once per tap removes two thirds of the activation half of that traffic.
+template <int BN, int STAGES, int NBUF, bool CONV3, int EPI_WARPS, bool PAIR = false, int NBST = 0>
 struct Cfg {
   static_assert(!(PAIR && CONV3), "the CTA-pair path is for the generic k-loop");
+  static constexpr bool BAND = NBST > 0;
+  static_assert(!(BAND && CONV3), "BAND streams the weights, CONV3 keeps them resident");
   static constexpr int NUM_THREADS = 64 + EPI_WARPS * 32;
-  static constexpr int A_ROWS = CONV3 ? BM + 2 : BM;
+  static constexpr int A_ROWS = (CONV3 || BAND) ? BM + 2 : BM;
   static constexpr int A_TX = A_ROWS * BK * 2;                 // bytes one A box delivers
   static constexpr int A_BYTES = ((A_TX + 1023) / 1024) * 1024;
   static constexpr int B_ROWS = PAIR ? BN / 2 : BN;            // weight rows this CTA stages
   static constexpr int B_BYTES = B_ROWS * BK * 2;
-  static constexpr int STAGE_BYTES = CONV3 ? A_BYTES : A_BYTES + ((B_BYTES + 1023) / 1024) * 1024;
-  static constexpr int BRES_BYTES = CONV3 ? 9 * B_BYTES : 0;   // resident weights
+  static constexpr int BB_BYTES = ((B_BYTES + 1023) / 1024) * 1024;
+  static constexpr int STAGE_BYTES = (CONV3 || BAND) ? A_BYTES : A_BYTES + BB_BYTES;
+  static constexpr int BRING_OFF = STAGES * STAGE_BYTES;       // BAND: the weight ring follows the band ring
+  static constexpr int BRES_BYTES = CONV3 ? 9 * B_BYTES : (BAND ? NBST * BB_BYTES : 0);   // resident weights / weight ring
   static constexpr int SUB = BN > 32 ? 32 : BN;               // legacy: columns staged at a time
   static constexpr int PITCH = SUB * 4 + 16;                  // legacy staging row pitch (bytes): 16B-phase conflict free
   static constexpr int STG_WARP = NBUF * STG_BUF;             // per epilogue warp (>= 32 * PITCH = 4608)
@@ -65,7 +75,7 @@ struct Cfg {
   static constexpr int STG_OFF = BRES_OFF + BRES_BYTES;
   static constexpr int BAR_OFF = STG_OFF + EPI_WARPS * STG_WARP;
   static constexpr int NACC = EPI_WARPS / 4 < 2 ? 2 : EPI_WARPS / 4;  // TMEM accumulator buffers: one per epilogue group, at least two
-  static constexpr int NBARS = 2 * STAGES + 2 * NACC + 1 + EPI_WARPS * NBUF;  // full[S], empty[S], tfull[NACC], tempty[NACC], bres, res[EPI][NBUF]
+  static constexpr int NBARS = 2 * STAGES + 2 * NACC + 1 + EPI_WARPS * NBUF + 2 * NBST;  // full[S], empty[S], tfull[NACC], tempty[NACC], bres, res[EPI][NBUF], bfull[NBST], bempty[NBST]
   // per epilogue group: this tile's scale / bias slice, double buffered by tile parity ([2][scale | bias][BN] floats);
   // configurations whose operand ring leaves no room for it (long contractions, where the epilogue hides under the
   // mainloop anyway) keep reading scale / bias through the read-only cache
@@ -78,14 +88,15 @@ struct Cfg {
   static_assert(NBUF >= 2 && STG_WARP >= 32 * PITCH, "staging too small");
 };
 
-template <int BN, int STAGES, int NBUF, int MODE, bool CONV3, int EPI_WARPS, bool PAIR>
+template <int BN, int STAGES, int NBUF, int MODE, bool CONV3, int EPI_WARPS, bool PAIR, int NBST>
 __global__ void __launch_bounds__(64 + EPI_WARPS * 32, 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                    const __grid_constant__ CUtensorMap tmA2,
                                                                    const __grid_constant__ CUtensorMap tmB,
                                                                    const __grid_constant__ CUtensorMap tmOut,
                                                                    const __grid_constant__ CUtensorMap tmRes,
                                                                    const CrogGemm g, int n_tiles, int total_tiles) {
-  using L = Cfg<BN, STAGES, NBUF, CONV3, EPI_WARPS, PAIR>;
+  using L = Cfg<BN, STAGES, NBUF, CONV3, EPI_WARPS, PAIR, NBST>;
+  constexpr bool BAND = NBST > 0;
   constexpr int GROUPS = EPI_WARPS / 4;
   constexpr int MT = PAIR ? 2 * BM : BM;  // rows of one tile (over the CTA pair)
   extern __shared__ uint8_t smem_raw[];
@@ -106,7 +117,8 @@ __global__ void __launch_bounds__(64 + EPI_WARPS * 32, 1) gemm_tc_kernel(const _
   const int num_kb = CONV3 ? 3 : g.taps * kchunks + g.cin2 / BK;  // CONV3: one k-block per ky band; a2: its chunks follow a's
   const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + STAGES), tfull0 = smem_u32(bars + 2 * STAGES),
                  tempty0 = smem_u32(bars + 2 * STAGES + L::NACC), bres = smem_u32(bars + 2 * STAGES + 2 * L::NACC),
-                 res0 = smem_u32(bars + 2 * STAGES + 2 * L::NACC + 1);
+                 res0 = smem_u32(bars + 2 * STAGES + 2 * L::NACC + 1),
+                 bfull0 = smem_u32(bars + 2 * STAGES + 2 * L::NACC + 1 + EPI_WARPS * NBUF), bempty0 = bfull0 + 8 * NBST;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -120,6 +132,7 @@ __global__ void __launch_bounds__(64 + EPI_WARPS * 32, 1) gemm_tc_kernel(const _
     for (int s = 0; s < STAGES; ++s) { mbar_init(full0 + 8 * s, PAIR ? 2 : 1); mbar_init(empty0 + 8 * s, 1); }
     for (int s = 0; s < L::NACC; ++s) { mbar_init(tfull0 + 8 * s, 1); mbar_init(tempty0 + 8 * s, (PAIR ? 2 : 1) * 4 * 32); }
     for (int s = 0; s < EPI_WARPS * NBUF; ++s) mbar_init(res0 + 8 * s, 1);
+    for (int s = 0; s < NBST; ++s) { mbar_init(bfull0 + 8 * s, PAIR ? 2 : 1); mbar_init(bempty0 + 8 * s, 1); }
     mbar_init(bres, 1);
     fence_barrier_init();
   }
@@ -149,6 +162,46 @@ __global__ void __launch_bounds__(64 + EPI_WARPS * 32, 1) gemm_tc_kernel(const _
             tma_load_2d(smem_u32(smem + s * L::STAGE_BYTES), &tmA, 0, (int)(row0 + (ky - 1) * (g.W + 2) - 1), full0 + 8 * s);
           }
         }
+      } else if constexpr (BAND) {
+        int ia = 0, ib = 0;  // band / weight-tile ring positions
+        for (int tile = tile0; tile < total_tiles; tile += tstep) {
+          const int n_t = tile % n_tiles, m_t = tile / n_tiles;
+          const long long row0 = (long long)m_t * MT + (PAIR ? (long long)rank * BM : 0);
+          const int wrow0 = n_t * BN + (PAIR ? (int)rank * L::B_ROWS : 0);
+          for (int ky = 0; ky < 3; ++ky)
+            for (int c = 0; c < kchunks; ++c) {
+              {
+                const int sA = ia % STAGES, it = ia / STAGES;
+                ++ia;
+                mbar_wait(empty0 + 8 * sA, (it & 1) ^ 1);
+                const uint32_t sa = smem_u32(smem + sA * L::STAGE_BYTES);
+                if constexpr (PAIR) {
+                  const uint32_t lfull = mapa_shared(full0 + 8 * sA, 0);
+                  mbar_expect_tx_cluster(lfull, L::A_TX);
+                  tma_load_2d_pair(sa, &tmA, c * BK, (int)(row0 + (ky - 1) * (g.W + 2) - 1), lfull);
+                } else {
+                  mbar_expect_tx(full0 + 8 * sA, L::A_TX);
+                  tma_load_2d(sa, &tmA, c * BK, (int)(row0 + (ky - 1) * (g.W + 2) - 1), full0 + 8 * sA);
+                }
+              }
+#pragma unroll
+              for (int kx = 0; kx < 3; ++kx) {
+                const int sB = ib % NBST, it = ib / NBST;
+                ++ib;
+                mbar_wait(bempty0 + 8 * sB, (it & 1) ^ 1);
+                const uint32_t sb = smem_u32(smem + L::BRING_OFF + sB * L::BB_BYTES);
+                const int wcol = (ky * 3 + kx) * g.cin + c * BK;
+                if constexpr (PAIR) {
+                  const uint32_t lfull = mapa_shared(bfull0 + 8 * sB, 0);
+                  mbar_expect_tx_cluster(lfull, L::B_BYTES);
+                  tma_load_2d_pair(sb, &tmB, wcol, wrow0, lfull);
+                } else {
+                  mbar_expect_tx(bfull0 + 8 * sB, L::B_BYTES);
+                  tma_load_2d(sb, &tmB, wcol, wrow0, bfull0 + 8 * sB);
+                }
+              }
+            }
+        }
       } else
       for (int tile = tile0; tile < total_tiles; tile += tstep) {
         const int n_t = tile % n_tiles, m_t = tile / n_tiles;
@@ -159,19 +212,25 @@ __global__ void __launch_bounds__(64 + EPI_WARPS * 32, 1) gemm_tc_kernel(const _
           const int s = kbg % STAGES, it = kbg / STAGES;
           mbar_wait(empty0 + 8 * s, (it & 1) ^ 1);
           const uint32_t sa = smem_u32(smem + s * L::STAGE_BYTES), sb = sa + L::A_BYTES;
-          const int tap = kb / kchunks, c0 = (kb % kchunks) * BK;
+          // k-block order.  3x3 convolutions: (ky, 64-channel chunk, kx) - the same order in every tile configuration
+          // (single CTA, CTA pair, BAND, CONV3), so that the fp32 accumulation and hence every output bit is independent
+          // of the configuration the autotuner picks; everything else: (tap, chunk), the second operand's chunks last.
+          int tap, c0;
+          if (g.taps == 9) { const int kyc = kb / 3; tap = (kyc / kchunks) * 3 + kb % 3; c0 = (kyc % kchunks) * BK; }
+          else { tap = kb / kchunks; c0 = (kb % kchunks) * BK; }
+          const int wcol = g.taps == 9 ? tap * g.cin + c0 : kb * BK;
           if constexpr (PAIR) {
             // both CTAs report to the LEADER's full barrier; this CTA stages its own rows of A and its half of the weights
             const uint32_t lfull = mapa_shared(full0 + 8 * s, 0);
             mbar_expect_tx_cluster(lfull, L::A_BYTES + L::B_BYTES);
             if (kb >= g.taps * kchunks) tma_load_2d_pair(sa, &tmA2, (kb - kchunks) * BK, (int)tr.row0, lfull);  // second operand (taps == 1)
             else tma_load_2d_pair(sa, &tmA, c0, (int)(tr.row0 + tap_shift(g.taps, tap, g.W)), lfull);
-            tma_load_2d_pair(sb, &tmB, kb * BK, wrow0 + (int)rank * L::B_ROWS, lfull);
+            tma_load_2d_pair(sb, &tmB, wcol, wrow0 + (int)rank * L::B_ROWS, lfull);
           } else {
             mbar_expect_tx(full0 + 8 * s, L::A_BYTES + L::B_BYTES);
             if (kb >= g.taps * kchunks) tma_load_2d(sa, &tmA2, (kb - kchunks) * BK, (int)tr.row0, full0 + 8 * s);  // second operand (taps == 1)
             else tma_load_2d(sa, &tmA, c0, (int)(tr.row0 + tap_shift(g.taps, tap, g.W)), full0 + 8 * s);
-            tma_load_2d(sb, &tmB, kb * BK, wrow0, full0 + 8 * s);
+            tma_load_2d(sb, &tmB, wcol, wrow0, full0 + 8 * s);
           }
         }
       }
@@ -227,6 +286,33 @@ __global__ void __launch_bounds__(64 + EPI_WARPS * 32, 1) gemm_tc_kernel(const _
               }
               tc_commit(empty0 + 8 * s);
             }
+          }
+        } else if constexpr (BAND) {
+          for (int kyc = 0; kyc < 3 * kchunks; ++kyc, ++kbg) {  // kbg counts bands here; the weight ring has its own cursor
+            const int sA = kbg % STAGES, ita = kbg / STAGES;
+            mbar_wait(full0 + 8 * sA, ita & 1);
+            const uint32_t sa = smem_u32(smem + sA * L::STAGE_BYTES);
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) {
+              const int ibm = kbg * 3 + kx, sB = ibm % NBST, itb = ibm / NBST;
+              mbar_wait(bfull0 + 8 * sB, itb & 1);
+              tc_fence_after();
+              const uint64_t da = make_sdesc(sa + kx * 128);  // rows [kx, kx + 128) of the band (see CONV3)
+              const uint64_t db = make_sdesc(smem_u32(smem + L::BRING_OFF + sB * L::BB_BYTES));
+              if constexpr (PAIR) {
+#pragma unroll
+                for (int k = 0; k < BK / UMMA_K; ++k)
+                  tc_mma_bf16_pair(tacc, da + (uint64_t)(k * UMMA_K * 2 / 16), db + (uint64_t)(k * UMMA_K * 2 / 16), idesc, (kyc | kx | k) != 0);
+                tc_commit_pair(bempty0 + 8 * sB, 3);
+              } else {
+#pragma unroll
+                for (int k = 0; k < BK / UMMA_K; ++k)
+                  tc_mma_bf16(tacc, da + (uint64_t)(k * UMMA_K * 2 / 16), db + (uint64_t)(k * UMMA_K * 2 / 16), idesc, (kyc | kx | k) != 0);
+                tc_commit(bempty0 + 8 * sB);
+              }
+            }
+            if constexpr (PAIR) tc_commit_pair(empty0 + 8 * sA, 3);
+            else tc_commit(empty0 + 8 * sA);
           }
         } else
         for (int kb = 0; kb < num_kb; ++kb, ++kbg) {
@@ -577,14 +663,14 @@ __global__ void __launch_bounds__(64 + EPI_WARPS * 32, 1) gemm_tc_kernel(const _
 // ---------------------------------------------------------------- host side
 int g_num_sms = 0;
 
-template <int BN, int STAGES, int NBUF, int MODE, bool CONV3 = false, int EPI_WARPS = 8, bool PAIR = false>
+template <int BN, int STAGES, int NBUF, int MODE, bool CONV3 = false, int EPI_WARPS = 8, bool PAIR = false, int NBST = 0>
 int launch(const CrogGemm* g, cudaStream_t stream) {
-  using L = Cfg<BN, STAGES, NBUF, CONV3, EPI_WARPS, PAIR>;
+  using L = Cfg<BN, STAGES, NBUF, CONV3, EPI_WARPS, PAIR, NBST>;
   static_assert(L::TOTAL <= 227 * 1024, "shared memory budget");
   static DeviceOnce once;  // function attributes are per device (one static per template instantiation)
   int dev = 0;
   if (once.need(&dev) || g_num_sms == 0) {
-    CROG_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES, NBUF, MODE, CONV3, EPI_WARPS, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+    CROG_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES, NBUF, MODE, CONV3, EPI_WARPS, PAIR, NBST>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
     CROG_CUDA_OK(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
     once.done(dev);
   }
@@ -625,12 +711,12 @@ int launch(const CrogGemm* g, cudaStream_t stream) {
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
-    CROG_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, STAGES, NBUF, MODE, CONV3, EPI_WARPS, PAIR>, tmA, tmA2, tmB, tmOut, tmRes, *g, n_tiles, total));
+    CROG_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, STAGES, NBUF, MODE, CONV3, EPI_WARPS, PAIR, NBST>, tmA, tmA2, tmB, tmOut, tmRes, *g, n_tiles, total));
     return CROG_OK;
   }
   int grid = total < g_num_sms ? total : g_num_sms;
   if (g->max_ctas > 0 && grid > g->max_ctas) grid = g->max_ctas;
-  crog_launch(gemm_tc_kernel<BN, STAGES, NBUF, MODE, CONV3, EPI_WARPS, PAIR>, dim3(grid), dim3(L::NUM_THREADS), L::TOTAL, stream, tmA, tmA2, tmB, tmOut, tmRes, *g, n_tiles, total);
+  crog_launch(gemm_tc_kernel<BN, STAGES, NBUF, MODE, CONV3, EPI_WARPS, PAIR, NBST>, dim3(grid), dim3(L::NUM_THREADS), L::TOTAL, stream, tmA, tmA2, tmB, tmOut, tmRes, *g, n_tiles, total);
   CROG_LAUNCH_OK("gemm_tc");
   return CROG_OK;
 }
@@ -640,6 +726,7 @@ int dispatch(const CrogGemm* g, cudaStream_t stream) {
   const long long Ktot = (long long)g->taps * g->cin + g->cin2;
   const bool conv3_ok = g->N <= 64 && g->taps == 9 && g->cin == BK && g->w_sample_stride == 0;
   const bool pair_ok = g->w_sample_stride == 0 && g->M > BM;  // shared weights, more than one CTA's worth of rows
+  const bool band_ok = g->taps == 9 && g->in_padded && g->w_sample_stride == 0 && g->a2 == nullptr && g->H > 0;
   if (g->tile_cfg != CROG_TILE_AUTO) {
     // forced configuration (plan-time autotuner, tests): every one of them accumulates the k-blocks in the same order
     switch (g->tile_cfg) {
@@ -665,11 +752,35 @@ int dispatch(const CrogGemm* g, cudaStream_t stream) {
       case CROG_TILE_CONV3:
         CROG_REQUIRE(conv3_ok, CROG_E_BADSHAPE, "gemm_tc: CONV3 tiles need a shared 3x3 kernel with cin == 64 and N <= 64");
         return launch<64, 5, 2, MODE, true>(g, stream);
+      case CROG_TILE_BAND_PAIR_256x256:
+        CROG_REQUIRE(band_ok && pair_ok && g->N > 128, CROG_E_BADSHAPE, "gemm_tc: BAND pair 256x256 needs a shared 3x3 kernel on the padded layout, M > 128, N > 128");
+        return launch<256, 3, 2, MODE, false, 4, true, 6>(g, stream);
+      case CROG_TILE_BAND_PAIR_256x256_E8:
+        CROG_REQUIRE(band_ok && pair_ok && g->N > 128, CROG_E_BADSHAPE, "gemm_tc: BAND pair 256x256 needs a shared 3x3 kernel on the padded layout, M > 128, N > 128");
+        return launch<256, 3, 2, MODE, false, 8, true, 5>(g, stream);
+      case CROG_TILE_BAND_PAIR_256x128:
+        CROG_REQUIRE(band_ok && pair_ok && g->N > 64, CROG_E_BADSHAPE, "gemm_tc: BAND pair 256x128 needs a shared 3x3 kernel on the padded layout, M > 128, N > 64");
+        return launch<128, 4, 2, MODE, false, 8, true, 8>(g, stream);
+      case CROG_TILE_BAND_128x128:
+        CROG_REQUIRE(band_ok && g->N > 64, CROG_E_BADSHAPE, "gemm_tc: BAND 128x128 needs a shared 3x3 kernel on the padded layout, N > 64");
+        return launch<128, 3, 2, MODE, false, 8, false, 6>(g, stream);
+      case CROG_TILE_BAND_128x256:
+        CROG_REQUIRE(band_ok && g->N > 128, CROG_E_BADSHAPE, "gemm_tc: BAND 128x256 needs a shared 3x3 kernel on the padded layout, N > 128");
+        return launch<256, 3, 2, MODE, false, 4, false, 4>(g, stream);
       default: CROG_REQUIRE(false, CROG_E_BADSHAPE, "gemm_tc: unknown tile_cfg %d", g->tile_cfg);
     }
   }
   if (conv3_ok && !getenv("CROG_GEMM_NO_CONV3")) return launch<64, 5, 2, MODE, true>(g, stream);
   if (g->N <= 64) return launch<64, 5, 3, MODE>(g, stream);
+  // 3x3 convolutions on the zero-haloed layout: activation bands (a third of the activation traffic into the SMs, which
+  // is what bounds them: measured +20-40 % on every such layer of the forward); CROG_GEMM_NO_BAND restores the per-tap loop
+  if (band_ok && !getenv("CROG_GEMM_NO_BAND")) {
+    if (g->N % 256 == 0) {
+      if (pair_ok && g->M >= 2 * 256 * 74) return launch<256, 3, 2, MODE, false, 4, true, 6>(g, stream);
+      return launch<256, 3, 2, MODE, false, 4, false, 4>(g, stream);
+    }
+    return launch<128, 3, 2, MODE, false, 8, false, 6>(g, stream);
+  }
   // 128 x 256 tiles cut the L2 -> smem operand traffic per FLOP by 25 % ((BM+BN)/(BM*BN)); worth it when the
   // contraction is long enough to be tensor/L2 bound rather than epilogue bound
   if (g->N % 256 == 0 && Ktot >= 1024) {

@@ -136,7 +136,16 @@ enum {
                                    the default for short contractions, where the epilogue is the pace */
   CROG_TILE_128x128_E12 = 10,   /* one CTA, 128 x 128 tiles, 3 stages, THREE epilogue groups (12 warps, three TMEM accumulators,
                                    2 staging buffers per warp): more warps per scheduler for epilogue-bound layers */
-  CROG_TILE_COUNT = 11
+  /* BAND configurations (3x3 convolutions on the zero-haloed layout with shared weights): one (BM + 2)-row activation
+     band per (ky, 64-channel chunk) serves the three kx taps through row-shifted views while the weight tiles stream
+     through their own ring - a third of the activation traffic between L2 and the SMs, which is what bounds the large
+     convolutions.  Same k-block order as every other configuration, hence bit-identical results. */
+  CROG_TILE_BAND_PAIR_256x256 = 11,    /* CTA pair, 256 x 256 tiles, 3 band + 6 weight stages, one epilogue group per CTA */
+  CROG_TILE_BAND_PAIR_256x256_E8 = 12, /* CTA pair, 256 x 256 tiles, 3 band + 5 weight stages, two epilogue groups per CTA */
+  CROG_TILE_BAND_PAIR_256x128 = 13,    /* CTA pair, 256 x 128 tiles, 4 band + 8 weight stages, two epilogue groups per CTA */
+  CROG_TILE_BAND_128x128 = 14,         /* one CTA, 128 x 128 tiles, 3 band + 6 weight stages, two epilogue groups */
+  CROG_TILE_BAND_128x256 = 15,         /* one CTA, 128 x 256 tiles, 3 band + 4 weight stages, one epilogue group */
+  CROG_TILE_COUNT = 16
 };
 int crog_gemm(const CrogGemm* g, void* stream);
 

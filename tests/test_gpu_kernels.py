@@ -500,6 +500,11 @@ def test_tile_cfgs_bit_identical(case):
         assert L.TILE_PAIR_256x128 in ran
     else:
         assert L.TILE_CONV3 in ran
+    if case in ("conv3x3_pad2pad", "conv3x3_pad2compact"):  # activation-band configurations (3x3 on the padded layout)
+        assert {L.TILE_BAND_PAIR_256x256, L.TILE_BAND_PAIR_256x256_E8, L.TILE_BAND_PAIR_256x128, L.TILE_BAND_128x128,
+                L.TILE_BAND_128x256} <= set(ran)
+    elif not case.startswith("conv3x3"):
+        assert not any(c >= L.TILE_BAND_PAIR_256x256 for c in ran)
 
 
 def test_plan_autotune_keeps_results():
