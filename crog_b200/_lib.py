@@ -19,7 +19,8 @@ IMPL_AUTO, IMPL_SIMT, IMPL_TCGEN05 = 0, 1, 2
 # CROG_TILE_* of include/crog_b200.h (CrogGemm.tile_cfg)
 (TILE_AUTO, TILE_128x128, TILE_128x256, TILE_128x256_E8, TILE_PAIR_256x256, TILE_PAIR_256x256_E8, TILE_PAIR_256x128,
  TILE_128x64, TILE_CONV3, TILE_128x128_S3, TILE_128x128_E12, TILE_BAND_PAIR_256x256, TILE_BAND_PAIR_256x256_E8,
- TILE_BAND_PAIR_256x128, TILE_BAND_128x128, TILE_BAND_128x256, TILE_COUNT) = range(17)
+ TILE_BAND_PAIR_256x128, TILE_BAND_128x128, TILE_BAND_128x256, TILE_CONV3_E12, TILE_CONV3_PAIR, TILE_CONV3_DUAL,
+ TILE_COUNT) = range(20)
 RS_COPY, RS_AVGPOOL2, RS_BILINEAR2, RS_SUBSAMPLE2, RS_BILINEAR2_AC = 0, 1, 2, 3, 4
 
 

@@ -53,12 +53,16 @@ enum { MODE_LEGACY = 0, MODE_TMA_BF16 = 1, MODE_TMA_F32 = 2 };
 // per (ky, kx, chunk).  The big 3x3 convolutions are bound by the L2 -> SM fabric (the launch list shows 11.3 TB/s of TMA
 // traffic into the SMs for proj.vis.3, the measured cap is ~6300 B/clk = 12 TB/s at 1.9 GHz): fetching every activation
 // row once per ky instead of once per tap removes two thirds of the activation half of that traffic.
-template <int BN, int STAGES, int NBUF, bool CONV3, int EPI_WARPS, bool PAIR = false, int NBST = 0>
+// DUAL (CONV3 only): two MMA-issuing warps, one per TMEM accumulator buffer, take the tiles alternately.  A 128 x 64 tile
+// is 36 short MMAs (32 clocks each); the issuing thread spends ~570 instructions per tile on descriptors, election loops
+// and barrier polls and was measured as the pace of the kernel (it never waits; tensor pipe 39 % active).
+template <int BN, int STAGES, int NBUF, bool CONV3, int EPI_WARPS, bool PAIR = false, int NBST = 0, bool DUAL = false>
 struct Cfg {
-  static_assert(!(PAIR && CONV3), "the CTA-pair path is for the generic k-loop");
+  static_assert(!DUAL || (CONV3 && EPI_WARPS == 8), "dual issue: CONV3 with two accumulator buffers");
+  static constexpr int EPI_WARP0 = DUAL ? 3 : 2;               // first epilogue warp
   static constexpr bool BAND = NBST > 0;
   static_assert(!(BAND && CONV3), "BAND streams the weights, CONV3 keeps them resident");
-  static constexpr int NUM_THREADS = 64 + EPI_WARPS * 32;
+  static constexpr int NUM_THREADS = (DUAL ? 96 : 64) + EPI_WARPS * 32;
   static constexpr int A_ROWS = (CONV3 || BAND) ? BM + 2 : BM;
   static constexpr int A_TX = A_ROWS * BK * 2;                 // bytes one A box delivers
   static constexpr int A_BYTES = ((A_TX + 1023) / 1024) * 1024;
@@ -88,14 +92,14 @@ struct Cfg {
   static_assert(NBUF >= 2 && STG_WARP >= 32 * PITCH, "staging too small");
 };
 
-template <int BN, int STAGES, int NBUF, int MODE, bool CONV3, int EPI_WARPS, bool PAIR, int NBST>
-__global__ void __launch_bounds__(64 + EPI_WARPS * 32, 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
+template <int BN, int STAGES, int NBUF, int MODE, bool CONV3, int EPI_WARPS, bool PAIR, int NBST, bool DUAL>
+__global__ void __launch_bounds__((DUAL ? 96 : 64) + EPI_WARPS * 32, 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                    const __grid_constant__ CUtensorMap tmA2,
                                                                    const __grid_constant__ CUtensorMap tmB,
                                                                    const __grid_constant__ CUtensorMap tmOut,
                                                                    const __grid_constant__ CUtensorMap tmRes,
                                                                    const CrogGemm g, int n_tiles, int total_tiles) {
-  using L = Cfg<BN, STAGES, NBUF, CONV3, EPI_WARPS, PAIR, NBST>;
+  using L = Cfg<BN, STAGES, NBUF, CONV3, EPI_WARPS, PAIR, NBST, DUAL>;
   constexpr bool BAND = NBST > 0;
   constexpr int GROUPS = EPI_WARPS / 4;
   constexpr int MT = PAIR ? 2 * BM : BM;  // rows of one tile (over the CTA pair)
@@ -133,7 +137,7 @@ __global__ void __launch_bounds__(64 + EPI_WARPS * 32, 1) gemm_tc_kernel(const _
     for (int s = 0; s < L::NACC; ++s) { mbar_init(tfull0 + 8 * s, 1); mbar_init(tempty0 + 8 * s, (PAIR ? 2 : 1) * 4 * 32); }
     for (int s = 0; s < EPI_WARPS * NBUF; ++s) mbar_init(res0 + 8 * s, 1);
     for (int s = 0; s < NBST; ++s) { mbar_init(bfull0 + 8 * s, PAIR ? 2 : 1); mbar_init(bempty0 + 8 * s, 1); }
-    mbar_init(bres, 1);
+    mbar_init(bres, PAIR ? 2 : 1);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -151,15 +155,27 @@ __global__ void __launch_bounds__(64 + EPI_WARPS * 32, 1) gemm_tc_kernel(const _
     if (lane == 0) {
       int kbg = 0;  // k-blocks issued so far (ring position)
       if constexpr (CONV3) {
-        mbar_expect_tx(bres, L::BRES_BYTES);
-        for (int t = 0; t < 9; ++t) tma_load_2d(smem_u32(smem + L::BRES_OFF + t * L::B_BYTES), &tmB, t * BK, 0, bres);
+        if constexpr (PAIR) {  // each CTA keeps its half of the weight rows; both report to the leader's barrier
+          const uint32_t lbres = mapa_shared(bres, 0);
+          mbar_expect_tx_cluster(lbres, L::BRES_BYTES);
+          for (int t = 0; t < 9; ++t) tma_load_2d_pair(smem_u32(smem + L::BRES_OFF + t * L::B_BYTES), &tmB, t * BK, (int)rank * L::B_ROWS, lbres);
+        } else {
+          mbar_expect_tx(bres, L::BRES_BYTES);
+          for (int t = 0; t < 9; ++t) tma_load_2d(smem_u32(smem + L::BRES_OFF + t * L::B_BYTES), &tmB, t * BK, 0, bres);
+        }
         for (int tile = tile0; tile < total_tiles; tile += tstep) {
-          const long long row0 = (long long)tile * BM;  // n_tiles == 1
+          const long long row0 = (long long)tile * MT + (PAIR ? (long long)rank * BM : 0);  // n_tiles == 1
           for (int ky = 0; ky < 3; ++ky, ++kbg) {
             const int s = kbg % STAGES, it = kbg / STAGES;
             mbar_wait(empty0 + 8 * s, (it & 1) ^ 1);
-            mbar_expect_tx(full0 + 8 * s, L::A_TX);
-            tma_load_2d(smem_u32(smem + s * L::STAGE_BYTES), &tmA, 0, (int)(row0 + (ky - 1) * (g.W + 2) - 1), full0 + 8 * s);
+            if constexpr (PAIR) {
+              const uint32_t lfull = mapa_shared(full0 + 8 * s, 0);
+              mbar_expect_tx_cluster(lfull, L::A_TX);
+              tma_load_2d_pair(smem_u32(smem + s * L::STAGE_BYTES), &tmA, 0, (int)(row0 + (ky - 1) * (g.W + 2) - 1), lfull);
+            } else {
+              mbar_expect_tx(full0 + 8 * s, L::A_TX);
+              tma_load_2d(smem_u32(smem + s * L::STAGE_BYTES), &tmA, 0, (int)(row0 + (ky - 1) * (g.W + 2) - 1), full0 + 8 * s);
+            }
           }
         }
       } else if constexpr (BAND) {
@@ -235,12 +251,15 @@ __global__ void __launch_bounds__(64 + EPI_WARPS * 32, 1) gemm_tc_kernel(const _
         }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == 1 || (DUAL && warp == 2)) {
     if (lane == 0 && rank == 0) {
       constexpr uint32_t idesc = make_idesc(MT, BN);
-      int kbg = 0, i = 0;
+      // dual issue: this warp takes the tiles of its own parity (= its accumulator buffer); ring position 3 per tile
+      constexpr int ISTEP = DUAL ? 2 : 1;
+      int i = DUAL ? warp - 1 : 0;
+      int kbg = DUAL ? 3 * i : 0;
       if constexpr (CONV3) mbar_wait(bres, 0);
-      for (int tile = tile0; tile < total_tiles; tile += tstep, ++i) {
+      for (int tile = tile0 + i * tstep; tile < total_tiles; tile += ISTEP * tstep, i += ISTEP, kbg += DUAL ? 3 : 0) {
         const int as = i % L::NACC;
         mbar_wait(tempty0 + 8 * as, ((i / L::NACC) & 1) ^ 1);  // epilogue group `as` has drained this accumulator buffer
         tc_fence_after();
@@ -261,10 +280,13 @@ __global__ void __launch_bounds__(64 + EPI_WARPS * 32, 1) gemm_tc_kernel(const _
                 const uint64_t da = make_sdesc(sa + kx * 128);
                 const uint64_t db = make_sdesc(smem_u32(smem + L::BRES_OFF + (ky * 3 + kx) * L::B_BYTES));
 #pragma unroll
-                for (int k = 0; k < BK / UMMA_K; ++k)
-                  tc_mma_bf16(tacc, da + (uint64_t)(k * UMMA_K * 2 / 16), db + (uint64_t)(k * UMMA_K * 2 / 16), idesc, (ky | kx | k) != 0);
+                for (int k = 0; k < BK / UMMA_K; ++k) {
+                  if constexpr (PAIR) tc_mma_bf16_pair(tacc, da + (uint64_t)(k * UMMA_K * 2 / 16), db + (uint64_t)(k * UMMA_K * 2 / 16), idesc, (ky | kx | k) != 0);
+                  else tc_mma_bf16(tacc, da + (uint64_t)(k * UMMA_K * 2 / 16), db + (uint64_t)(k * UMMA_K * 2 / 16), idesc, (ky | kx | k) != 0);
+                }
               }
-              tc_commit(empty0 + 8 * s);
+              if constexpr (PAIR) tc_commit_pair(empty0 + 8 * s, 3);
+              else tc_commit(empty0 + 8 * s);
             }
           } else {
             const uint32_t tmask = (uint32_t)g.tap_mask;
@@ -280,11 +302,14 @@ __global__ void __launch_bounds__(64 + EPI_WARPS * 32, 1) gemm_tc_kernel(const _
                 const uint64_t da = make_sdesc(sa + kx * 128);
                 const uint64_t db = make_sdesc(smem_u32(smem + L::BRES_OFF + (ky * 3 + kx) * L::B_BYTES));
 #pragma unroll
-                for (int k = 0; k < BK / UMMA_K; ++k)
-                  tc_mma_bf16(tacc, da + (uint64_t)(k * UMMA_K * 2 / 16), db + (uint64_t)(k * UMMA_K * 2 / 16), idesc, acc_on | (uint32_t)k);
+                for (int k = 0; k < BK / UMMA_K; ++k) {
+                  if constexpr (PAIR) tc_mma_bf16_pair(tacc, da + (uint64_t)(k * UMMA_K * 2 / 16), db + (uint64_t)(k * UMMA_K * 2 / 16), idesc, acc_on | (uint32_t)k);
+                  else tc_mma_bf16(tacc, da + (uint64_t)(k * UMMA_K * 2 / 16), db + (uint64_t)(k * UMMA_K * 2 / 16), idesc, acc_on | (uint32_t)k);
+                }
                 acc_on = 1;
               }
-              tc_commit(empty0 + 8 * s);
+              if constexpr (PAIR) tc_commit_pair(empty0 + 8 * s, 3);
+              else tc_commit(empty0 + 8 * s);
             }
           }
         } else if constexpr (BAND) {
@@ -338,7 +363,7 @@ __global__ void __launch_bounds__(64 + EPI_WARPS * 32, 1) gemm_tc_kernel(const _
       }
     }
   } else {
-    const int ew = warp - 2;                 // 0..EPI_WARPS-1
+    const int ew = warp - L::EPI_WARP0;      // 0..EPI_WARPS-1
     const int grp = ew >> 2;                 // this warp's group drains tiles grp, grp + GROUPS, ... (buffer = tile parity)
     const int q = warp & 3;                  // TMEM lane quarter this warp may read
     uint8_t* stg = smem + L::STG_OFF + ew * L::STG_WARP;
@@ -349,6 +374,13 @@ __global__ void __launch_bounds__(64 + EPI_WARPS * 32, 1) gemm_tc_kernel(const _
     auto stage_scale_bias = [&](int ord, int n0, uint32_t tfull_bar, uint32_t tfull_parity) -> const float* {
       float* sbt = sb_base + (ord & 1) * (2 * BN);
       if constexpr (L::SB) {
+        // one column tile (N <= BN): every tile of this CTA uses the same scale / bias slice, and after the group's first
+        // two tiles both parity buffers hold it - no global loads, no shared-memory writes, no group barrier (the load's
+        // L2 round trip in front of every short tile was a quarter of the epilogue warps' stall samples)
+        if (n_tiles == 1 && ord >= 2) {
+          mbar_wait(tfull_bar, tfull_parity);
+          return sbt;
+        }
         float v[(2 * BN + 127) / 128];
 #pragma unroll
         for (int u = 0; u < (2 * BN + 127) / 128; ++u) {
@@ -663,14 +695,14 @@ __global__ void __launch_bounds__(64 + EPI_WARPS * 32, 1) gemm_tc_kernel(const _
 // ---------------------------------------------------------------- host side
 int g_num_sms = 0;
 
-template <int BN, int STAGES, int NBUF, int MODE, bool CONV3 = false, int EPI_WARPS = 8, bool PAIR = false, int NBST = 0>
+template <int BN, int STAGES, int NBUF, int MODE, bool CONV3 = false, int EPI_WARPS = 8, bool PAIR = false, int NBST = 0, bool DUAL = false>
 int launch(const CrogGemm* g, cudaStream_t stream) {
-  using L = Cfg<BN, STAGES, NBUF, CONV3, EPI_WARPS, PAIR, NBST>;
+  using L = Cfg<BN, STAGES, NBUF, CONV3, EPI_WARPS, PAIR, NBST, DUAL>;
   static_assert(L::TOTAL <= 227 * 1024, "shared memory budget");
   static DeviceOnce once;  // function attributes are per device (one static per template instantiation)
   int dev = 0;
   if (once.need(&dev) || g_num_sms == 0) {
-    CROG_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES, NBUF, MODE, CONV3, EPI_WARPS, PAIR, NBST>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+    CROG_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES, NBUF, MODE, CONV3, EPI_WARPS, PAIR, NBST, DUAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
     CROG_CUDA_OK(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
     once.done(dev);
   }
@@ -711,12 +743,12 @@ int launch(const CrogGemm* g, cudaStream_t stream) {
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
-    CROG_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, STAGES, NBUF, MODE, CONV3, EPI_WARPS, PAIR, NBST>, tmA, tmA2, tmB, tmOut, tmRes, *g, n_tiles, total));
+    CROG_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, STAGES, NBUF, MODE, CONV3, EPI_WARPS, PAIR, NBST, DUAL>, tmA, tmA2, tmB, tmOut, tmRes, *g, n_tiles, total));
     return CROG_OK;
   }
   int grid = total < g_num_sms ? total : g_num_sms;
   if (g->max_ctas > 0 && grid > g->max_ctas) grid = g->max_ctas;
-  crog_launch(gemm_tc_kernel<BN, STAGES, NBUF, MODE, CONV3, EPI_WARPS, PAIR, NBST>, dim3(grid), dim3(L::NUM_THREADS), L::TOTAL, stream, tmA, tmA2, tmB, tmOut, tmRes, *g, n_tiles, total);
+  crog_launch(gemm_tc_kernel<BN, STAGES, NBUF, MODE, CONV3, EPI_WARPS, PAIR, NBST, DUAL>, dim3(grid), dim3(L::NUM_THREADS), L::TOTAL, stream, tmA, tmA2, tmB, tmOut, tmRes, *g, n_tiles, total);
   CROG_LAUNCH_OK("gemm_tc");
   return CROG_OK;
 }
@@ -752,6 +784,15 @@ int dispatch(const CrogGemm* g, cudaStream_t stream) {
       case CROG_TILE_CONV3:
         CROG_REQUIRE(conv3_ok, CROG_E_BADSHAPE, "gemm_tc: CONV3 tiles need a shared 3x3 kernel with cin == 64 and N <= 64");
         return launch<64, 5, 2, MODE, true>(g, stream);
+      case CROG_TILE_CONV3_E12:
+        CROG_REQUIRE(conv3_ok, CROG_E_BADSHAPE, "gemm_tc: CONV3 tiles need a shared 3x3 kernel with cin == 64 and N <= 64");
+        return launch<64, 3, 2, MODE, true, 12>(g, stream);
+      case CROG_TILE_CONV3_DUAL:
+        CROG_REQUIRE(conv3_ok, CROG_E_BADSHAPE, "gemm_tc: CONV3 tiles need a shared 3x3 kernel with cin == 64 and N <= 64");
+        return launch<64, 5, 2, MODE, true, 8, false, 0, true>(g, stream);
+      case CROG_TILE_CONV3_PAIR:
+        CROG_REQUIRE(conv3_ok && pair_ok, CROG_E_BADSHAPE, "gemm_tc: CONV3 pair tiles need a shared 3x3 kernel with cin == 64, N <= 64, M > 128");
+        return launch<64, 5, 2, MODE, true, 8, true>(g, stream);
       case CROG_TILE_BAND_PAIR_256x256:
         CROG_REQUIRE(band_ok && pair_ok && g->N > 128, CROG_E_BADSHAPE, "gemm_tc: BAND pair 256x256 needs a shared 3x3 kernel on the padded layout, M > 128, N > 128");
         return launch<256, 3, 2, MODE, false, 4, true, 6>(g, stream);

@@ -145,7 +145,13 @@ enum {
   CROG_TILE_BAND_PAIR_256x128 = 13,    /* CTA pair, 256 x 128 tiles, 4 band + 8 weight stages, two epilogue groups per CTA */
   CROG_TILE_BAND_128x128 = 14,         /* one CTA, 128 x 128 tiles, 3 band + 6 weight stages, two epilogue groups */
   CROG_TILE_BAND_128x256 = 15,         /* one CTA, 128 x 256 tiles, 3 band + 4 weight stages, one epilogue group */
-  CROG_TILE_COUNT = 16
+  CROG_TILE_CONV3_E12 = 16,            /* CROG_TILE_CONV3 with three epilogue groups and three band stages: a 128 x 64 tile's
+                                          36 MMAs take ~1.2k clocks, its epilogue ~6k, so two groups leave the tensor pipe idle */
+  CROG_TILE_CONV3_PAIR = 17,           /* CROG_TILE_CONV3 on a CTA pair (256 x 64 tiles, each CTA keeps half of the weight rows):
+                                          one MMA-issuing thread feeds two SMs - the N = 64 MMAs are so short (32 clocks) that
+                                          the single issuing thread, not the tensor pipe, paces the one-CTA form */
+  CROG_TILE_CONV3_DUAL = 18,           /* CROG_TILE_CONV3 with TWO MMA-issuing warps (one per accumulator buffer, alternate tiles) */
+  CROG_TILE_COUNT = 19
 };
 int crog_gemm(const CrogGemm* g, void* stream);
 
