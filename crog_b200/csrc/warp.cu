@@ -63,19 +63,10 @@ __device__ __forceinline__ SrcCoord src_coord(const double* __restrict__ M, int 
   return c;
 }
 
-// src [NP][B][Hs][Ws] -> dst [NP][B][h][w]; grid (ceil(w*h/256), B).  The 32 phases' 1-D cubic coefficients are tabulated
-// once per CTA in shared memory (they were ~50 non-contractable float operations per pixel and axis), the 16 weight
-// products are formed once per pixel and reused by every plane.
+// src [NP][B][Hs][Ws] -> dst [NP][B][h][w]; grid (ceil(w*h/256), B)
 __global__ void __launch_bounds__(256) warp_cubic_f32_kernel(const float* __restrict__ src, int NP, int B, int Hs, int Ws,
                                                              const double* __restrict__ minv, float* __restrict__ dst, int h,
                                                              int w, float cv) {
-  __shared__ float ctab[TAB][4];
-  if (threadIdx.x < TAB) {
-    float c4[4];
-    cubic_coeffs(threadIdx.x, c4);
-    ctab[threadIdx.x][0] = c4[0]; ctab[threadIdx.x][1] = c4[1]; ctab[threadIdx.x][2] = c4[2]; ctab[threadIdx.x][3] = c4[3];
-  }
-  __syncthreads();
   const int b = blockIdx.y;
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= h * w) return;
@@ -88,30 +79,23 @@ __global__ void __launch_bounds__(256) warp_cubic_f32_kernel(const float* __rest
     return;
   }
   float vx[4], vy[4];
-#pragma unroll
-  for (int k = 0; k < 4; ++k) { vx[k] = ctab[c.ax][k]; vy[k] = ctab[c.ay][k]; }
+  cubic_coeffs(c.ax, vx);
+  cubic_coeffs(c.ay, vy);
   const bool inside = c.sx >= 0 && c.sx < max(Ws - 3, 0) && c.sy >= 0 && c.sy < max(Hs - 3, 0);
   if (inside) {
-    float wgt[16];
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-      for (int j = 0; j < 4; ++j) wgt[i * 4 + j] = __fmul_rn(vy[i], vx[j]);
-    const float* S = src + (long long)b * splane + (long long)c.sy * Ws + c.sx;
-    float* D = dst + (long long)b * dplane + p;
-    const long long sstep = (long long)B * splane, dstep = (long long)B * dplane;
-    for (int pl = 0; pl < NP; ++pl, S += sstep, D += dstep) {
+    for (int pl = 0; pl < NP; ++pl) {
+      const float* S = src + ((long long)pl * B + b) * splane + (long long)c.sy * Ws + c.sx;
       float sum = 0.f;
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const float* R = S + i * Ws;
-        float r = __fmul_rn(__ldg(R), wgt[i * 4]);
-        r = __fadd_rn(r, __fmul_rn(__ldg(R + 1), wgt[i * 4 + 1]));
-        r = __fadd_rn(r, __fmul_rn(__ldg(R + 2), wgt[i * 4 + 2]));
-        r = __fadd_rn(r, __fmul_rn(__ldg(R + 3), wgt[i * 4 + 3]));
+        float r = __fmul_rn(__ldg(R), __fmul_rn(vy[i], vx[0]));
+        r = __fadd_rn(r, __fmul_rn(__ldg(R + 1), __fmul_rn(vy[i], vx[1])));
+        r = __fadd_rn(r, __fmul_rn(__ldg(R + 2), __fmul_rn(vy[i], vx[2])));
+        r = __fadd_rn(r, __fmul_rn(__ldg(R + 3), __fmul_rn(vy[i], vx[3])));
         sum = i == 0 ? r : __fadd_rn(sum, r);
       }
-      *D = sum;
+      dst[((long long)pl * B + b) * dplane + p] = sum;
     }
   } else {
     for (int pl = 0; pl < NP; ++pl) {

@@ -28,11 +28,11 @@ ids = sorted(launches)
 assert len(ids) == len(names), (len(ids), len(names))
 with open(out, "w", newline="") as f:
     w = csv.writer(f)
-    w.writerow(["launch", "op", "tile_cfg", "kernel", "grid", "block", "time_us", "dram_read_MB", "dram_write_MB", "tensor_active_pct", "sm_throughput_pct"])
+    w.writerow(["launch", "op", "tile_cfg", "kernel", "grid", "block", "time_us", "dram_read_MB", "dram_write_MB", "tensor_active_pct", "sm_throughput_pct", "l2_MB"])
     for i, (k, (name, tc)) in enumerate(zip(ids, names)):
         d = launches[k]
         t = d.get("gpu__time_duration.sum", 0.0)
         w.writerow([i, name, tc, d["kernel"].replace("void ", "").replace("<unnamed>::", "").split("(")[0][:60], d["grid"], d["block"], round(t, 2), round(d.get("dram__bytes_read.sum", 0) / 1e6, 1),
                     round(d.get("dram__bytes_write.sum", 0) / 1e6, 1), round(d.get("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", 0), 1),
-                    round(d.get("sm__throughput.avg.pct_of_peak_sustained_elapsed", 0), 1)])
+                    round(d.get("sm__throughput.avg.pct_of_peak_sustained_elapsed", 0), 1), round(d.get("lts__t_bytes.sum", 0) / 1e6, 1)])
 print("wrote", out, len(ids), "launches")
