@@ -287,3 +287,48 @@ def test_stem_pixel_pairs_equal_channel_padded_form(monkeypatch):
     stem1, stem0 = outs["1"][0], outs["0"][0]
     assert float((stem1 - stem0).norm() / stem0.norm()) < 3e-3
     assert float((outs["1"][1] - outs["0"][1]).norm() / outs["0"][1].norm()) < 2.5e-2
+
+
+def test_forward_bf16_batch64_autotuned_plan_parity():
+    """Parity on what is actually benched: the 64-sample plan with its plan-time tile autotune (other tile configurations,
+    M tails, CTA pairs and activation bands than the small-batch tests reach).  8 of the 64 samples against the CPU oracle
+    (fp32) with the stated bf16 bars; per-sample results must not depend on the batch they ride in (bit-identical to a
+    2-sample plan); and the decode / Jaccard tail on all 64 post-processed maps is bit-exact against the oracle's serial loop."""
+    from crog_b200.engine import GraspEvaluator
+    from oracle import crog_forward as O
+    from oracle import grasp_tail_c as TC
+
+    Lw, B = 17, 64
+    cfg, sd, model = _build(Lw, "perturbed", "bf16")
+    model.prepare(B)
+    plan = model.plan_for(B, 416)
+    assert sum(1 for v in plan.tile_choice.values() if v[0] != 0) > 20, "the autotuner should have re-tiled a good part of the plan"
+    img, word, gt, cnt = synth.make_global_samples(0, B, Lw)
+    ev = GraspEvaluator(model)
+    post, peaks, n, grasps, flags = ev.step(img.cuda(), word.cuda(), torch.from_numpy(gt.copy()).cuda(), torch.from_numpy(cnt).cuda())
+    maps, _ = model(img.cuda(), word.cuda())
+    torch.cuda.synchronize()
+    got = torch.stack([m[:, 0] for m in maps], 1).float().cpu()          # [64, 5, 104, 104]
+    sel = list(range(0, B, 8))
+    torch.set_num_threads(os.cpu_count() or 1)
+    ref_maps, _ = O.crog_forward(sd, cfg, img[sel], word[sel])
+    ref = torch.stack([m[:, 0] for m in ref_maps], 1)
+    rel = max(float((got[sel][:, i] - ref[:, i]).norm() / ref[:, i].norm()) for i in range(5))
+    mx = float((got[sel] - ref).abs().max())
+    assert rel <= 5e-2 and mx <= 0.5, (rel, mx)
+    # batch independence: the same two samples through a 2-sample plan
+    small, _ = model(img[8:10].cuda(), word[8:10].cuda())   # served by the big plan's first rows
+    assert all(torch.equal(s_.cpu(), m_[8:10].cpu()) for s_, m_ in zip(small, maps))
+    model2 = _build(Lw, "perturbed", "bf16")[2]
+    model2.autotune = False
+    two, _ = model2(img[8:10].cuda(), word[8:10].cuda())     # its own 2-sample plan, heuristic tiles
+    assert all(torch.equal(t_.cpu(), m_[8:10].cpu()) for t_, m_ in zip(two, maps)), "results depend on batch size / tile choice"
+    # tail on the 64 maps the GPU produced
+    p = post.cpu().numpy()
+    g_ref, n_ref, j_ref, c_ref = TC.tail_batch(p[1], p[2], p[3], p[4], gt, cnt)
+    assert np.array_equal(n.cpu().numpy(), n_ref) and np.array_equal(flags.cpu().numpy(), j_ref)
+    gg = grasps.cpu().numpy()
+    for b in range(B):
+        k = int(n_ref[b])
+        assert np.array_equal(gg[b, :k, :4], g_ref[b, :k, :4])
+    assert np.array_equal(ev.counters.cpu().numpy(), c_ref)
