@@ -18,6 +18,14 @@ NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--use_fast_math=false",
          "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
 FLAGS.remove("--use_fast_math=false")
+# same-box A/B of two builds: CROG_BUILD_EXTRA="-DNAME=value ..." adds compiler flags, CROG_BUILD_TAG=name builds into
+# lib/libcrog_b200.<name>.so (objects in lib/obj.<name>/); load it with CROG_B200_SO=...
+_TAG = os.environ.get("CROG_BUILD_TAG", "")
+if os.environ.get("CROG_BUILD_EXTRA"):
+    FLAGS += os.environ["CROG_BUILD_EXTRA"].split()
+if _TAG:
+    OBJ_DIR = os.path.join(OUT_DIR, "obj." + _TAG)
+    SO_PATH = os.path.join(OUT_DIR, f"libcrog_b200.{_TAG}.so")
 
 
 def _stale(target: str, deps) -> bool:

@@ -367,6 +367,42 @@ __global__ void dynconv_gather_kernel(const float* __restrict__ z, int ldz, floa
   }
 }
 
+// Tiled form: a CTA owns GT_H x GT_W output pixels, stages the (GT_H + 2) x (GT_W + 2) rows of Z it needs in shared memory
+// with coalesced 16-byte loads (a Z row is ldz = 48 contiguous floats; adjacent pixels are adjacent rows), then every thread
+// sums its nine taps from shared memory.  The per-thread form above reads 45 scalars at a 192-byte stride between lanes:
+// 32 cache lines per warp load, 95 us per 64 samples at 1.5 TB/s; same arithmetic, same summation order.
+constexpr int GT_H = 8, GT_W = 32;
+__global__ void __launch_bounds__(GT_H * GT_W) dynconv_gather_tiled_kernel(const float* __restrict__ z, int ldz, float* __restrict__ out, int B,
+                                                                      int H, int W, int NH) {
+  extern __shared__ float s_z[];  // [(GT_H + 2) * (GT_W + 2)][ldz + 1]
+  pdl_launch();
+  pdl_wait();
+  const int b = blockIdx.z, y0 = blockIdx.y * GT_H, x0 = blockIdx.x * GT_W;
+  const int PW = W + 2, pitch = ldz + 1;
+  const int rows = (GT_H + 2) * (GT_W + 2), q4 = ldz / 4;
+  for (int i = threadIdx.x; i < rows * q4; i += blockDim.x) {
+    const int r = i / q4, c4 = i - r * q4;
+    const int ty = r / (GT_W + 2), tx = r - ty * (GT_W + 2);
+    const int py = y0 + ty, px = x0 + tx;  // padded coordinates of (y - 1 + ty, x - 1 + tx)
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (py < H + 2 && px < PW) v = __ldg(reinterpret_cast<const float4*>(z + (((long long)b * (H + 2) + py) * PW + px) * ldz) + c4);
+    float* d = s_z + r * pitch + c4 * 4;
+    d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+  }
+  __syncthreads();
+  const int ly = threadIdx.x / GT_W, lx = threadIdx.x % GT_W;
+  const int y = y0 + ly, x = x0 + lx;
+  if (y >= H || x >= W) return;
+  const long long total = (long long)B * H * W, i = ((long long)b * H + y) * W + x;
+  for (int h = 0; h < NH; ++h) {
+    float acc = 0.f;
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap)
+      acc += s_z[((ly + tap / 3) * (GT_W + 2) + lx + tap % 3) * pitch + h * 9 + tap];
+    out[(long long)h * total + i] = acc;
+  }
+}
+
 __global__ void split_heads_kernel(const float* __restrict__ in, int ld, float* __restrict__ out, long long rows, int NH) {
   const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (i >= rows) return;
@@ -610,6 +646,19 @@ extern "C" int crog_dynw_fold(const void* state, int32_t state_dtype, const floa
 extern "C" int crog_dynconv_gather(const float* z, int32_t ldz, float* out, int32_t B, int32_t H, int32_t W, int32_t NH, void* stream) {
   const long long total = (long long)B * H * W;
   if (total == 0) return CROG_OK;
+  const size_t smem = (size_t)(GT_H + 2) * (GT_W + 2) * (ldz + 1) * sizeof(float);
+  if (ldz % 4 == 0 && aligned16(z) && smem <= 100 * 1024 && B <= 65535 && !getenv("CROG_GATHER_SIMPLE")) {
+    static DeviceOnce once;
+    int dev_;
+    if (once.need(&dev_)) {
+      CROG_CUDA_OK(cudaFuncSetAttribute(dynconv_gather_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+      once.done(dev_);
+    }
+    crog_launch(dynconv_gather_tiled_kernel, dim3((W + GT_W - 1) / GT_W, (H + GT_H - 1) / GT_H, B), dim3(GT_H * GT_W), smem, (cudaStream_t)stream,
+                z, ldz, out, B, H, W, NH);
+    CROG_LAUNCH_OK("dynconv_gather");
+    return CROG_OK;
+  }
   crog_launch(dynconv_gather_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, (cudaStream_t)stream, z, ldz, out, B, H, W, NH);
   CROG_LAUNCH_OK("dynconv_gather");
   return CROG_OK;

@@ -451,13 +451,15 @@ __global__ void __launch_bounds__((DUAL ? 96 : 64) + EPI_WARPS * 32, 1) gemm_tc_
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN;
         for (int c = 0; c < nvc; ++c) {
           float acc[CW];
+          {  // both 32-column TMEM loads of a 64-column chunk in flight before the one wait (one TMEM round trip per chunk)
+            uint32_t r[CW / 32][32];
 #pragma unroll
-          for (int h = 0; h < CW / 32; ++h) {
-            uint32_t r[32];
-            tc_ld32(taddr + c * CW + h * 32, r);
+            for (int h = 0; h < CW / 32; ++h) tc_ld32(taddr + c * CW + h * 32, r[h]);
             tc_wait_ld();
 #pragma unroll
-            for (int j = 0; j < 32; ++j) acc[h * 32 + j] = __uint_as_float(r[j]);
+            for (int h = 0; h < CW / 32; ++h)
+#pragma unroll
+              for (int j = 0; j < 32; ++j) acc[h * 32 + j] = __uint_as_float(r[h][j]);
           }
           if (c == nvc - 1) {  // last read of this accumulator buffer: hand it back to the (leader's) MMA warp
             tc_fence_before();

@@ -47,7 +47,11 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   unsigned long long t0;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
   uint32_t spins = 0;
+#ifdef CROG_MBAR_HINT_NS
+  while (!mbar_try_wait_hint(bar, parity, CROG_MBAR_HINT_NS)) {
+#else
   while (!mbar_try_wait(bar, parity)) {
+#endif
     if ((++spins & 0x3ff) == 0) {
       unsigned long long t1;
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
