@@ -12,7 +12,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 SO_PATH = os.environ.get("CROG_B200_SO") or os.path.join(_HERE, "lib", "libcrog_b200.so")  # override: A/B of two builds
 
-ABI_VERSION = 4  # crog_abi_version() of the library these signatures were written for
+ABI_VERSION = 5  # crog_abi_version() of the library these signatures were written for
 F32, BF16 = 0, 1
 ACT_NONE, ACT_RELU, ACT_QUICKGELU, ACT_TANH = 0, 1, 2, 3
 IMPL_AUTO, IMPL_SIMT, IMPL_TCGEN05 = 0, 1, 2
@@ -41,7 +41,7 @@ class CrogGemm(C.Structure):
         ("a2", C.c_void_p), ("a2_ld", C.c_int32), ("cin2", C.c_int32),
         ("row_stats_out", C.c_void_p), ("row_stats_in", C.c_void_p), ("row_stats_chunks", C.c_int32),
         ("row_stats_width", C.c_int32), ("row_stats_eps", C.c_float),
-        ("max_ctas", C.c_int32), ("tap_mask", C.c_int32),
+        ("max_ctas", C.c_int32), ("tap_mask", C.c_int32), ("reverse", C.c_int32),
     ]
 
 

@@ -115,8 +115,15 @@ __global__ void __launch_bounds__((DUAL ? 96 : 64) + EPI_WARPS * 32, 1) gemm_tc_
   // Written as expressions, not variables: with named copies of blockIdx.x / gridDim.x nvcc schedules the single-CTA
   // CONV3 kernels 11 % slower (measured A/B on one box: stem.conv2 260 -> 292 us) although the SASS mix is identical.
 #define rank (PAIR ? cluster_ctarank() : 0u)                          /* 0 = leader (issues the MMAs) */
-#define tile0 (PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x)       /* both CTAs of a pair walk the same tiles */
-#define tstep (PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x)
+#define tile0f (PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x)      /* both CTAs of a pair walk the same tiles */
+#define tstepf (PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x)
+  // g.reverse: the same walk from the last tile down (tile indices leave the range below 0: unsigned compares)
+#define tile0 (g.reverse ? total_tiles - 1 - tile0f : tile0f)
+#define tstep (g.reverse ? -tstepf : tstepf)
+#define TILE_IN(t) ((unsigned)(t) < (unsigned)total_tiles)
+  // (Measured negative, round 2: evict_first L2 hints on the activation / residual loads.  The hinted lines leave the L2
+  // before their own re-reads - the three ky bands of a 3x3 tile, the n-tiles of one row block - and the forward's DRAM
+  // reads rise from 12.3 to 14.3 GB, +0.25 ms.  evict_last on the output stores: 12.3 -> 12.0 GB, time unchanged.)
   const int kchunks = g.cin / BK;
   const int num_kb = CONV3 ? 3 : g.taps * kchunks + g.cin2 / BK;  // CONV3: one k-block per ky band; a2: its chunks follow a's
   const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + STAGES), tfull0 = smem_u32(bars + 2 * STAGES),
@@ -163,7 +170,7 @@ __global__ void __launch_bounds__((DUAL ? 96 : 64) + EPI_WARPS * 32, 1) gemm_tc_
           mbar_expect_tx(bres, L::BRES_BYTES);
           for (int t = 0; t < 9; ++t) tma_load_2d(smem_u32(smem + L::BRES_OFF + t * L::B_BYTES), &tmB, t * BK, 0, bres);
         }
-        for (int tile = tile0; tile < total_tiles; tile += tstep) {
+        for (int tile = tile0; TILE_IN(tile); tile += tstep) {
           const long long row0 = (long long)tile * MT + (PAIR ? (long long)rank * BM : 0);  // n_tiles == 1
           for (int ky = 0; ky < 3; ++ky, ++kbg) {
             const int s = kbg % STAGES, it = kbg / STAGES;
@@ -180,7 +187,7 @@ __global__ void __launch_bounds__((DUAL ? 96 : 64) + EPI_WARPS * 32, 1) gemm_tc_
         }
       } else if constexpr (BAND) {
         int ia = 0, ib = 0;  // band / weight-tile ring positions
-        for (int tile = tile0; tile < total_tiles; tile += tstep) {
+        for (int tile = tile0; TILE_IN(tile); tile += tstep) {
           const int n_t = tile % n_tiles, m_t = tile / n_tiles;
           const long long row0 = (long long)m_t * MT + (PAIR ? (long long)rank * BM : 0);
           const int wrow0 = n_t * BN + (PAIR ? (int)rank * L::B_ROWS : 0);
@@ -219,7 +226,7 @@ __global__ void __launch_bounds__((DUAL ? 96 : 64) + EPI_WARPS * 32, 1) gemm_tc_
             }
         }
       } else
-      for (int tile = tile0; tile < total_tiles; tile += tstep) {
+      for (int tile = tile0; TILE_IN(tile); tile += tstep) {
         const int n_t = tile % n_tiles, m_t = tile / n_tiles;
         TileRows tr = tile_rows(g, m_t, MT);
         if constexpr (PAIR) tr.row0 += (long long)rank * BM;  // shared weights only: tiles are plain row ranges
@@ -259,7 +266,7 @@ __global__ void __launch_bounds__((DUAL ? 96 : 64) + EPI_WARPS * 32, 1) gemm_tc_
       int i = DUAL ? warp - 1 : 0;
       int kbg = DUAL ? 3 * i : 0;
       if constexpr (CONV3) mbar_wait(bres, 0);
-      for (int tile = tile0 + i * tstep; tile < total_tiles; tile += ISTEP * tstep, i += ISTEP, kbg += DUAL ? 3 : 0) {
+      for (int tile = tile0 + i * tstep; TILE_IN(tile); tile += ISTEP * tstep, i += ISTEP, kbg += DUAL ? 3 : 0) {
         const int as = i % L::NACC;
         mbar_wait(tempty0 + 8 * as, ((i / L::NACC) & 1) ^ 1);  // epilogue group `as` has drained this accumulator buffer
         tc_fence_after();
@@ -421,7 +428,7 @@ __global__ void __launch_bounds__((DUAL ? 96 : 64) + EPI_WARPS * 32, 1) gemm_tc_
       bool pf_ok = false;
       auto pf_set_tile = [&]() {
         const int tile = tile0 + pf_i * tstep;
-        pf_ok = tile < total_tiles;
+        pf_ok = TILE_IN(tile);
         if (pf_ok) { pf_n0 = (tile % n_tiles) * BN; pf_row = (tile / n_tiles) * MT + (int)rank * BM + q * 32; }
       };
       pf_set_tile();
@@ -439,7 +446,7 @@ __global__ void __launch_bounds__((DUAL ? 96 : 64) + EPI_WARPS * 32, 1) gemm_tc_
         for (int j = 0; j < NBUF - 1; ++j) issue_prefetch();
       for (int i = grp;; i += GROUPS) {
         const int tile = tile0 + i * tstep;
-        if (tile >= total_tiles) break;
+        if (!TILE_IN(tile)) break;
         const int buf = i % L::NACC;
         const uint32_t tfull = tfull0 + 8 * buf, tempty = tempty0 + 8 * buf;
         const int n0 = (tile % n_tiles) * BN, row0 = (tile / n_tiles) * MT + (int)rank * BM;
@@ -571,7 +578,7 @@ __global__ void __launch_bounds__((DUAL ? 96 : 64) + EPI_WARPS * 32, 1) gemm_tc_
       const int u = lane % UPR, rsub = lane / UPR;
       for (int i = grp;; i += GROUPS) {
         const int tile = tile0 + i * tstep;
-        if (tile >= total_tiles) break;
+        if (!TILE_IN(tile)) break;
         const int buf = i % L::NACC;
         const uint32_t tfull = tfull0 + 8 * buf, tempty = tempty0 + 8 * buf;
         const int n_t = tile % n_tiles, m_t = tile / n_tiles;
@@ -693,6 +700,9 @@ __global__ void __launch_bounds__((DUAL ? 96 : 64) + EPI_WARPS * 32, 1) gemm_tc_
 #undef rank
 #undef tile0
 #undef tstep
+#undef tile0f
+#undef tstepf
+#undef TILE_IN
 
 // ---------------------------------------------------------------- host side
 int g_num_sms = 0;

@@ -146,6 +146,10 @@ class ForwardPlan:
         self.stem_pairs = (precision == "bf16" and gemm_impl != L.IMPL_SIMT and os.environ.get("CROG_STEM_PAIRS", "1") != "0")
         # SMs the text tower's persistent GEMMs may occupy while it runs beside the image front (0: no partition)
         self.text_sms = int(os.environ.get("CROG_TEXT_SMS", "16")) if precision == "bf16" and gemm_impl != L.IMPL_SIMT else 0
+        # consecutive GEMMs walk their tiles in opposite directions: a consumer starts where its producer finished, so the
+        # producer's most recent output is read from L2 instead of HBM (CROG_SNAKE=0: every GEMM walks upwards)
+        self.snake = os.environ.get("CROG_SNAKE", "1") != "0"
+        self._wdir = {}  # buffer address -> direction its producer GEMM walked
         self.front_end = 0  # ops [0, front_end) are the image front (stem, layer1, layer2) that overlaps the text tower
         self._side = None
         self._side2 = None
@@ -213,6 +217,9 @@ class ForwardPlan:
              alg_flops: Optional[int] = None, alg_bytes: Optional[int] = None):
         g = L.CrogGemm()
         g.tap_mask = tap_mask
+        if getattr(self, "snake", False):
+            g.reverse = 1 - self._wdir.get(a.ptr, 0)
+            self._wdir[out.ptr] = g.reverse
         cin = cin if cin is not None else a.C
         cin2 = a2.C if a2 is not None else 0
         assert w.shape[-1] == taps * cin + cin2, (name, tuple(w.shape), taps, cin, cin2)

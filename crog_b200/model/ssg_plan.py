@@ -11,6 +11,7 @@ What is specific to the torchvision-style trunk:
 """
 from __future__ import annotations
 
+import os
 from typing import Dict, List, Optional
 
 import torch
@@ -36,6 +37,7 @@ class SSGPlan(ForwardPlan):
         self.n_launches, self.gemm_flops, self.gemm_alg_flops, self.gemm_alg_bytes = 0, 0, {}, {}
         self.gemm_ops, self.tile_choice, self.gemm_index = [], {}, {}
         self.text_sms, self.front_end, self.stem_pairs = 0, 0, False
+        self.snake, self._wdir = os.environ.get("CROG_SNAKE", "1") != "0", {}
         self.op_side, self.op_after, self.side_helpers, self.fuse_downsample = set(), {}, False, False
         self._side = self._ev = None
         self.text_range = (0, 0)

@@ -120,6 +120,9 @@ typedef struct CrogGemm {
                              Masked taps must have zero weights (other tile configurations still contract them): the
                              pixel-pair stem (two 32-channel pixels per 64-channel row) only reaches two of the three
                              horizontal pair offsets per output parity. */
+  int32_t reverse;        /* tcgen05 path: 1 = the persistent CTAs walk the tiles from the last to the first.  Results are
+                             unchanged; a consumer that starts where its producer finished finds the producer's last
+                             ~60-100 MB of output still in the 126 MB L2 (the forward plan alternates directions). */
 } CrogGemm;
 enum {
   CROG_TILE_AUTO = 0,

@@ -34,7 +34,7 @@ def conv_w(w: torch.Tensor, dtype) -> torch.Tensor:
 
 def run_gemm(a, w, N, out, *, taps=1, cin=None, H=0, W=0, in_padded=False, out_padded=False, sample_rows=0, scale=None,
              bias=None, act=0, addmat=None, gate=None, scale2=None, bias2=None, residual=None, residual_relu=False,
-             w_sample_stride=0, impl=0, a_col0=0, out_col0=0, tile_cfg=0, max_ctas=0, tap_mask=0):
+             w_sample_stride=0, impl=0, a_col0=0, out_col0=0, tile_cfg=0, max_ctas=0, tap_mask=0, reverse=0):
     g = L.CrogGemm()
     es = a.element_size()
     g.a, g.a_rows, g.a_ld = a.data_ptr() + a_col0 * es, a.shape[0], a.shape[1]
@@ -54,7 +54,7 @@ def run_gemm(a, w, N, out, *, taps=1, cin=None, H=0, W=0, in_padded=False, out_p
     g.out, g.out_ld, g.out_dtype = out.data_ptr() + out_col0 * out.element_size(), out.shape[1], L.dtype_code(out.dtype)
     g.impl = impl
     g.tile_cfg = tile_cfg
-    g.max_ctas, g.tap_mask = max_ctas, tap_mask
+    g.max_ctas, g.tap_mask, g.reverse = max_ctas, tap_mask, reverse
     L.check(L.lib().crog_gemm(C.byref(g), L.stream_ptr()))
     torch.cuda.synchronize()
 

@@ -465,10 +465,10 @@ def test_tile_cfgs_bit_identical(case):
         a, wk = pad_nhwc(x, dt), conv_w(w, dt)
         out_padded = case != "conv3x3_pad2compact"
 
-        def run(cfg):
+        def run(cfg, reverse=0):
             rows = B * (H + 2) * (W + 2) if out_padded else B * H * W
             out = torch.zeros((rows, Cout), device="cuda", dtype=dt)
-            run_gemm(a, wk, Cout, out, taps=9, H=H, W=W, in_padded=True, out_padded=out_padded,
+            run_gemm(a, wk, Cout, out, taps=9, H=H, W=W, in_padded=True, out_padded=out_padded, reverse=reverse,
                      sample_rows=(H + 2) * (W + 2), scale=sc, bias=bi, act=L.ACT_RELU, impl=L.IMPL_TCGEN05, tile_cfg=cfg)
             return out
     else:
@@ -481,10 +481,10 @@ def test_tile_cfgs_bit_identical(case):
         res = torch.randn(M, N, device="cuda").to(odt)
         addmat = torch.randn(97, N, device="cuda") if "addmat" in case else None
 
-        def run(cfg):
+        def run(cfg, reverse=0):
             out = res.clone()
             run_gemm(a, w, N, out, bias=bi, residual=None if addmat is not None else out, residual_relu="relu" in case,
-                     addmat=addmat, sample_rows=97 if addmat is not None else 0, impl=L.IMPL_TCGEN05, tile_cfg=cfg)
+                     addmat=addmat, sample_rows=97 if addmat is not None else 0, impl=L.IMPL_TCGEN05, tile_cfg=cfg, reverse=reverse)
             return out
     want = run(L.TILE_AUTO)
     ran = []
@@ -495,6 +495,8 @@ def test_tile_cfgs_bit_identical(case):
             continue  # does not apply to this shape
         ran.append(cfg)
         assert torch.equal(got, want), f"tile_cfg {cfg}: max diff {maxerr(got, want)}"
+        # CrogGemm.reverse: the same tiles walked from the last to the first
+        assert torch.equal(run(cfg, reverse=1), want), f"tile_cfg {cfg} reversed: max diff {maxerr(got, want)}"
     assert L.TILE_128x128 in ran and L.TILE_128x64 in ran
     if case != "conv3x3_cin64_n64":
         assert L.TILE_PAIR_256x128 in ran
