@@ -22,7 +22,10 @@ namespace {
 constexpr int BAND_SMALL = 32; // output rows per CTA band when few maps must fill the GPU
 constexpr int BAND_LARGE = 104; // ... and when there are plenty (4 halo rows per band: 3.8 % instead of 12.5 % re-read)
 constexpr int STRIP = 120;     // columns owned per warp (30 lanes x 4; lanes 0 and 31 carry the halo)
-constexpr int CAPW = 512;      // per-warp candidate list capacity
+#ifndef CROG_CAPW
+#define CROG_CAPW 512
+#endif
+constexpr int CAPW = CROG_CAPW;      // per-warp candidate list capacity
 constexpr int TSEL = 32;       // keys kept per warp segment
 constexpr int MAXK = 32;
 
@@ -273,7 +276,10 @@ __global__ void __launch_bounds__(256, 2) peak_scan_generic_kernel(const float* 
 //    final selection, so the segment written out is unchanged).  On iid-uniform maps, where 4 % of all pixels are 5x5
 //    maxima above the threshold, the appends decay like tsel / candidates seen and the scan stays a streaming kernel.
 constexpr int SCAN_R = 5;    // rows per stage (= ring length, so ring slots are compile-time)
-constexpr int SCAN_NST = 4;  // stages
+#ifndef CROG_SCAN_NST
+#define CROG_SCAN_NST 4
+#endif
+constexpr int SCAN_NST = CROG_SCAN_NST;  // stages
 constexpr int SEL_SLACK = 64; // keys a warp appends after a selection before it selects again
 
 __device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
@@ -281,10 +287,19 @@ __device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void* src, uint
                ::"r"(dst), "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(bar) : "memory");
 }
 
+// Cold paths of the scan, out of line: the streaming loop stays small enough for the instruction caches (with the
+// append logic inlined in each of the five unrolled row bodies the loop was 30 KB of SASS and a quarter of all
+// issue slots were lost to no_instruction stalls).
+__device__ __noinline__ int scan_make_room(unsigned long long* list, int count, int tsel, int kdist, int lane,
+                                           unsigned long long* bound_io) {
+  __syncwarp();
+  return select_and_cut(list, count, tsel, kdist, lane, bound_io);
+}
+
 template <bool TRACK>
 __device__ __forceinline__ void scan_rows(const float* stage0, uint32_t full0, uint32_t empty0, int W, int row0, int nrows, int y0,
                                           int y1, int ccol, int c0, bool owner, float tx_, float ty_, float tz_, float tw_, float p0,
-                                          int lane, unsigned long long* list, unsigned long long* top, int& count,
+                                          int lane, unsigned long long* list, int& count,
                                           int& truncated, int& nonconst, const int tsel, const int kdist,
                                           unsigned long long& bound) {
   const float NEG = -INFINITY;
@@ -295,91 +310,135 @@ __device__ __forceinline__ void scan_rows(const float* stage0, uint32_t full0, u
   //    distinct value yields at least one accepted peak.  Once the warp holds kdist = K + 1 distinct values, no
   //    candidate below the kdist-th of them can be reached before K peaks are accepted: it is dropped unseen (and the
   //    bound (value, lowest key) never flags a map, because the pass ends above it).
-  // On iid maps (all values distinct) the cut sits at the warp's (K+1)-th best value after the first selection, so only
-  // a few per cent of the later candidates touch the list at all.
+  // The warp keeps its distinct candidate values sorted across its lanes (`topv`), so the value cut follows every
+  // append; on iid maps the appends then die out like kdist / rows seen.
   unsigned long long cut = bound;
-  // per-lane emission thresholds (+inf for columns that may not emit).  After a selection they are raised to just below
-  // the cut's value, so the threshold-first vote below skips every row without a candidate that can still matter: a
-  // dense map (most pixels above the user threshold) then costs what a sparse one costs.
+  // per-lane emission thresholds (+inf for columns that may not emit), raised to just below the cut's value: the
+  // threshold-first votes skip every row without a candidate that can still matter, so a dense map (most pixels above
+  // the user threshold) costs little more than a sparse one.
   float tx = tx_, ty = ty_, tz = tz_, tw = tw_;
-  int next_sel = 16;  // first selection early (establishes the value cut); then see below
+  int next_sel = SEL_SLACK;
+  float topv = NEG;   // lane i: the i-th largest distinct candidate value this warp has appended (-inf: none yet)
+  float vcut = NEG;   // the kdist-th of them once there are that many
+  const bool vcut_on = kdist <= 32;
   float4 raw[5], hm[5];
 #pragma unroll
   for (int u = 0; u < 5; ++u) { raw[u] = make_float4(NEG, NEG, NEG, NEG); hm[u] = raw[u]; }
+  const uint32_t lt = (1u << lane) - 1u;
   const int nst = (nrows + SCAN_R - 1) / SCAN_R;
   for (int k = 0; k < nst; ++k) {
     const int s = k % SCAN_NST;
     mbar_wait(full0 + 8 * s, (k / SCAN_NST) & 1);
     const float* srow = stage0 + (long long)s * SCAN_R * W + ccol;
+    // The stage's five rows are handled as a batch: all loads, then the threshold votes of the five centre rows (rows
+    // 5k-2 .. 5k+2: two from the previous stage, three new) back to back, and - the common case - one warp-uniform
+    // branch for the whole stage when no centre pixel can emit; the horizontal maxima of the five new rows are then
+    // independent instruction streams.  (Row at a time, every row paid its own load -> shuffle -> vote -> branch
+    // latency chain.)
+    const int nvalid = min(SCAN_R, nrows - k * SCAN_R);  // rows of this stage that exist (the rest: stale ring data)
+    float4 v[SCAN_R];
+#pragma unroll
+    for (int u = 0; u < SCAN_R; ++u) v[u] = *reinterpret_cast<const float4*>(srow + u * W);
+    if (TRACK) {
+#pragma unroll
+      for (int u = 0; u < SCAN_R; ++u) {
+        const int r = row0 + k * SCAN_R + u;  // rows past the stage's last valid one lie at or beyond y1
+        if (owner && r >= y0 && r < y1) nonconst |= (v[u].x != p0) | (v[u].y != p0) | (v[u].z != p0) | (v[u].w != p0);
+      }
+    }
+    bool pass[SCAN_R];
+    bool any_pass = false;
 #pragma unroll
     for (int u = 0; u < SCAN_R; ++u) {
-      const int idx = k * SCAN_R + u;
-      if (idx >= nrows) break;  // warp-uniform
-      const float4 v = *reinterpret_cast<const float4*>(srow + u * W);
-      const float l2 = __shfl_up_sync(0xffffffffu, v.z, 1), l1 = __shfl_up_sync(0xffffffffu, v.w, 1);
-      const float r1 = __shfl_down_sync(0xffffffffu, v.x, 1), r2 = __shfl_down_sync(0xffffffffu, v.y, 1);
-      if (TRACK) {
-        const int r = row0 + idx;
-        if (owner && r >= y0 && r < y1) nonconst |= (v.x != p0) | (v.y != p0) | (v.z != p0) | (v.w != p0);
+      const float4 c = u < 2 ? raw[u + 3] : v[u - 2];  // centre row of row u = row u - 2
+      pass[u] = __any_sync(0xffffffffu, (c.x > tx) | (c.y > ty) | (c.z > tz) | (c.w > tw)) && k * SCAN_R + u >= 4 && u < nvalid;
+      any_pass |= pass[u];
+    }
+    if (!any_pass) {  // warp-uniform: nothing can emit in this stage, only the ring moves on (branch-free, five-way ILP)
+#pragma unroll
+      for (int u = 0; u < SCAN_R; ++u) {
+        const float l2 = __shfl_up_sync(0xffffffffu, v[u].z, 1), l1 = __shfl_up_sync(0xffffffffu, v[u].w, 1);
+        const float r1 = __shfl_down_sync(0xffffffffu, v[u].x, 1), r2 = __shfl_down_sync(0xffffffffu, v[u].y, 1);
+        const float mxyz = max3(v[u].x, v[u].y, v[u].z), myzw = max3(v[u].y, v[u].z, v[u].w);
+        raw[u] = v[u];
+        hm[u] = make_float4(max3(mxyz, l2, l1), max3(mxyz, l1, v[u].w), max3(myzw, v[u].x, r1), max3(myzw, r1, r2));
       }
-      const float mxyz = max3(v.x, v.y, v.z), myzw = max3(v.y, v.z, v.w);
-      raw[u] = v;
-      hm[u] = make_float4(max3(mxyz, l2, l1), max3(mxyz, l1, v.w), max3(myzw, v.x, r1), max3(myzw, r1, r2));
-      if (idx >= 4) {  // warp-uniform; false only for the four warm-up rows
-        const float4 ctr = raw[(u + 3) % 5];  // centre row = this row - 2
-        // threshold first: the vertical maxima are only needed for strips that hold an above-threshold pixel
-        const bool a0 = ctr.x > tx, a1 = ctr.y > ty, a2 = ctr.z > tz, a3 = ctr.w > tw;
-        if (!__any_sync(0xffffffffu, a0 | a1 | a2 | a3)) continue;
-        const float vx = max3(max3(hm[0].x, hm[1].x, hm[2].x), hm[3].x, hm[4].x);
-        const float vy = max3(max3(hm[0].y, hm[1].y, hm[2].y), hm[3].y, hm[4].y);
-        const float vz = max3(max3(hm[0].z, hm[1].z, hm[2].z), hm[3].z, hm[4].z);
-        const float vw = max3(max3(hm[0].w, hm[1].w, hm[2].w), hm[3].w, hm[4].w);
-        // (values equal to the cut's pass the raised thresholds; the exact 64-bit key comparison follows in the append path)
-        const bool k0 = a0 && ctr.x == vx, k1 = a1 && ctr.y == vy;
-        const bool k2 = a2 && ctr.z == vz, k3 = a3 && ctr.w == vw;
-        if (__any_sync(0xffffffffu, k0 | k1 | k2 | k3)) {
-          // exact filter on the 64-bit keys (value, then row-major index): a candidate that ties the cut's value but
-          // comes later in the map is below the cut, so a plateau at the top value stops appending after tsel entries
-          const int rc = row0 + idx - 2;
-          const float cv[4] = {ctr.x, ctr.y, ctr.z, ctr.w};
-          const uint32_t lo0 = 0xffffffffu - (uint32_t)(rc * W + c0);  // low key word of column c0 (column j: lo0 - j)
-          uint32_t chi = (uint32_t)(cut >> 32), clo = (uint32_t)cut;
-          bool keep[4] = {k0, k1, k2, k3};
+      __syncwarp();
+      if (lane == 0) mbar_arrive(empty0 + 8 * s);  // this warp is done reading the stage
+      continue;
+    }
+    const int count0 = count;
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const uint32_t hi = f2ord(cv[j]);
-            keep[j] = keep[j] && (hi > chi || (hi == chi && lo0 - j > clo));
-          }
-          if (__any_sync(0xffffffffu, keep[0] | keep[1] | keep[2] | keep[3])) {
-            if (count + 128 > CAPW || count >= next_sel) {
-              __syncwarp();
-              count = select_and_cut(list, count, tsel, kdist, lane, &bound);
-              cut = bound;
-              truncated = bound != 0ull;
-              // a short list means the value cut is active (distinct values): re-select often, each selection tightens the
-              // cut and the appends die out like kdist / candidates seen; a full list (ties) re-selects every SEL_SLACK keys
-              next_sel = count + (count < 16 ? 10 : SEL_SLACK);
-              chi = (uint32_t)(cut >> 32); clo = (uint32_t)cut;
-              if (cut) {  // "value > prev(cutv)" == "value >= cutv": no float lies between the two
-                const float pc = float_prev(key_val(cut));
-                tx = fmaxf(tx, pc); ty = fmaxf(ty, pc); tz = fmaxf(tz, pc); tw = fmaxf(tw, pc);
-              }
-            }
-            const uint32_t lt = (1u << lane) - 1u;
+    for (int u = 0; u < SCAN_R; ++u) {
+      {
+        const float l2 = __shfl_up_sync(0xffffffffu, v[u].z, 1), l1 = __shfl_up_sync(0xffffffffu, v[u].w, 1);
+        const float r1 = __shfl_down_sync(0xffffffffu, v[u].x, 1), r2 = __shfl_down_sync(0xffffffffu, v[u].y, 1);
+        const float mxyz = max3(v[u].x, v[u].y, v[u].z), myzw = max3(v[u].y, v[u].z, v[u].w);
+        raw[u] = v[u];
+        hm[u] = make_float4(max3(mxyz, l2, l1), max3(mxyz, l1, v[u].w), max3(myzw, v[u].x, r1), max3(myzw, r1, r2));
+      }
+      if (!pass[u]) continue;  // warp-uniform (voted with the thresholds of the stage's start: a superset)
+      const float4 ctr = raw[(u + 3) % 5];  // centre row = this row - 2
+      const float vx = max3(max3(hm[0].x, hm[1].x, hm[2].x), hm[3].x, hm[4].x);
+      const float vy = max3(max3(hm[0].y, hm[1].y, hm[2].y), hm[3].y, hm[4].y);
+      const float vz = max3(max3(hm[0].z, hm[1].z, hm[2].z), hm[3].z, hm[4].z);
+      const float vw = max3(max3(hm[0].w, hm[1].w, hm[2].w), hm[3].w, hm[4].w);
+      const float cv[4] = {ctr.x, ctr.y, ctr.z, ctr.w};
+      const bool kk[4] = {ctr.x > tx && ctr.x == vx, ctr.y > ty && ctr.y == vy, ctr.z > tz && ctr.z == vz, ctr.w > tw && ctr.w == vw};
+      if (!__any_sync(0xffffffffu, kk[0] | kk[1] | kk[2] | kk[3])) continue;
+      if (count + 128 > CAPW) {  // rare: a stage of a plateau map
+        count = scan_make_room(list, count, tsel, kdist, lane, &bound);
+        cut = bound;
+      }
+      // exact filter on the 64-bit keys (value, then row-major index): a candidate that ties the cut's value but comes
+      // later in the map is below the cut, so a plateau at the top value stops appending after tsel entries
+      const uint32_t chi = (uint32_t)(cut >> 32), clo = (uint32_t)cut;
+      const uint32_t lo0 = 0xffffffffu - (uint32_t)((row0 + k * SCAN_R + u - 2) * W + c0);  // low key word of column c0 (column j: lo0 - j)
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const uint32_t hi = f2ord(cv[j]);
-              const bool kp = keep[j] && (hi > chi || (hi == chi && lo0 - j > clo));
-              const uint32_t m = __ballot_sync(0xffffffffu, kp);
-              if (kp) list[count + __popc(m & lt)] = ((unsigned long long)hi << 32) | (unsigned long long)(lo0 - j);
-              count += __popc(m);
-            }
-          }
+      for (int j = 0; j < 4; ++j) {
+        const uint32_t hi = f2ord(cv[j]);
+        const bool kp = kk[j] && (hi > chi || (hi == chi && lo0 - j > clo));
+        const uint32_t m = __ballot_sync(0xffffffffu, kp);
+        if (kp) list[count + __popc(m & lt)] = ((unsigned long long)hi << 32) | (unsigned long long)(lo0 - j);
+        count += __popc(m);
+      }
+    }
+    if (count != count0) {  // once per stage that appended: value cut, thresholds, selection (one copy of this code)
+      __syncwarp();
+      if (vcut_on) {
+        for (int i = count0; i < count; ++i) {  // enter the new values into the warp's sorted list of distinct values
+          const float nv = key_val(list[i]);
+          const uint32_t gt = __ballot_sync(0xffffffffu, topv > nv);
+          if (__any_sync(0xffffffffu, topv == nv)) continue;
+          const float up = __shfl_up_sync(0xffffffffu, topv, 1);
+          const int pos = __popc(gt);  // the lanes holding larger values are exactly lanes [0, pos)
+          if (lane == pos) topv = nv;
+          else if (lane > pos) topv = up;
+        }
+        const float vc = __shfl_sync(0xffffffffu, topv, kdist - 1);
+        if (vc > vcut) {  // "value > prev(vc)" == "value >= vc": no float lies between the two
+          vcut = vc;
+          const float pc = float_prev(vc);
+          tx = fmaxf(tx, pc); ty = fmaxf(ty, pc); tz = fmaxf(tz, pc); tw = fmaxf(tw, pc);
+        }
+      }
+      if (count >= next_sel) {  // lists only grow long on tie-heavy maps: keep the best tsel keys, cut at the worst kept
+        count = scan_make_room(list, count, tsel, kdist, lane, &bound);
+        cut = bound;
+        next_sel = count + SEL_SLACK;
+        if (cut) {
+          const float pc = float_prev(key_val(cut));
+          tx = fmaxf(tx, pc); ty = fmaxf(ty, pc); tz = fmaxf(tz, pc); tw = fmaxf(tw, pc);
         }
       }
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(empty0 + 8 * s);  // this warp is done reading the stage
+  }
+  truncated = bound != 0ull;
+  if (vcut > NEG) {  // everything the raised thresholds skipped lies below the value cut
+    const unsigned long long ck = (unsigned long long)f2ord(vcut) << 32;
+    bound = ck > bound ? ck : bound;
   }
 }
 
@@ -427,7 +486,6 @@ __global__ void __launch_bounds__(288, MINB) peak_scan_kernel(const float* __res
   }
   // ---- consumers
   unsigned long long* list = s_lists + warp * (CAPW + TSEL);
-  unsigned long long* top = list + CAPW;
   const int c0 = warp * STRIP + (lane - 1) * 4;
   const bool inrange = c0 >= 0 && c0 + 3 < W;  // W % 4 == 0: a lane's four columns are all in or all out
   const bool owner = lane >= 1 && lane <= 30 && inrange;
@@ -439,15 +497,11 @@ __global__ void __launch_bounds__(288, MINB) peak_scan_kernel(const float* __res
   int nonconst = track ? 0 : 1;
   int count = 0, truncated = 0;
   unsigned long long bound = 0ull;
-  if (track) scan_rows<true>(stage0, full0, empty0, W, row0, nrows, y0, y1, ccol, c0, owner, tx, ty, tz, tw, p0, lane, list, top, count, truncated, nonconst, tsel, kdist, bound);
-  else scan_rows<false>(stage0, full0, empty0, W, row0, nrows, y0, y1, ccol, c0, owner, tx, ty, tz, tw, p0, lane, list, top, count, truncated, nonconst, tsel, kdist, bound);
+  if (track) scan_rows<true>(stage0, full0, empty0, W, row0, nrows, y0, y1, ccol, c0, owner, tx, ty, tz, tw, p0, lane, list, count, truncated, nonconst, tsel, kdist, bound);
+  else scan_rows<false>(stage0, full0, empty0, W, row0, nrows, y0, y1, ccol, c0, owner, tx, ty, tz, tw, p0, lane, list, count, truncated, nonconst, tsel, kdist, bound);
   __syncwarp();
-  if (count > tsel) {
-    warp_select_top(list, count, tsel, top, lane);
-    const unsigned long long w = list[tsel - 1];
-    bound = w > bound ? w : bound;
-    count = tsel;
-  }
+  // one closing selection: best tsel keys, then the value cut (drops what was appended while the cut was still lower)
+  if (count > min(tsel, kdist)) count = select_and_cut(list, count, tsel, kdist, lane, &bound);
   truncated = bound != 0ull;
   nonconst = __any_sync(0xffffffffu, nonconst);
   uint8_t* seg = ws + ((long long)(b * nbands + band) * nwarps + warp) * SEG_BYTES;
