@@ -267,14 +267,18 @@ __global__ void __launch_bounds__(256, 2) peak_scan_generic_kernel(const float* 
 //  * A band visits rows [lo-2, hi+2) for its centre rows [lo, hi): four warm-up rows fill the register ring, every
 //    later row emits, so the steady-state row has no row-range test; the column tests are folded into per-lane
 //    thresholds (+inf for columns that may not emit).
-//  * Per lane-row (4 pixels): one LDS.128, four shuffles, six FMNMX3 for the horizontal maxima, eight for the
-//    vertical ones, eight compares, one vote.
+//  * Per lane-row (4 pixels): one LDS.128, four shuffles, six FMNMX3 for the horizontal maxima; a stage's five rows are
+//    loaded and voted as a batch, so a stage in which nothing can emit (the common case) is one warp-uniform branch.
+//    Only rows that passed the threshold vote pay the eight FMNMX3 of the vertical maxima and the eight compares.
 //  * The "trivial image" rule (A.1 step 2) costs nothing unless the map's four probe pixels are equal (TRACK).
-//  * Density independence: a warp keeps only its best `tsel` keys in the end, so once it has selected them for the first
-//    time (after tsel + SEL_SLACK candidates) the worst kept key is a running cut that can only rise: later candidates
-//    below it are dropped by one float compare instead of being appended and selected away (they could never survive the
-//    final selection, so the segment written out is unchanged).  On iid-uniform maps, where 4 % of all pixels are 5x5
-//    maxima above the threshold, the appends decay like tsel / candidates seen and the scan stays a streaming kernel.
+//  * Density independence: the value cut (see scan_rows) is updated after every stage that appended, from the warp's
+//    sorted distinct candidate values, and the emission thresholds follow it; on iid-uniform maps, where 4 % of all
+//    pixels are 5x5 maxima above the threshold, the appends decay like (K + 1) / rows seen (23 % of the rows reach
+//    the vertical maxima, 53 % of the stages take the slow branch).  Ties are bounded by the key-level cut of the
+//    selections (tsel best keys, every SEL_SLACK appends).
+//  * Code size matters here: with the append / selection logic inlined into each of the five unrolled row bodies the
+//    hot loop was 30 KB of SASS and a quarter of the issue slots went to stall_no_instruction; the per-stage
+//    bookkeeping now exists once, after the unrolled rows, and the selections are out of line (12 KB).
 constexpr int SCAN_R = 5;    // rows per stage (= ring length, so ring slots are compile-time)
 #ifndef CROG_SCAN_NST
 #define CROG_SCAN_NST 4
