@@ -12,7 +12,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 SO_PATH = os.environ.get("CROG_B200_SO") or os.path.join(_HERE, "lib", "libcrog_b200.so")  # override: A/B of two builds
 
-ABI_VERSION = 5  # crog_abi_version() of the library these signatures were written for
+ABI_VERSION = 6  # crog_abi_version() of the library these signatures were written for
 F32, BF16 = 0, 1
 ACT_NONE, ACT_RELU, ACT_QUICKGELU, ACT_TANH = 0, 1, 2, 3
 IMPL_AUTO, IMPL_SIMT, IMPL_TCGEN05 = 0, 1, 2
@@ -75,7 +75,7 @@ SIGNATURES = {
     "crog_ssg_nms_workspace_bytes": (C.c_int64, [_I, _I]),
     "crog_ssg_fast_nms": (C.c_int, [_P, _P, _P, _I, _I, _F, _I, _I, _F, _P, _P, _P, _P, _P, _P]),
     "crog_ssg_detect": (C.c_int, [_P, _P, _P, _I, _I, _F, _F, _I, _I, _F, _P, _P, _P, _P, _P, _P, _P, _P]),
-    "crog_ssg_masks": (C.c_int, [_P, _I, _I, _I, _P, _P, _P, _P, _P, _I, _P, _P, _I, _I, _I, _I, _P]),
+    "crog_ssg_masks": (C.c_int, [_P, _I, _I, _I, _P, _P, _P, _P, _P, _I, _P, _P, _P, _I, _I, _I, _I, _P]),
     "crog_gaussian": (C.c_int, [_P, _P, _P, _I, _I, _I, _P, _I, _P, _I, _I, _P]),
     "crog_warp_affine_cubic_f32": (C.c_int, [_P, _I, _I, _I, _I, _P, _P, _I, _I, _F, _P]),
     "crog_preprocess_workspace_bytes": (C.c_int64, []),

@@ -28,7 +28,7 @@ bool crog_pdl_enabled() {
   }
   return on != 0;
 }
-extern "C" int crog_abi_version(void) { return 5; }
+extern "C" int crog_abi_version(void) { return 6; }
 
 extern "C" int crog_check_device(void) {
   int dev = 0;

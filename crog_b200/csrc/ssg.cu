@@ -372,7 +372,7 @@ __global__ void __launch_bounds__(256) ssg_lowres_kernel(const float* __restrict
 constexpr int BC_ROWS = 8;  // output rows per thread: the horizontal source indices / weights are computed once per column
 __global__ void __launch_bounds__(256) bilinear_crop_kernel(const float* __restrict__ in, int h, int w, float* __restrict__ out, int oh,
                                                             int ow, int S, const int* __restrict__ n_planes, int planes_per_det,
-                                                            uint32_t bin_mask, int det_stride) {
+                                                            uint32_t bin_mask, int det_stride, float* __restrict__ alt1) {
   const int pl = blockIdx.z;
   if (n_planes && pl >= *n_planes * planes_per_det) return;
   const int ox = blockIdx.x * blockDim.x + threadIdx.x;
@@ -386,6 +386,7 @@ __global__ void __launch_bounds__(256) bilinear_crop_kernel(const float* __restr
   const bool bin = (bin_mask >> k) & 1u;
   // output is map-major: [planes_per_det][det_stride detections][oh][ow], so each map type is one contiguous batch
   float* dst = out + ((long long)k * det_stride + d) * oh * ow + ox;
+  if (alt1 != nullptr && k == 1) dst = alt1 + (long long)d * oh * ow + ox;  // plane 1 (raw quality) to its own [det][oh][ow] buffer
 #pragma unroll
   for (int j = 0; j < BC_ROWS; ++j) {
     const int oy = blockIdx.y * BC_ROWS + j;
@@ -476,6 +477,75 @@ __global__ void __launch_bounds__(256) gaussian_horz_kernel(const float* __restr
 #pragma unroll
     for (int j = -R; j < 0; ++j) acc = __dadd_rn(acc, __dmul_rn(__dadd_rn((double)t[j], (double)t[-j]), g.w[j + R]));
     out[base + (long long)(y0 + rr) * W + x] = (float)acc;
+  }
+}
+
+// Both passes in one kernel: a CTA stages a (GF_TH + 2R) x (GF_TW + 2R) clamped input tile in shared memory, runs the
+// vertical pass for all GF_TW + 2R columns into a second tile (rounded to float32 exactly where the two-pass form stores
+// its intermediate), then the horizontal pass from that tile.  Same per-output operation order as above, so the results
+// are bit-identical; the float32 intermediate never goes to HBM (3.8 GB -> 1.9 GB per 768 maps of 480 x 640) and a
+// thread converts 3 values per output to float64 instead of 17.  What is left is the float64 pipe: 50 separately
+// rounded DADD / DMUL per output.
+constexpr int GF_TW = 128, GF_TH = 32;
+template <int R>
+__global__ void __launch_bounds__(256) gaussian_fused_kernel(const float* __restrict__ in, float* __restrict__ out, int H, int W,
+                                                             const int* __restrict__ n_planes, int plane_stride_sel, int plane_sel, GaussW g) {
+  constexpr int TWH = GF_TW + 2 * R;
+  __shared__ float t_in[GF_TH + 2 * R][TWH];
+  __shared__ __align__(16) float t_mid[GF_TH][TWH];
+  const int pz = blockIdx.z;
+  if (n_planes && pz >= *n_planes) return;
+  const long long base = ((long long)pz * plane_stride_sel + plane_sel) * H * W;
+  const int x0 = blockIdx.x * GF_TW, y0 = blockIdx.y * GF_TH;
+  for (int i = threadIdx.x; i < (GF_TH + 2 * R) * TWH; i += 256) {
+    const int rr = i / TWH, cc = i - rr * TWH;
+    const int yy = min(max(y0 - R + rr, 0), H - 1), xx = min(max(x0 - R + cc, 0), W - 1);
+    t_in[rr][cc] = __ldg(in + base + (long long)yy * W + xx);
+  }
+  __syncthreads();
+  // vertical pass: task = (column, group of 8 rows); consecutive threads take consecutive columns
+  for (int task = threadIdx.x; task < TWH * (GF_TH / 8); task += 256) {
+    const int gy = task / TWH, c = task - gy * TWH;
+    double v[8 + 2 * R];
+#pragma unroll
+    for (int j = 0; j < 8 + 2 * R; ++j) v[j] = (double)t_in[gy * 8 + j][c];
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+      double acc = __dmul_rn(v[t + R], g.w[R]);
+#pragma unroll
+      for (int j = -R; j < 0; ++j) acc = __dadd_rn(acc, __dmul_rn(__dadd_rn(v[t + R + j], v[t + R - j]), g.w[j + R]));
+      t_mid[gy * 8 + t][c] = (float)acc;
+    }
+  }
+  __syncthreads();
+  // horizontal pass: task = (row, group of 8 columns); a thread's 8 + 2R inputs are six 16-byte shared-memory loads
+  for (int task = threadIdx.x; task < GF_TH * (GF_TW / 8); task += 256) {
+    const int r = task / (GF_TW / 8), gx = task - r * (GF_TW / 8);
+    const int y = y0 + r, xb = x0 + gx * 8;
+    if (y >= H || xb >= W) continue;
+    double v[8 + 2 * R];
+    const float4* src = reinterpret_cast<const float4*>(&t_mid[r][gx * 8]);
+#pragma unroll
+    for (int j = 0; j < (8 + 2 * R) / 4; ++j) {
+      const float4 q = src[j];
+      v[4 * j] = (double)q.x; v[4 * j + 1] = (double)q.y; v[4 * j + 2] = (double)q.z; v[4 * j + 3] = (double)q.w;
+    }
+    float o[8];
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+      double acc = __dmul_rn(v[t + R], g.w[R]);
+#pragma unroll
+      for (int j = -R; j < 0; ++j) acc = __dadd_rn(acc, __dmul_rn(__dadd_rn(v[t + R + j], v[t + R - j]), g.w[j + R]));
+      o[t] = (float)acc;
+    }
+    float* dst = out + base + (long long)y * W + xb;
+    if (xb + 8 <= W && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+      reinterpret_cast<float4*>(dst)[0] = make_float4(o[0], o[1], o[2], o[3]);
+      reinterpret_cast<float4*>(dst)[1] = make_float4(o[4], o[5], o[6], o[7]);
+    } else {
+#pragma unroll
+      for (int t = 0; t < 8; ++t) if (xb + t < W) dst[t] = o[t];
+    }
   }
 }
 
@@ -583,7 +653,8 @@ extern "C" int crog_ssg_detect(const float* cls, const float* box, const float* 
 
 extern "C" int crog_ssg_masks(const float* protos, int32_t h, int32_t w, int32_t num_protos, const float* coef, const float* gcoef,
                               const float* boxes, const int32_t* det_anchor, const int32_t* det_n, int32_t max_det, float* lowres,
-                              float* out, int32_t out_det_stride, int32_t out_h, int32_t out_w, int32_t resize_to, void* stream) {
+                              float* out, float* quality_raw, int32_t out_det_stride, int32_t out_h, int32_t out_w, int32_t resize_to,
+                              void* stream) {
   CROG_REQUIRE(num_protos % 4 == 0 && num_protos <= 256 && aligned16(protos), CROG_E_BADSHAPE, "ssg_masks: num_protos %d", num_protos);
   CROG_REQUIRE(out_h <= resize_to && out_w <= resize_to && max_det * 5 <= 65535, CROG_E_BADSHAPE, "ssg_masks: bad output extent");
   if (out_det_stride <= 0) out_det_stride = max_det;
@@ -593,7 +664,7 @@ extern "C" int crog_ssg_masks(const float* protos, int32_t h, int32_t w, int32_t
   ssg_lowres_kernel<<<g1, 256, 5 * num_protos * sizeof(float), s>>>(protos, h, w, num_protos, coef, gcoef, boxes, det_anchor, det_n, lowres);
   CROG_LAUNCH_OK("ssg_lowres");
   dim3 g2((out_w + 255) / 256, (out_h + BC_ROWS - 1) / BC_ROWS, max_det * 5);
-  bilinear_crop_kernel<<<g2, 256, 0, s>>>(lowres, h, w, out, out_h, out_w, resize_to, det_n, 5, 1u, out_det_stride);
+  bilinear_crop_kernel<<<g2, 256, 0, s>>>(lowres, h, w, out, out_h, out_w, resize_to, det_n, 5, 1u, out_det_stride, quality_raw);
   CROG_LAUNCH_OK("ssg_resize");
   return CROG_OK;
 }
@@ -608,7 +679,14 @@ extern "C" int crog_gaussian(const float* in, float* tmp, float* out, int32_t P,
   g.r = r;
   for (int i = 0; i <= 2 * r; ++i) g.w[i] = weights_host[i];
   cudaStream_t s = (cudaStream_t)stream;
-  if (radius == 8 && !getenv("CROG_GAUSSIAN_GENERIC")) {  // sigma = 2, the only radius the reference uses (grasp_eval.py:198)
+  if (radius == 8 && in != out && !getenv("CROG_GAUSSIAN_GENERIC") && !getenv("CROG_GAUSSIAN_TWOPASS")) {  // sigma = 2, the reference's (grasp_eval.py:198)
+    static_assert((GF_TW + 16) % 4 == 0 && GF_TH % 8 == 0 && GF_TW % 8 == 0, "tile shape");
+    gaussian_fused_kernel<8><<<dim3((W + GF_TW - 1) / GF_TW, (H + GF_TH - 1) / GF_TH, P), 256, 0, s>>>(in, out, H, W, n_planes, plane_stride, plane_sel, g);
+    CROG_LAUNCH_OK("gaussian_fused");
+    return CROG_OK;
+  }
+  CROG_REQUIRE(tmp != nullptr, CROG_E_BADSHAPE, "gaussian: the two-pass forms (in-place call, radius != 8) need the tmp buffer");
+  if (radius == 8 && !getenv("CROG_GAUSSIAN_GENERIC")) {
     gaussian_vert_kernel<8><<<dim3((W + 255) / 256, (H + GV_TY - 1) / GV_TY, P), 256, 0, s>>>(in, tmp, H, W, n_planes, plane_stride, plane_sel, g);
     CROG_LAUNCH_OK("gaussian_rows");
     gaussian_horz_kernel<8><<<dim3((W + 255) / 256, (H + GH_ROWS - 1) / GH_ROWS, P), 256, 0, s>>>(tmp, out, H, W, n_planes, plane_stride, plane_sel, g);

@@ -10,6 +10,7 @@ There is no CPU implementation here: without a B200 every function raises.
 """
 from __future__ import annotations
 
+import os
 from typing import Optional, Tuple
 
 import numpy as np
@@ -249,11 +250,15 @@ def gaussian_batched(maps: torch.Tensor, sigma: float = 2.0, out: Optional[torch
     assert maps.is_cuda and maps.dtype == torch.float32 and maps.dim() == 3 and maps.is_contiguous()
     taps = gaussian_taps(sigma)
     P, H, W = maps.shape
-    tmp = torch.empty_like(maps)
     out = torch.empty_like(maps) if out is None else out
+    radius = (len(taps) - 1) // 2
+    # out of place with sigma = 2 the library runs both passes in one kernel; otherwise it needs the intermediate buffer
+    two_pass = (out.data_ptr() == maps.data_ptr() or radius != 8 or "CROG_GAUSSIAN_TWOPASS" in os.environ
+                or "CROG_GAUSSIAN_GENERIC" in os.environ)
+    tmp = torch.empty_like(maps) if two_pass else None
     with torch.cuda.device(maps.device):
-        L.check(lib.crog_gaussian(maps.data_ptr(), tmp.data_ptr(), out.data_ptr(), P, H, W, taps.ctypes.data, (len(taps) - 1) // 2,
-                                  None, 1, 0, L.stream_ptr()))
+        L.check(lib.crog_gaussian(maps.data_ptr(), tmp.data_ptr() if two_pass else None, out.data_ptr(), P, H, W, taps.ctypes.data,
+                                  radius, None, 1, 0, L.stream_ptr()))
     return out
 
 
@@ -318,16 +323,13 @@ def ssg_masks_device(cfg, output_b, boxes, det_anchor, n: int, ori_size):
     hr = torch.empty((5, n, ori_h, ori_w), dtype=torch.float32, device=dev)
     if n == 0:
         return hr
-    taps = gaussian_taps(2.0)
-    tmp = torch.empty((n, ori_h, ori_w), dtype=torch.float32, device=dev)
+    qraw = torch.empty((n, ori_h, ori_w), dtype=torch.float32, device=dev)  # un-smoothed quality maps
     n_dev = torch.full((1,), n, dtype=torch.int32, device=dev)
     with torch.cuda.device(dev):
         L.check(lib.crog_ssg_masks(protos.data_ptr(), h, w, npz, coef.data_ptr(), gco.data_ptr(), boxes.data_ptr(),
-                                   det_anchor.data_ptr(), n_dev.data_ptr(), n, lowres.data_ptr(), hr.data_ptr(), n, ori_h, ori_w, S,
-                                   L.stream_ptr()))
-        q = hr[1]
-        L.check(lib.crog_gaussian(q.data_ptr(), tmp.data_ptr(), q.data_ptr(), n, ori_h, ori_w, taps.ctypes.data, (len(taps) - 1) // 2,
-                                  None, 1, 0, L.stream_ptr()))
+                                   det_anchor.data_ptr(), n_dev.data_ptr(), n, lowres.data_ptr(), hr.data_ptr(), qraw.data_ptr(), n,
+                                   ori_h, ori_w, S, L.stream_ptr()))
+    gaussian_batched(qraw, 2.0, out=hr[1])
     return hr
 
 
@@ -423,6 +425,7 @@ def ssg_post_processing_batched(cfg, output_dict, ori_size=(480, 640)):
         tot = offs[-1]
         hr = torch.empty((5, max(tot, 1), ori_h, ori_w), dtype=torch.float32, device=dev)
         lowres = torch.empty((max(tot, 1), 5, h, w), dtype=torch.float32, device=dev)
+        qraw = torch.empty((max(tot, 1), ori_h, ori_w), dtype=torch.float32, device=dev)  # un-smoothed quality maps
         plane = ori_h * ori_w
         for b in range(B):
             if counts[b] == 0:
@@ -430,12 +433,10 @@ def ssg_post_processing_batched(cfg, output_dict, ori_size=(480, 640)):
             # detection stride of the map-major output = tot instances: image b fills instances [offs[b], offs[b] + n_b)
             L.check(lib.crog_ssg_masks(protos[b].data_ptr(), h, w, npz, coef[b].data_ptr(), gco[b].data_ptr(), boxes[b].data_ptr(),
                                        det_anchor[b].data_ptr(), det_n[b:].data_ptr(), counts[b], lowres[offs[b]:].data_ptr(),
-                                       hr.data_ptr() + offs[b] * plane * 4, tot, ori_h, ori_w, S, s))
+                                       hr.data_ptr() + offs[b] * plane * 4, qraw.data_ptr() + offs[b] * plane * 4, tot, ori_h, ori_w,
+                                       S, s))
         if tot > 0:
-            taps = gaussian_taps(2.0)
-            tmp = torch.empty((tot, ori_h, ori_w), dtype=torch.float32, device=dev)
-            L.check(lib.crog_gaussian(hr[1].data_ptr(), tmp.data_ptr(), hr[1].data_ptr(), tot, ori_h, ori_w, taps.ctypes.data,
-                                      (len(taps) - 1) // 2, None, 1, 0, s))
+            gaussian_batched(qraw[:tot], 2.0, out=hr[1, :tot])  # smoothed out of place into the quality plane
             _, npk, grasps = detect_grasps_batched(hr[1, :tot], hr[2, :tot], hr[3, :tot], hr[4, :tot], 5)
         else:
             npk = torch.zeros((0,), dtype=torch.int32, device=dev)

@@ -291,14 +291,19 @@ int crog_ssg_detect(const float* cls, const float* box, const float* anchors, in
  * (sigmoid on ins / qua / wid), [max_det, 5, h, w]; out[k][d] = bilinear resize to resize_to^2 (align_corners=False)
  * cropped to [out_h, out_w], map-major [5, out_det_stride, out_h, out_w] (out_det_stride <= 0: max_det; a larger stride
  * lets several images fill disjoint instance ranges of one batch-wide tensor); the instance plane is thresholded
- * (> 0.5 -> 1.0).  Only the first *det_n (<= max_det) detections are written. */
+ * (> 0.5 -> 1.0).  Only the first *det_n (<= max_det) detections are written.  quality_raw (may be NULL): when given,
+ * the un-smoothed quality plane is written there as [max_det, out_h, out_w] instead of into out's plane 1, so that
+ * crog_gaussian can smooth it INTO out's plane 1 out of place (its one-kernel form). */
 int crog_ssg_masks(const float* protos, int32_t h, int32_t w, int32_t num_protos, const float* coef, const float* gcoef,
                    const float* boxes, const int32_t* det_anchor, const int32_t* det_n, int32_t max_det, float* lowres,
-                   float* out, int32_t out_det_stride, int32_t out_h, int32_t out_w, int32_t resize_to, void* stream);
+                   float* out, float* quality_raw, int32_t out_det_stride, int32_t out_h, int32_t out_w, int32_t resize_to,
+                   void* stream);
 /* skimage.filters.gaussian(map, sigma, preserve_range=True) of grasp_eval.py:198 = scipy.ndimage.gaussian_filter(mode='nearest'):
  * separable (rows first), float64 accumulation in scipy's tap order, float32 result per pass.  weights_host: the 2*radius+1
  * normalised float64 taps (HOST pointer; computed by the caller exactly as scipy does).  Planes smoothed:
- * p * plane_stride + plane_sel for p < min(P, *n_planes) (n_planes may be NULL); tmp and out use the same layout; out may alias in. */
+ * p * plane_stride + plane_sel for p < min(P, *n_planes) (n_planes may be NULL); tmp and out use the same layout.  With
+ * out != in and radius 8 (sigma 2) both passes run in one kernel (the float32 intermediate stays in shared memory) and tmp
+ * may be NULL; out may alias in, which selects the two-pass form through tmp.  Bit-identical either way. */
 int crog_gaussian(const float* in, float* tmp, float* out, int32_t P, int32_t H, int32_t W, const double* weights_host,
                   int32_t radius, const int32_t* n_planes, int32_t plane_stride, int32_t plane_sel, void* stream);
 

@@ -28,7 +28,7 @@ def test_header_symbols_are_exported(built):
     assert declared == set(L.SIGNATURES), declared ^ set(L.SIGNATURES)
     for name in declared:
         assert hasattr(built, name), name
-    assert built.crog_abi_version() == L.ABI_VERSION == 5
+    assert built.crog_abi_version() == L.ABI_VERSION == 6
     assert built.crog_detect_workspace_bytes(4096, 416, 416, 5) > 0  # pure host arithmetic, no device needed
 
 
