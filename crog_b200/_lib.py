@@ -76,6 +76,8 @@ SIGNATURES = {
     "crog_ssg_fast_nms": (C.c_int, [_P, _P, _P, _I, _I, _F, _I, _I, _F, _P, _P, _P, _P, _P, _P]),
     "crog_ssg_detect": (C.c_int, [_P, _P, _P, _I, _I, _F, _F, _I, _I, _F, _P, _P, _P, _P, _P, _P, _P, _P]),
     "crog_ssg_masks": (C.c_int, [_P, _I, _I, _I, _P, _P, _P, _P, _P, _I, _P, _P, _P, _I, _I, _I, _I, _P]),
+    "crog_ssg_detect_batched": (C.c_int, [_P, _P, _P, _I, _I, _I, _F, _F, _I, _I, _F, _P, _P, _P, _P, _P, _P, _P, _L, _P]),
+    "crog_ssg_masks_batched": (C.c_int, [_P, _I, _I, _I, _P, _P, _P, _P, _I, _I, _P, _P, _I, _P, _P, _P, _I, _I, _I, _P]),
     "crog_gaussian": (C.c_int, [_P, _P, _P, _I, _I, _I, _P, _I, _P, _I, _I, _P]),
     "crog_warp_affine_cubic_f32": (C.c_int, [_P, _I, _I, _I, _I, _P, _P, _I, _I, _F, _P]),
     "crog_preprocess_workspace_bytes": (C.c_int64, []),

@@ -156,6 +156,10 @@ __global__ void ssg_decode_kernel(const float* __restrict__ cls, const float* __
                                   int N, int nc, float thr, int* __restrict__ keep, float* __restrict__ boxes) {
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= N) return;
+  {  // blockIdx.y = image of a batch-wide launch ([B,N,nc] scores, [B,N,4] offsets; the anchors are shared)
+    const long long img = blockIdx.y;
+    cls += img * N * nc; box += img * N * 4; keep += img * N; boxes += img * N * 4;
+  }
   float mx = -INFINITY;
   for (int c = 1; c < nc; ++c) mx = fmaxf(mx, cls[(long long)n * nc + c]);
   keep[n] = mx > thr;
@@ -209,7 +213,14 @@ __device__ __forceinline__ float box_iou1(const float4 a, const float4 b) {
 __global__ void __launch_bounds__(NMS_T) ssg_nms_class_kernel(const float* __restrict__ cls, const int* __restrict__ keep,
                                                               const float* __restrict__ boxes, int N, int nc, int top_k, float iou_thr,
                                                               unsigned long long* __restrict__ cand, int* __restrict__ cand_keep,
-                                                              int* __restrict__ cand_n) {
+                                                              int* __restrict__ cand_n, long long ws_stride) {
+  {  // blockIdx.y = image of a batch-wide launch; every image has its own workspace slice (ws_stride bytes apart)
+    const long long img = blockIdx.y;
+    cls += img * N * nc; keep += img * N; boxes += img * N * 4;
+    cand = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(cand) + img * ws_stride);
+    cand_keep = reinterpret_cast<int*>(reinterpret_cast<char*>(cand_keep) + img * ws_stride);
+    cand_n = reinterpret_cast<int*>(reinterpret_cast<char*>(cand_n) + img * ws_stride);
+  }
   extern __shared__ unsigned long long s_keys[];  // [NMS_CAP]
   __shared__ unsigned long long s_sel[NMS_SEL];
   __shared__ float4 s_box[NMS_SEL];
@@ -288,7 +299,14 @@ constexpr int MRG_CAP = 8192;
 __global__ void __launch_bounds__(1024) ssg_nms_merge_kernel(const unsigned long long* __restrict__ cand, const int* __restrict__ cand_keep,
                                                              const int* __restrict__ cand_n, int ncls, int top_k, int max_det, float thr2,
                                                              int* __restrict__ det_n, int* __restrict__ det_anchor, int* __restrict__ det_class,
-                                                             float* __restrict__ det_score) {
+                                                             float* __restrict__ det_score, long long ws_stride) {
+  {  // blockIdx.x = image of a batch-wide launch
+    const long long img = blockIdx.x;
+    cand = reinterpret_cast<const unsigned long long*>(reinterpret_cast<const char*>(cand) + img * ws_stride);
+    cand_keep = reinterpret_cast<const int*>(reinterpret_cast<const char*>(cand_keep) + img * ws_stride);
+    cand_n = reinterpret_cast<const int*>(reinterpret_cast<const char*>(cand_n) + img * ws_stride);
+    det_n += img; det_anchor += img * max_det; det_class += img * max_det; det_score += img * max_det;
+  }
   extern __shared__ unsigned long long s_k[];  // [MRG_CAP]
   __shared__ int s_pass;
   for (int i = threadIdx.x; i < MRG_CAP; i += blockDim.x) {
@@ -330,11 +348,23 @@ __global__ void __launch_bounds__(1024) ssg_nms_merge_kernel(const unsigned long
 __global__ void __launch_bounds__(256) ssg_lowres_kernel(const float* __restrict__ protos, int h, int w, int np_,
                                                          const float* __restrict__ coef, const float* __restrict__ gcoef,
                                                          const float* __restrict__ boxes, const int* __restrict__ det_anchor,
-                                                         const int* __restrict__ det_n, float* __restrict__ out) {
+                                                         const int* __restrict__ det_n, float* __restrict__ out,
+                                                         const int* __restrict__ inst_image, const int* __restrict__ inst_det, int N,
+                                                         int max_det) {
   extern __shared__ float s_c[];  // [5][np]
   const int d = blockIdx.y;
-  if (d >= *det_n) return;
-  const int a = det_anchor[d];
+  int a;
+  if (inst_image != nullptr) {  // batch-wide call: instance d of the batch = detection inst_det[d] of image inst_image[d]
+    const int b = inst_image[d];
+    a = det_anchor[b * max_det + inst_det[d]];
+    protos += (long long)b * h * w * np_;
+    coef += (long long)b * N * np_;
+    gcoef += (long long)b * N * 4 * np_;
+    boxes += (long long)b * N * 4;
+  } else {
+    if (d >= *det_n) return;
+    a = det_anchor[d];
+  }
   for (int i = threadIdx.x; i < 5 * np_; i += blockDim.x) {
     const int k = i / np_, j = i % np_;
     s_c[i] = k == 0 ? coef[(long long)a * np_ + j] : gcoef[((long long)a * 4 + (k - 1)) * np_ + j];
@@ -369,15 +399,30 @@ __global__ void __launch_bounds__(256) ssg_lowres_kernel(const float* __restrict
 
 // ------------------------------------------------------------------ F.interpolate(size=(S,S), bilinear, align_corners=False) + [:oh, :ow] crop
 // planes [P][h][w] -> [P][oh][ow]; planes whose bit is set in bin_mask (by plane % planes_per_det) are thresholded > 0.5.
-constexpr int BC_ROWS = 8;  // output rows per thread: the horizontal source indices / weights are computed once per column
+constexpr int BC_ROWS = 32;  // output rows per thread
+// A thread owns one output column and BC_ROWS consecutive rows.  The horizontal source indices / weights are computed once
+// per column, the vertical ones once per CTA (shared-memory table), and the two horizontally interpolated source rows
+// slide down the column: at scale 136 -> 640 a new source row (2 loads, 3 flops) is needed every ~4.7 output rows, so an
+// output costs ~10 instructions instead of ~35 (4 loads + full address / weight arithmetic per output: 2.9 ms for the
+// 3.1 GB of masks of a 64-image batch, 1.05 TB/s).
 __global__ void __launch_bounds__(256) bilinear_crop_kernel(const float* __restrict__ in, int h, int w, float* __restrict__ out, int oh,
                                                             int ow, int S, const int* __restrict__ n_planes, int planes_per_det,
                                                             uint32_t bin_mask, int det_stride, float* __restrict__ alt1) {
+  __shared__ int s_y0[BC_ROWS];
+  __shared__ float s_ly[BC_ROWS];
   const int pl = blockIdx.z;
   if (n_planes && pl >= *n_planes * planes_per_det) return;
+  const float sc_h = (float)h / (float)S, sc_w = (float)w / (float)S;
+  const int oyb = blockIdx.y * BC_ROWS;
+  if (threadIdx.x < BC_ROWS) {
+    const float sy = fmaxf(__fsub_rn(__fmul_rn(sc_h, (float)(oyb + (int)threadIdx.x) + 0.5f), 0.5f), 0.f);
+    const int y0 = min((int)sy, h - 1);
+    s_y0[threadIdx.x] = y0;
+    s_ly[threadIdx.x] = sy - y0;
+  }
+  __syncthreads();
   const int ox = blockIdx.x * blockDim.x + threadIdx.x;
   if (ox >= ow) return;
-  const float sc_h = (float)h / (float)S, sc_w = (float)w / (float)S;
   const float sx = fmaxf(__fsub_rn(__fmul_rn(sc_w, (float)ox + 0.5f), 0.5f), 0.f);
   const int x0 = (int)sx, x1 = x0 + (x0 < w - 1);
   const float lx = sx - x0, hx = 1.f - lx;
@@ -387,14 +432,22 @@ __global__ void __launch_bounds__(256) bilinear_crop_kernel(const float* __restr
   // output is map-major: [planes_per_det][det_stride detections][oh][ow], so each map type is one contiguous batch
   float* dst = out + ((long long)k * det_stride + d) * oh * ow + ox;
   if (alt1 != nullptr && k == 1) dst = alt1 + (long long)d * oh * ow + ox;  // plane 1 (raw quality) to its own [det][oh][ow] buffer
-#pragma unroll
+  auto hrow = [&](int y) { return hx * __ldg(src + y * w + x0) + lx * __ldg(src + y * w + x1); };
+  int cur = -2;
+  float top = 0.f, bot = 0.f;
+#pragma unroll 4
   for (int j = 0; j < BC_ROWS; ++j) {
-    const int oy = blockIdx.y * BC_ROWS + j;
+    const int oy = oyb + j;
     if (oy >= oh) break;
-    const float sy = fmaxf(__fsub_rn(__fmul_rn(sc_h, (float)oy + 0.5f), 0.5f), 0.f);
-    const int y0 = (int)sy, y1 = y0 + (y0 < h - 1);
-    const float ly = sy - y0, hy = 1.f - ly;
-    const float v = hy * (hx * __ldg(src + y0 * w + x0) + lx * __ldg(src + y0 * w + x1)) + ly * (hx * __ldg(src + y1 * w + x0) + lx * __ldg(src + y1 * w + x1));
+    const int y0 = s_y0[j];  // warp-uniform
+    if (y0 != cur) {
+      const bool last = y0 >= h - 1;
+      top = (y0 == cur + 1 && cur >= 0) ? bot : hrow(y0);
+      bot = last ? top : hrow(y0 + 1);
+      cur = y0;
+    }
+    const float ly = s_ly[j], hy = 1.f - ly;
+    const float v = hy * top + ly * bot;
     dst[(long long)oy * ow] = bin ? (v > 0.5f ? 1.f : 0.f) : v;
   }
 }
@@ -615,13 +668,14 @@ extern "C" int64_t crog_ssg_nms_workspace_bytes(int32_t num_classes, int32_t top
   return n * 8 + n * 4 + (int64_t)(num_classes - 1) * 4 + 256;
 }
 
-extern "C" int crog_ssg_fast_nms(const float* cls, const int32_t* keep, const float* boxes, int32_t N, int32_t num_classes, float iou_thr,
-                                 int32_t top_k, int32_t max_det, float score_thr2, int32_t* det_n, int32_t* det_anchor, int32_t* det_class,
-                                 float* det_score, void* workspace, void* stream) {
+static int ssg_fast_nms_launch(const float* cls, const int32_t* keep, const float* boxes, int32_t B, int32_t N, int32_t num_classes,
+                               float iou_thr, int32_t top_k, int32_t max_det, float score_thr2, int32_t* det_n, int32_t* det_anchor,
+                               int32_t* det_class, float* det_score, void* workspace, long long ws_stride, void* stream) {
   CROG_REQUIRE(N >= 0 && num_classes >= 2 && top_k >= 1 && top_k <= NMS_SEL && max_det >= 1 && max_det <= 1024, CROG_E_BADSHAPE,
                "ssg_fast_nms: N %d classes %d top_k %d max_det %d", N, num_classes, top_k, max_det);
   CROG_REQUIRE(N <= NMS_CAP && (num_classes - 1) * top_k <= MRG_CAP, CROG_E_BADSHAPE, "ssg_fast_nms: at most %d anchors and %d candidates", NMS_CAP, MRG_CAP);
-  CROG_REQUIRE(aligned16(boxes) && aligned16(workspace), CROG_E_BADALIGN, "ssg_fast_nms: 16B alignment");
+  CROG_REQUIRE(aligned16(boxes) && aligned16(workspace) && ws_stride % 16 == 0, CROG_E_BADALIGN, "ssg_fast_nms: 16B alignment");
+  CROG_REQUIRE(B >= 1 && B <= 65535, CROG_E_BADSHAPE, "ssg_fast_nms: batch %d", B);
   cudaStream_t s = (cudaStream_t)stream;
   const int ncls = num_classes - 1;
   unsigned long long* cand = (unsigned long long*)workspace;
@@ -634,13 +688,32 @@ extern "C" int crog_ssg_fast_nms(const float* cls, const int32_t* keep, const fl
     CROG_CUDA_OK(cudaFuncSetAttribute(ssg_nms_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MRG_CAP * 8));
     once.done(dev_);
   }
-  ssg_nms_class_kernel<<<ncls, NMS_T, NMS_CAP * 8, s>>>(cls, keep, boxes, N, num_classes, top_k, iou_thr, cand, cand_keep, cand_n);
+  ssg_nms_class_kernel<<<dim3(ncls, B), NMS_T, NMS_CAP * 8, s>>>(cls, keep, boxes, N, num_classes, top_k, iou_thr, cand, cand_keep, cand_n,
+                                                                 ws_stride);
   CROG_LAUNCH_OK("ssg_nms_class");
-  ssg_nms_merge_kernel<<<1, 1024, MRG_CAP * 8, s>>>(cand, cand_keep, cand_n, ncls, top_k, max_det, score_thr2, det_n, det_anchor, det_class, det_score);
+  ssg_nms_merge_kernel<<<B, 1024, MRG_CAP * 8, s>>>(cand, cand_keep, cand_n, ncls, top_k, max_det, score_thr2, det_n, det_anchor, det_class,
+                                                    det_score, ws_stride);
   CROG_LAUNCH_OK("ssg_nms_merge");
   return CROG_OK;
 }
-
+extern "C" int crog_ssg_fast_nms(const float* cls, const int32_t* keep, const float* boxes, int32_t N, int32_t num_classes, float iou_thr,
+                                 int32_t top_k, int32_t max_det, float score_thr2, int32_t* det_n, int32_t* det_anchor, int32_t* det_class,
+                                 float* det_score, void* workspace, void* stream) {
+  return ssg_fast_nms_launch(cls, keep, boxes, 1, N, num_classes, iou_thr, top_k, max_det, score_thr2, det_n, det_anchor, det_class, det_score,
+                             workspace, 0, stream);
+}
+extern "C" int crog_ssg_detect_batched(const float* cls, const float* box, const float* anchors, int32_t B, int32_t N, int32_t num_classes,
+                                       float score_thr, float iou_thr, int32_t top_k, int32_t max_det, float score_thr2, int32_t* keep,
+                                       float* boxes, int32_t* det_n, int32_t* det_anchor, int32_t* det_class, float* det_score,
+                                       void* workspace, int64_t workspace_stride, void* stream) {
+  CROG_REQUIRE(N >= 1 && B >= 0 && B <= 65535, CROG_E_BADSHAPE, "ssg_detect_batched: B %d N %d", B, N);
+  CROG_REQUIRE(workspace_stride >= crog_ssg_nms_workspace_bytes(num_classes, top_k), CROG_E_BADSHAPE, "ssg_detect_batched: workspace stride too small");
+  if (B == 0) return CROG_OK;
+  ssg_decode_kernel<<<dim3((N + 255) / 256, B), 256, 0, (cudaStream_t)stream>>>(cls, box, anchors, N, num_classes, score_thr, keep, boxes);
+  CROG_LAUNCH_OK("ssg_decode");
+  return ssg_fast_nms_launch(cls, keep, boxes, B, N, num_classes, iou_thr, top_k, max_det, score_thr2, det_n, det_anchor, det_class, det_score,
+                             workspace, workspace_stride, stream);
+}
 extern "C" int crog_ssg_detect(const float* cls, const float* box, const float* anchors, int32_t N, int32_t num_classes, float score_thr,
                                float iou_thr, int32_t top_k, int32_t max_det, float score_thr2, int32_t* keep, float* boxes,
                                int32_t* det_n, int32_t* det_anchor, int32_t* det_class, float* det_score, void* workspace, void* stream) {
@@ -661,11 +734,38 @@ extern "C" int crog_ssg_masks(const float* protos, int32_t h, int32_t w, int32_t
   CROG_REQUIRE(max_det >= 1, CROG_E_BADSHAPE, "ssg_masks: max_det");
   cudaStream_t s = (cudaStream_t)stream;
   dim3 g1((h * w + 255) / 256, max_det);
-  ssg_lowres_kernel<<<g1, 256, 5 * num_protos * sizeof(float), s>>>(protos, h, w, num_protos, coef, gcoef, boxes, det_anchor, det_n, lowres);
+  ssg_lowres_kernel<<<g1, 256, 5 * num_protos * sizeof(float), s>>>(protos, h, w, num_protos, coef, gcoef, boxes, det_anchor, det_n, lowres,
+                                                                    nullptr, nullptr, 0, 0);
   CROG_LAUNCH_OK("ssg_lowres");
   dim3 g2((out_w + 255) / 256, (out_h + BC_ROWS - 1) / BC_ROWS, max_det * 5);
   bilinear_crop_kernel<<<g2, 256, 0, s>>>(lowres, h, w, out, out_h, out_w, resize_to, det_n, 5, 1u, out_det_stride, quality_raw);
   CROG_LAUNCH_OK("ssg_resize");
+  return CROG_OK;
+}
+
+extern "C" int crog_ssg_masks_batched(const float* protos, int32_t h, int32_t w, int32_t num_protos, const float* coef, const float* gcoef,
+                                      const float* boxes, const int32_t* det_anchor, int32_t N, int32_t max_det,
+                                      const int32_t* inst_image, const int32_t* inst_det, int32_t total, float* lowres, float* out,
+                                      float* quality_raw, int32_t out_h, int32_t out_w, int32_t resize_to, void* stream) {
+  CROG_REQUIRE(num_protos % 4 == 0 && num_protos <= 256 && aligned16(protos), CROG_E_BADSHAPE, "ssg_masks_batched: num_protos %d", num_protos);
+  CROG_REQUIRE(out_h <= resize_to && out_w <= resize_to && N >= 1 && max_det >= 1, CROG_E_BADSHAPE, "ssg_masks_batched: bad extent");
+  CROG_REQUIRE(inst_image != nullptr && inst_det != nullptr, CROG_E_BADSHAPE, "ssg_masks_batched: instance maps missing");
+  if (total <= 0) return CROG_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  const int CH = 13000;  // instances per launch (grid.z = 5 planes per instance <= 65535)
+  const long long plane = (long long)out_h * out_w;
+  for (int i0 = 0; i0 < total; i0 += CH) {
+    const int n = total - i0 < CH ? total - i0 : CH;
+    dim3 g1((h * w + 255) / 256, n);
+    ssg_lowres_kernel<<<g1, 256, 5 * num_protos * sizeof(float), s>>>(protos, h, w, num_protos, coef, gcoef, boxes, det_anchor, nullptr,
+                                                                      lowres + (long long)i0 * 5 * h * w, inst_image + i0, inst_det + i0, N,
+                                                                      max_det);
+    CROG_LAUNCH_OK("ssg_lowres");
+    dim3 g2((out_w + 255) / 256, (out_h + BC_ROWS - 1) / BC_ROWS, n * 5);
+    bilinear_crop_kernel<<<g2, 256, 0, s>>>(lowres + (long long)i0 * 5 * h * w, h, w, out + i0 * plane, out_h, out_w, resize_to, nullptr, 5,
+                                            1u, total, quality_raw ? quality_raw + i0 * plane : nullptr);
+    CROG_LAUNCH_OK("ssg_resize");
+  }
   return CROG_OK;
 }
 

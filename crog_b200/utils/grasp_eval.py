@@ -373,10 +373,9 @@ def ssg_post_processing(cfg, output_dict, data_dict):
 @torch.no_grad()
 def ssg_post_processing_batched(cfg, output_dict, ori_size=(480, 640)):
     """Device-resident batched form used by the engine / benchmark: the per-image stages of ssg_post_processing for every
-    sample of a batch with ONE host synchronisation (the detection counts) and nothing else leaving HBM.  The detection
-    stage is launched per image into slices of batch-wide buffers; after the counts are known, the masks of all images are
-    assembled into ONE map-major tensor ``[5, sum(n), H, W]`` (each image writes its own instance range), then one
-    Gaussian and one peak decode run over all ``sum(n)`` instance maps.
+    sample of a batch with ONE host synchronisation (the detection counts) and nothing else leaving HBM.  Every stage is a
+    batch-wide launch: box decode + Fast NMS (three kernels, grid dimension = image); after the counts are known, the masks
+    of all instances into ONE map-major tensor ``[5, sum(n), H, W]`` (two kernels), one Gaussian, one peak decode.
     Returns a list of per-sample dicts of CUDA tensors (views): n, cls, boxes, scores, hr [5,n,H,W], n_peaks [n],
     grasps [n,5,5]."""
     lib = L.lib()
@@ -401,23 +400,11 @@ def ssg_post_processing_batched(cfg, output_dict, ori_size=(480, 640)):
     ws = torch.empty((B, ws_bytes), dtype=torch.uint8, device=dev)
     with torch.cuda.device(dev):
         s = L.stream_ptr()
-        # the per-image detection kernels have small grids (one CTA per class): images are independent, so they are spread
-        # over a pool of streams and fill the GPU side by side instead of queueing behind each other
-        main = torch.cuda.current_stream()
-        pool = _stream_pool(dev, min(8, B))
-        fork = torch.cuda.Event()
-        fork.record(main)
-        for st in pool:
-            st.wait_event(fork)
-        for b in range(B):
-            L.check(lib.crog_ssg_detect(cls[b].data_ptr(), box[b].data_ptr(), anchors.data_ptr(), N, nc, float(cfg.nms_score_thre),
-                                        float(cfg.nms_iou_thre), int(cfg.top_k), md, 0.3, keep[b].data_ptr(), boxes[b].data_ptr(),
-                                        det_n[b:].data_ptr(), det_anchor[b].data_ptr(), det_class[b].data_ptr(),
-                                        det_score[b].data_ptr(), ws[b].data_ptr(), pool[b % len(pool)].cuda_stream))
-        for st in pool:
-            join = torch.cuda.Event()
-            join.record(st)
-            main.wait_event(join)
+        # box decode + Fast NMS of every image in three launches (grid dimension = image)
+        L.check(lib.crog_ssg_detect_batched(cls.data_ptr(), box.data_ptr(), anchors.data_ptr(), B, N, nc, float(cfg.nms_score_thre),
+                                            float(cfg.nms_iou_thre), int(cfg.top_k), md, 0.3, keep.data_ptr(), boxes.data_ptr(),
+                                            det_n.data_ptr(), det_anchor.data_ptr(), det_class.data_ptr(), det_score.data_ptr(),
+                                            ws.data_ptr(), ws_bytes, s))
         counts = det_n.cpu().tolist()  # the one sync: output shapes are data dependent, as in the reference
         offs = [0]
         for n in counts:
@@ -426,24 +413,26 @@ def ssg_post_processing_batched(cfg, output_dict, ori_size=(480, 640)):
         hr = torch.empty((5, max(tot, 1), ori_h, ori_w), dtype=torch.float32, device=dev)
         lowres = torch.empty((max(tot, 1), 5, h, w), dtype=torch.float32, device=dev)
         qraw = torch.empty((max(tot, 1), ori_h, ori_w), dtype=torch.float32, device=dev)  # un-smoothed quality maps
-        plane = ori_h * ori_w
-        for b in range(B):
-            if counts[b] == 0:
-                continue
-            # detection stride of the map-major output = tot instances: image b fills instances [offs[b], offs[b] + n_b)
-            L.check(lib.crog_ssg_masks(protos[b].data_ptr(), h, w, npz, coef[b].data_ptr(), gco[b].data_ptr(), boxes[b].data_ptr(),
-                                       det_anchor[b].data_ptr(), det_n[b:].data_ptr(), counts[b], lowres[offs[b]:].data_ptr(),
-                                       hr.data_ptr() + offs[b] * plane * 4, qraw.data_ptr() + offs[b] * plane * 4, tot, ori_h, ori_w,
-                                       S, s))
+        if tot > 0:
+            # all instances of the batch in two launches: instance i = detection inst[1, i] of image inst[0, i]
+            inst = torch.from_numpy(np.stack([np.repeat(np.arange(B, dtype=np.int32), counts),
+                                              np.concatenate([np.arange(n, dtype=np.int32) for n in counts])])).to(dev)
+            L.check(lib.crog_ssg_masks_batched(protos.data_ptr(), h, w, npz, coef.data_ptr(), gco.data_ptr(), boxes.data_ptr(),
+                                               det_anchor.data_ptr(), N, md, inst[0].data_ptr(), inst[1].data_ptr(), tot,
+                                               lowres.data_ptr(), hr.data_ptr(), qraw.data_ptr(), ori_h, ori_w, S, s))
         if tot > 0:
             gaussian_batched(qraw[:tot], 2.0, out=hr[1, :tot])  # smoothed out of place into the quality plane
             _, npk, grasps = detect_grasps_batched(hr[1, :tot], hr[2, :tot], hr[3, :tot], hr[4, :tot], 5)
         else:
             npk = torch.zeros((0,), dtype=torch.int32, device=dev)
             grasps = torch.zeros((0, 5, 5), dtype=torch.float64, device=dev)
+        # per-sample views of batch-wide results (one gather for all boxes instead of one per image)
+        sel = det_anchor.long().clamp_(0, N - 1)  # entries past an image's count are unused
+        boxes_sel = torch.gather(boxes, 1, sel[..., None].expand(-1, -1, 4))
+        cls1 = det_class + 1
     out = []
     for b in range(B):
         n, o = counts[b], offs[b]
-        out.append({"n": n, "cls": det_class[b, :n] + 1, "boxes": boxes[b][det_anchor[b, :n].long()], "scores": det_score[b, :n],
+        out.append({"n": n, "cls": cls1[b, :n], "boxes": boxes_sel[b, :n], "scores": det_score[b, :n],
                     "hr": hr[:, o:o + n], "n_peaks": npk[o:o + n], "grasps": grasps[o:o + n]})
     return out

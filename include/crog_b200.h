@@ -287,6 +287,13 @@ int crog_ssg_fast_nms(const float* cls, const int32_t* keep, const float* boxes,
 int crog_ssg_detect(const float* cls, const float* box, const float* anchors, int32_t N, int32_t num_classes, float score_thr,
                     float iou_thr, int32_t top_k, int32_t max_det, float score_thr2, int32_t* keep, float* boxes,
                     int32_t* det_n, int32_t* det_anchor, int32_t* det_class, float* det_score, void* workspace, void* stream);
+/* crog_ssg_detect for B images in three launches: cls [B,N,nc], box [B,N,4], keep [B,N], boxes [B,N,4], det_n [B],
+ * det_anchor / det_class / det_score [B,max_det]; workspace = B slices of workspace_stride bytes (>= the per-image size,
+ * multiple of 16).  Per image identical to crog_ssg_detect. */
+int crog_ssg_detect_batched(const float* cls, const float* box, const float* anchors, int32_t B, int32_t N, int32_t num_classes,
+                            float score_thr, float iou_thr, int32_t top_k, int32_t max_det, float score_thr2, int32_t* keep,
+                            float* boxes, int32_t* det_n, int32_t* det_anchor, int32_t* det_class, float* det_score, void* workspace,
+                            int64_t workspace_stride, void* stream);
 /* Mask stage (grasp_eval.py:171-194): lowres[d][k] = crop(act_k(protos . coef_k(d))) for k = ins, qua, sin, cos, wid
  * (sigmoid on ins / qua / wid), [max_det, 5, h, w]; out[k][d] = bilinear resize to resize_to^2 (align_corners=False)
  * cropped to [out_h, out_w], map-major [5, out_det_stride, out_h, out_w] (out_det_stride <= 0: max_det; a larger stride
@@ -298,6 +305,13 @@ int crog_ssg_masks(const float* protos, int32_t h, int32_t w, int32_t num_protos
                    const float* boxes, const int32_t* det_anchor, const int32_t* det_n, int32_t max_det, float* lowres,
                    float* out, float* quality_raw, int32_t out_det_stride, int32_t out_h, int32_t out_w, int32_t resize_to,
                    void* stream);
+/* The same mask stage for ALL instances of a batch in two launches: instance i (of `total`) is detection inst_det[i] of
+ * image inst_image[i]; protos [B,h,w,np], coef [B,N,np], gcoef [B,N,4,np], boxes [B,N,4], det_anchor [B,max_det].
+ * lowres [total,5,h,w]; out map-major [5,total,out_h,out_w]; quality_raw [total,out_h,out_w] or NULL (as above). */
+int crog_ssg_masks_batched(const float* protos, int32_t h, int32_t w, int32_t num_protos, const float* coef, const float* gcoef,
+                           const float* boxes, const int32_t* det_anchor, int32_t N, int32_t max_det, const int32_t* inst_image,
+                           const int32_t* inst_det, int32_t total, float* lowres, float* out, float* quality_raw, int32_t out_h,
+                           int32_t out_w, int32_t resize_to, void* stream);
 /* skimage.filters.gaussian(map, sigma, preserve_range=True) of grasp_eval.py:198 = scipy.ndimage.gaussian_filter(mode='nearest'):
  * separable (rows first), float64 accumulation in scipy's tap order, float32 result per pass.  weights_host: the 2*radius+1
  * normalised float64 taps (HOST pointer; computed by the caller exactly as scipy does).  Planes smoothed:
