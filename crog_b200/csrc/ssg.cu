@@ -400,55 +400,81 @@ __global__ void __launch_bounds__(256) ssg_lowres_kernel(const float* __restrict
 // ------------------------------------------------------------------ F.interpolate(size=(S,S), bilinear, align_corners=False) + [:oh, :ow] crop
 // planes [P][h][w] -> [P][oh][ow]; planes whose bit is set in bin_mask (by plane % planes_per_det) are thresholded > 0.5.
 constexpr int BC_ROWS = 32;  // output rows per thread
-// A thread owns one output column and BC_ROWS consecutive rows.  The horizontal source indices / weights are computed once
-// per column, the vertical ones once per CTA (shared-memory table), and the two horizontally interpolated source rows
-// slide down the column: at scale 136 -> 640 a new source row (2 loads, 3 flops) is needed every ~4.7 output rows, so an
-// output costs ~10 instructions instead of ~35 (4 loads + full address / weight arithmetic per output: 2.9 ms for the
-// 3.1 GB of masks of a 64-image batch, 1.05 TB/s).
-__global__ void __launch_bounds__(256) bilinear_crop_kernel(const float* __restrict__ in, int h, int w, float* __restrict__ out, int oh,
-                                                            int ow, int S, const int* __restrict__ n_planes, int planes_per_det,
-                                                            uint32_t bin_mask, int det_stride, float* __restrict__ alt1) {
-  __shared__ int s_y0[BC_ROWS];
-  __shared__ float s_ly[BC_ROWS];
+constexpr int BC_WARPS = 8;  // row groups (warps) per CTA
+// A warp owns a 128-column x BC_ROWS-row block of one plane; a thread 4 consecutive output columns (one 16-byte store
+// per row).  The horizontal source indices / weights are computed once per column, the vertical ones once per warp
+// (shared-memory table), and the two horizontally interpolated source rows slide down the columns: at scale 136 -> 640 a
+// new source row (2 loads, 3 flops per column) is needed every ~4.7 output rows, so an output costs ~5 instructions
+// instead of ~35 (4 loads + full address / weight arithmetic per output: 2.9 ms for the 3.1 GB of masks of a 64-image
+// batch).
+__global__ void __launch_bounds__(32 * BC_WARPS) bilinear_crop_kernel(const float* __restrict__ in, int h, int w, float* __restrict__ out,
+                                                                      int oh, int ow, int S, const int* __restrict__ n_planes,
+                                                                      int planes_per_det, uint32_t bin_mask, int det_stride,
+                                                                      float* __restrict__ alt1) {
+  __shared__ int s_y0[BC_WARPS][BC_ROWS];
+  __shared__ float s_ly[BC_WARPS][BC_ROWS];
   const int pl = blockIdx.z;
   if (n_planes && pl >= *n_planes * planes_per_det) return;
+  const int lane = threadIdx.x, rg = threadIdx.y;
   const float sc_h = (float)h / (float)S, sc_w = (float)w / (float)S;
-  const int oyb = blockIdx.y * BC_ROWS;
-  if (threadIdx.x < BC_ROWS) {
-    const float sy = fmaxf(__fsub_rn(__fmul_rn(sc_h, (float)(oyb + (int)threadIdx.x) + 0.5f), 0.5f), 0.f);
+  const int oyb = (blockIdx.y * BC_WARPS + rg) * BC_ROWS;
+  if (oyb >= oh) return;  // warp-uniform
+  {
+    const float sy = fmaxf(__fsub_rn(__fmul_rn(sc_h, (float)(oyb + lane) + 0.5f), 0.5f), 0.f);
     const int y0 = min((int)sy, h - 1);
-    s_y0[threadIdx.x] = y0;
-    s_ly[threadIdx.x] = sy - y0;
+    s_y0[rg][lane] = y0;
+    s_ly[rg][lane] = sy - y0;
   }
-  __syncthreads();
-  const int ox = blockIdx.x * blockDim.x + threadIdx.x;
-  if (ox >= ow) return;
-  const float sx = fmaxf(__fsub_rn(__fmul_rn(sc_w, (float)ox + 0.5f), 0.5f), 0.f);
-  const int x0 = (int)sx, x1 = x0 + (x0 < w - 1);
-  const float lx = sx - x0, hx = 1.f - lx;
+  __syncwarp();
+  const int oxb = (blockIdx.x * 32 + lane) * 4;
+  if (oxb >= ow) return;
+  int x0[4], x1[4];
+  float lx[4], hx[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int ox = min(oxb + i, ow - 1);  // columns past the edge (ow % 4 != 0) repeat the last one and are not stored
+    const float sx = fmaxf(__fsub_rn(__fmul_rn(sc_w, (float)ox + 0.5f), 0.5f), 0.f);
+    x0[i] = (int)sx; x1[i] = x0[i] + (x0[i] < w - 1);
+    lx[i] = sx - x0[i]; hx[i] = 1.f - lx[i];
+  }
   const float* src = in + (long long)pl * h * w;
   const int d = pl / planes_per_det, k = pl % planes_per_det;
   const bool bin = (bin_mask >> k) & 1u;
   // output is map-major: [planes_per_det][det_stride detections][oh][ow], so each map type is one contiguous batch
-  float* dst = out + ((long long)k * det_stride + d) * oh * ow + ox;
-  if (alt1 != nullptr && k == 1) dst = alt1 + (long long)d * oh * ow + ox;  // plane 1 (raw quality) to its own [det][oh][ow] buffer
-  auto hrow = [&](int y) { return hx * __ldg(src + y * w + x0) + lx * __ldg(src + y * w + x1); };
+  float* dst = out + ((long long)k * det_stride + d) * oh * ow + oxb;
+  if (alt1 != nullptr && k == 1) dst = alt1 + (long long)d * oh * ow + oxb;  // plane 1 (raw quality) to its own [det][oh][ow] buffer
+  const bool vec = oxb + 4 <= ow && (ow & 3) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0;
   int cur = -2;
-  float top = 0.f, bot = 0.f;
+  float top[4] = {0.f, 0.f, 0.f, 0.f}, bot[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll 4
   for (int j = 0; j < BC_ROWS; ++j) {
     const int oy = oyb + j;
     if (oy >= oh) break;
-    const int y0 = s_y0[j];  // warp-uniform
+    const int y0 = s_y0[rg][j];  // warp-uniform
     if (y0 != cur) {
-      const bool last = y0 >= h - 1;
-      top = (y0 == cur + 1 && cur >= 0) ? bot : hrow(y0);
-      bot = last ? top : hrow(y0 + 1);
+      const bool reuse = y0 == cur + 1 && cur >= 0, last = y0 >= h - 1;
+      const float* r0 = src + y0 * w;
+      const float* r1 = r0 + (last ? 0 : w);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        top[i] = reuse ? bot[i] : hx[i] * __ldg(r0 + x0[i]) + lx[i] * __ldg(r0 + x1[i]);
+        bot[i] = last ? top[i] : hx[i] * __ldg(r1 + x0[i]) + lx[i] * __ldg(r1 + x1[i]);
+      }
       cur = y0;
     }
-    const float ly = s_ly[j], hy = 1.f - ly;
-    const float v = hy * top + ly * bot;
-    dst[(long long)oy * ow] = bin ? (v > 0.5f ? 1.f : 0.f) : v;
+    const float ly = s_ly[rg][j], hy = 1.f - ly;
+    float v[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      v[i] = hy * top[i] + ly * bot[i];
+      if (bin) v[i] = v[i] > 0.5f ? 1.f : 0.f;
+    }
+    float* o = dst + (long long)oy * ow;
+    if (vec) *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
+    else {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) if (oxb + i < ow) o[i] = v[i];
+    }
   }
 }
 
@@ -737,8 +763,8 @@ extern "C" int crog_ssg_masks(const float* protos, int32_t h, int32_t w, int32_t
   ssg_lowres_kernel<<<g1, 256, 5 * num_protos * sizeof(float), s>>>(protos, h, w, num_protos, coef, gcoef, boxes, det_anchor, det_n, lowres,
                                                                     nullptr, nullptr, 0, 0);
   CROG_LAUNCH_OK("ssg_lowres");
-  dim3 g2((out_w + 255) / 256, (out_h + BC_ROWS - 1) / BC_ROWS, max_det * 5);
-  bilinear_crop_kernel<<<g2, 256, 0, s>>>(lowres, h, w, out, out_h, out_w, resize_to, det_n, 5, 1u, out_det_stride, quality_raw);
+  dim3 g2((out_w + 127) / 128, (out_h + BC_ROWS * BC_WARPS - 1) / (BC_ROWS * BC_WARPS), max_det * 5);
+  bilinear_crop_kernel<<<g2, dim3(32, BC_WARPS), 0, s>>>(lowres, h, w, out, out_h, out_w, resize_to, det_n, 5, 1u, out_det_stride, quality_raw);
   CROG_LAUNCH_OK("ssg_resize");
   return CROG_OK;
 }
@@ -761,8 +787,8 @@ extern "C" int crog_ssg_masks_batched(const float* protos, int32_t h, int32_t w,
                                                                       lowres + (long long)i0 * 5 * h * w, inst_image + i0, inst_det + i0, N,
                                                                       max_det);
     CROG_LAUNCH_OK("ssg_lowres");
-    dim3 g2((out_w + 255) / 256, (out_h + BC_ROWS - 1) / BC_ROWS, n * 5);
-    bilinear_crop_kernel<<<g2, 256, 0, s>>>(lowres + (long long)i0 * 5 * h * w, h, w, out + i0 * plane, out_h, out_w, resize_to, nullptr, 5,
+    dim3 g2((out_w + 127) / 128, (out_h + BC_ROWS * BC_WARPS - 1) / (BC_ROWS * BC_WARPS), n * 5);
+    bilinear_crop_kernel<<<g2, dim3(32, BC_WARPS), 0, s>>>(lowres + (long long)i0 * 5 * h * w, h, w, out + i0 * plane, out_h, out_w, resize_to, nullptr, 5,
                                             1u, total, quality_raw ? quality_raw + i0 * plane : nullptr);
     CROG_LAUNCH_OK("ssg_resize");
   }
