@@ -16,6 +16,53 @@ __device__ __forceinline__ long long prow(int b, int y, int x, int H, int W, int
 // ------------------------------------------------------------------ stem: 7x7 / stride 2 / pad 3 patches -> [rows, Kp]
 // K index = (ky*7 + kx)*cin + c (matches the [Cout, ky, kx, Cin] weight packing), zero padded to Kp.
 // One thread per (output pixel, 8-wide K group), K fastest so every warp store is a contiguous run of 16-byte vectors.
+// Tiled form (compile-time channel count): a CTA stages the 7 input rows x (2 * 64 + 5) columns x CIN planes behind 64
+// consecutive output pixels of one output row in shared memory (coalesced plane reads), then writes the patch rows with
+// 16-byte stores.  The index arithmetic is constant divisions only and every input value is read from HBM / L2 once per
+// CTA instead of ~12 times through L1 (the generic kernel below: 3.8 ms for 64 x 544 x 544, a quarter of the SSG forward).
+constexpr int S7_PX = 64, S7_SW = 2 * S7_PX + 5;
+template <typename T, int CIN>
+__global__ void __launch_bounds__(256) stem7_patches_tiled_kernel(const float* __restrict__ rgb, const float* __restrict__ depth, int B,
+                                                                  int H, int W, int Kp, T* __restrict__ out) {
+  __shared__ float s_in[7 * CIN + 1][S7_SW + 1];  // last row: zeros (the padding columns of a patch row read it)
+  const int OH = (H + 6 - 7) / 2 + 1, OW = (W + 6 - 7) / 2 + 1;
+  const int segs = (OW + S7_PX - 1) / S7_PX;
+  const int seg = blockIdx.x % segs, oy = (blockIdx.x / segs) % OH, b = blockIdx.x / (segs * OH);
+  const int ox0 = seg * S7_PX, ix0 = 2 * ox0 - 3, iy0 = 2 * oy - 3;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int r = warp; r < 7 * CIN; r += 8) {  // a warp stages whole rows: no index divisions, coalesced plane reads
+    const int c = r % CIN, ky = r / CIN, iy = iy0 + ky;
+    const bool rowok = iy >= 0 && iy < H;
+    const float* src = c < 3 ? rgb + ((long long)(b * 3 + c) * H + iy) * W : depth + ((long long)b * H + iy) * W;
+    for (int col = lane; col < S7_SW; col += 32) {
+      const int ix = ix0 + col;
+      s_in[r][col] = (rowok && ix >= 0 && ix < W) ? __ldg(src + ix) : 0.f;
+    }
+  }
+  for (int col = threadIdx.x; col < S7_SW + 1; col += 256) s_in[7 * CIN][col] = 0.f;
+  __syncthreads();
+  // thread = one 8-wide k group (its eight source offsets are computed once) x every 8th pixel of the segment
+  const int groups = Kp / 8;
+  T* orow = out + ((long long)(b * OH + oy) * OW + ox0) * Kp;
+  const int npx = min(S7_PX, OW - ox0);
+  for (int gk = lane; gk < groups; gk += 32) {
+    int off[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int k = gk * 8 + j;
+      const int c = k % CIN, t = k / CIN, ky = t / 7, kx = t % 7;
+      off[j] = k < 49 * CIN ? (ky * CIN + c) * (S7_SW + 1) + kx : 7 * CIN * (S7_SW + 1);
+    }
+    const float* base = &s_in[0][0];
+    for (int p = warp; p < npx; p += 8) {
+      float v[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = base[off[j] + 2 * p];
+      store8(orow + (long long)p * Kp + gk * 8, v);
+    }
+  }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256) stem7_patches_kernel(const float* __restrict__ rgb, const float* __restrict__ depth, int B,
                                                             int H, int W, int cin, int Kp, T* __restrict__ out) {
@@ -639,6 +686,19 @@ extern "C" int crog_stem7_patches(const float* rgb, const float* depth, int32_t 
   if (total == 0) return CROG_OK;
   long long g = (total + 255) / 256;
   if (g > 148 * 64) g = 148 * 64;
+  {
+    const int OH = (H - 1) / 2 + 1, OW = (W - 1) / 2 + 1;
+    const long long ctas = (long long)B * OH * ((OW + S7_PX - 1) / S7_PX);
+    if (ctas <= 0x7fffffffLL && !getenv("CROG_STEM7_GENERIC")) {
+      cudaStream_t s = (cudaStream_t)stream;
+#define S7(T, C) stem7_patches_tiled_kernel<T, C><<<(int)ctas, 256, 0, s>>>(rgb, depth, B, H, W, Kp, (T*)out)
+      if (out_dtype == CROG_F32) { if (cin == 4) S7(float, 4); else S7(float, 3); }
+      else { if (cin == 4) S7(bf16, 4); else S7(bf16, 3); }
+#undef S7
+      CROG_LAUNCH_OK("stem7_patches");
+      return CROG_OK;
+    }
+  }
   if (out_dtype == CROG_F32) stem7_patches_kernel<float><<<(int)g, 256, 0, (cudaStream_t)stream>>>(rgb, depth, B, H, W, cin, Kp, (float*)out);
   else stem7_patches_kernel<bf16><<<(int)g, 256, 0, (cudaStream_t)stream>>>(rgb, depth, B, H, W, cin, Kp, (bf16*)out);
   CROG_LAUNCH_OK("stem7_patches");

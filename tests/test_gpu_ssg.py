@@ -30,17 +30,21 @@ def _rand(*shape, seed=0):
 
 
 @pytest.mark.parametrize("dt", [torch.float32, BF])
-def test_stem7_patches(dt):
-    B, S, Kp = 2, 36, 256
+@pytest.mark.parametrize("S,cin,Kp", [(36, 4, 256), (150, 4, 256), (150, 3, 192), (274, 4, 200)])
+def test_stem7_patches(dt, S, cin, Kp):
+    """7x7 / stride 2 / pad 3 patch rows, (tap, channel) order, zero-padded to Kp; several 64-pixel row segments, a ragged
+    last segment, and the 3-channel (no depth) form."""
+    B, O = 2, (S - 1) // 2 + 1
     rgb, depth = torch.rand(B, 3, S, S, device=DEV), torch.rand(B, 1, S, S, device=DEV)
-    out = torch.full((B * 18 * 18, Kp), 7.0, device=DEV, dtype=dt)
-    L.check(L.lib().crog_stem7_patches(rgb.data_ptr(), depth.data_ptr(), B, S, S, 4, Kp, out.data_ptr(), L.dtype_code(dt), L.stream_ptr()))
+    out = torch.full((B * O * O, Kp), 7.0, device=DEV, dtype=dt)
+    L.check(L.lib().crog_stem7_patches(rgb.data_ptr(), depth.data_ptr() if cin == 4 else None, B, S, S, cin, Kp, out.data_ptr(),
+                                       L.dtype_code(dt), L.stream_ptr()))
     torch.cuda.synchronize()
-    img = torch.cat([rgb, depth], 1).to(dt).float()
-    cols = F.unfold(img, 7, padding=3, stride=2)  # [B, 4*49, L], channel-major rows
-    want = cols.view(B, 4, 49, -1).permute(0, 3, 2, 1).reshape(B * 18 * 18, 196)  # -> (tap, channel)
-    assert torch.equal(out[:, :196].float(), want)
-    assert out[:, 196:].abs().max() == 0
+    img = (torch.cat([rgb, depth], 1) if cin == 4 else rgb).to(dt).float()
+    cols = F.unfold(img, 7, padding=3, stride=2)  # [B, cin*49, L], channel-major rows
+    want = cols.view(B, cin, 49, -1).permute(0, 3, 2, 1).reshape(B * O * O, 49 * cin)  # -> (tap, channel)
+    assert torch.equal(out[:, :49 * cin].float(), want)
+    assert out[:, 49 * cin:].abs().max() == 0
 
 
 @pytest.mark.parametrize("dt", [torch.float32, BF])
