@@ -658,7 +658,10 @@ __global__ void angle_map_kernel(const float* __restrict__ s, const float* __res
 }
 
 // ------------------------------------------------------------------ Jaccard
-constexpr int JT = 128;  // threads per sample CTA
+#ifndef CROG_JT
+#define CROG_JT 128
+#endif
+constexpr int JT = CROG_JT;  // threads per sample CTA (>= MAXK, multiple of 32)
 #ifndef JACCARD_CTAS_PER_SM
 #define JACCARD_CTAS_PER_SM 8  // latency / barrier bound kernel: more resident samples per SM (64 registers, 24.5 KB smem each)
 #endif
@@ -674,8 +677,19 @@ __device__ __forceinline__ int block_sum(int v, int* s_red) {
   return t;
 }
 
+#ifdef CROG_JAC_NOINLINE_RECT
+__device__ __noinline__ void make_rect_nl(const double* rect5, TgRect* R) { tg_make_rect(rect5, R); }
+#else
+#define make_rect_nl tg_make_rect
+#endif
+#ifdef CROG_JAC_NOINLINE_SLOW
+#define JAC_SLOW_ATTR __noinline__
+#else
+#define JAC_SLOW_ATTR
+#endif
+
 // pixel count of one rectangle / of the intersection of two, exact for any size (slow path)
-__device__ int slow_count(const TgRect* A, const TgRect* Bq, int* s_red) {
+__device__ JAC_SLOW_ATTR int slow_count(const TgRect* A, const TgRect* Bq, int* s_red) {
   const int x0 = Bq ? max(A->x0, Bq->x0) : A->x0, x1 = Bq ? min(A->x1, Bq->x1) : A->x1;
   const int y0 = Bq ? max(A->y0, Bq->y0) : A->y0, y1 = Bq ? min(A->y1, Bq->y1) : A->y1;
   int cnt = 0;
@@ -731,7 +745,7 @@ __global__ void __launch_bounds__(JT, JACCARD_CTAS_PER_SM) jaccard_kernel(const 
     return;
   }
   if (tid == 0) { s_j1 = 0; s_jk = 0; s_slow = 0; }
-  if (tid < n) tg_make_rect(P + tid * 5, &s_pred[tid]);
+  if (tid < n) make_rect_nl(P + tid * 5, &s_pred[tid]);
   __syncthreads();
   int all_fast = 1;
   for (int k = 0; k < n; ++k) all_fast &= s_pred[k].fast;
@@ -741,12 +755,14 @@ __global__ void __launch_bounds__(JT, JACCARD_CTAS_PER_SM) jaccard_kernel(const 
     const TgRect* R = &s_pred[k];
     if (!R->fast) continue;
     int cnt = 0;
-    const int X = R->x0 + tid;
-    uint32_t* row = s_mask + ((long long)k * TG_MAXROWS + tid) * TG_WORDS;
-    if (X <= R->x1) {
-      tg_row_mask(R, X, row);
+    for (int r = tid; r < TG_MAXROWS; r += JT) {
+      const int X = R->x0 + r;
+      uint32_t* row = s_mask + ((long long)k * TG_MAXROWS + r) * TG_WORDS;
+      if (X <= R->x1) {
+        tg_row_mask(R, X, row);
 #pragma unroll
-      for (int w = 0; w < TG_WORDS; ++w) cnt += __popc(row[w]);
+        for (int w = 0; w < TG_WORDS; ++w) cnt += __popc(row[w]);
+      }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
@@ -788,7 +804,7 @@ __global__ void __launch_bounds__(JT, JACCARD_CTAS_PER_SM) jaccard_kernel(const 
         }
         if (pass) {
           TgRect Gr;
-          tg_make_rect(g, &Gr);
+          make_rect_nl(g, &Gr);
           if (!Gr.fast) {
             s_slow = 1;  // oversized GT (only possible with edit_gt == 0): handled by the CTA-synchronous path below
           } else {
@@ -866,7 +882,7 @@ __global__ void __launch_bounds__(JT, JACCARD_CTAS_PER_SM) jaccard_kernel(const 
     }
     if (!pass) continue;  // block-uniform
     __syncthreads();
-    if (tid == 0) tg_make_rect(g, &s_gt);
+    if (tid == 0) make_rect_nl(g, &s_gt);
     __syncthreads();
     const TgRect* Gr = &s_gt;
     if (all_fast && Gr->fast) continue;  // already handled by the warp path (block-uniform)

@@ -12,7 +12,7 @@ B = 64
 rgb, depth = synth.make_ssg_inputs(B, cfg.img_size)
 model({"rgb": rgb.to(dev), "depth": depth.to(dev)}); torch.cuda.synchronize()
 plan = model.plan_for(B)
-durs = bench._op_durations(plan, reps=3)
+durs = bench._op_durations(plan, reps=3) * 1e3  # ms -> us
 rows = sorted(zip(durs, plan.op_names), reverse=True)
 tot = float(durs.sum())
 print("total %.2f ms, %d ops" % (tot / 1e3, len(durs)))
