@@ -30,6 +30,17 @@ __device__ __forceinline__ int sat_int(double v) {  // saturate_cast<int>(double
   return __double2int_rn(v);
 }
 __device__ __forceinline__ int sat_short(int v) { return v < -32768 ? -32768 : (v > 32767 ? 32767 : v); }
+// c + a.lo16 * b.byte0 + a.hi16 * b.byte1 (lo) / ... byte2, byte3 (hi): signed 16-bit halves times UNSIGNED bytes
+__device__ __forceinline__ int dp2a_lo_su(int a, uint32_t b, int c) {
+  int d;
+  asm("dp2a.lo.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+  return d;
+}
+__device__ __forceinline__ int dp2a_hi_su(int a, uint32_t b, int c) {
+  int d;
+  asm("dp2a.hi.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+  return d;
+}
 
 // interpolateCubic(x = phase / 32, coeffs) in float32 without contraction
 __device__ __forceinline__ void cubic_coeffs(int phase, float (&c)[4]) {
@@ -63,6 +74,31 @@ __device__ __forceinline__ SrcCoord src_coord(const double* __restrict__ M, int 
   return c;
 }
 
+// The same coordinates for a 32 x 8 pixel block: OpenCV itself computes adelta / bdelta once per destination column and
+// X0 / Y0 once per row; a CTA does the 40 float64 evaluations once and a pixel adds two table entries.
+struct BlockCoords { int ad[32], bd[32], x0[8], y0[8]; };
+__device__ __forceinline__ void block_coords_fill(BlockCoords* t, const double* __restrict__ M, int xb, int yb, int tid) {
+  if (tid < 32) {
+    const double x = (double)(xb + tid);
+    t->ad[tid] = sat_int(__dmul_rn(__dmul_rn(M[0], x), 1024.0));
+    t->bd[tid] = sat_int(__dmul_rn(__dmul_rn(M[3], x), 1024.0));
+  } else if (tid < 40) {
+    const double y = (double)(yb + tid - 32);
+    t->x0[tid - 32] = sat_int(__dmul_rn(__dadd_rn(__dmul_rn(M[1], y), M[2]), 1024.0)) + ROUND_DELTA;
+    t->y0[tid - 32] = sat_int(__dmul_rn(__dadd_rn(__dmul_rn(M[4], y), M[5]), 1024.0)) + ROUND_DELTA;
+  }
+}
+__device__ __forceinline__ SrcCoord block_coord(const BlockCoords* t, int tx, int ty) {
+  const int X = (int)((unsigned)t->x0[ty] + (unsigned)t->ad[tx]) >> (AB_BITS - INTER_BITS);
+  const int Y = (int)((unsigned)t->y0[ty] + (unsigned)t->bd[tx]) >> (AB_BITS - INTER_BITS);
+  SrcCoord c;
+  c.sx = sat_short(X >> INTER_BITS) - 1;
+  c.sy = sat_short(Y >> INTER_BITS) - 1;
+  c.ax = X & (TAB - 1);
+  c.ay = Y & (TAB - 1);
+  return c;
+}
+
 // Second form of the float warp: 32 x 8 pixel blocks (no index division), the 32 x 4 table of cubic coefficients built once
 // per CTA in shared memory (a lookup instead of ~50 non-contractable flops per pixel), the 16 weight products of a pixel
 // computed once for all planes (they are OpenCV's table entries, so their rounding is unchanged), plane-to-plane pointer
@@ -71,17 +107,19 @@ __global__ void __launch_bounds__(256, 4) warp_cubic_f32_v2_kernel(const float* 
                                                                    const double* __restrict__ minv, float* __restrict__ dst, int h,
                                                                    int w, float cv) {
   __shared__ float s_tab[TAB][4];
+  __shared__ BlockCoords s_bc;
   const int tid = threadIdx.y * 32 + threadIdx.x;
+  const int b = blockIdx.z;
   if (tid < TAB) {
     float c4[4];
     cubic_coeffs(tid, c4);
     s_tab[tid][0] = c4[0]; s_tab[tid][1] = c4[1]; s_tab[tid][2] = c4[2]; s_tab[tid][3] = c4[3];
   }
+  block_coords_fill(&s_bc, minv + b * 6, blockIdx.x * 32, blockIdx.y * 8, 255 - tid);  // the other end of the CTA
   __syncthreads();
-  const int b = blockIdx.z;
   const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
   if (x >= w || y >= h) return;
-  const SrcCoord c = src_coord(minv + b * 6, x, y);
+  const SrcCoord c = block_coord(&s_bc, threadIdx.x, threadIdx.y);
   const long long splane = (long long)Hs * Ws, dplane = (long long)h * w;
   const long long sps = (long long)B * splane, dps = (long long)B * dplane;
   float* D = dst + (long long)b * dplane + (long long)y * w + x;
@@ -237,30 +275,27 @@ __global__ void __launch_bounds__(256) preprocess_u8_kernel(const short* __restr
   // the result pixel is an integer 0..255: (v / 255 - mean) / std has 256 possible values per channel, computed once per
   // CTA with the reference's two IEEE divisions instead of six divisions per pixel
   __shared__ float lut[3][256];
+  __shared__ BlockCoords s_bc;
+  const int tid = threadIdx.y * 32 + threadIdx.x, b = blockIdx.z;
   {
-    const float v = __fdiv_rn((float)threadIdx.x, 255.f);
-    lut[0][threadIdx.x] = __fdiv_rn(__fsub_rn(v, m0), s0);
-    lut[1][threadIdx.x] = __fdiv_rn(__fsub_rn(v, m1), s1);
-    lut[2][threadIdx.x] = __fdiv_rn(__fsub_rn(v, m2), s2);
+    const float v = __fdiv_rn((float)tid, 255.f);
+    lut[0][tid] = __fdiv_rn(__fsub_rn(v, m0), s0);
+    lut[1][tid] = __fdiv_rn(__fsub_rn(v, m1), s1);
+    lut[2][tid] = __fdiv_rn(__fsub_rn(v, m2), s2);
   }
+  block_coords_fill(&s_bc, minv + b * 6, blockIdx.x * 32, blockIdx.y * 8, tid);
   __syncthreads();
-  const int b = blockIdx.y;
-  const int p = blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= Sh * Sw) return;
-  const int y = p / Sw, x = p - y * Sw;
-  const SrcCoord c = src_coord(minv + b * 6, x, y);
+  const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
+  if (x >= Sw || y >= Sh) return;
+  const int p = y * Sw + x;
+  const SrcCoord c = block_coord(&s_bc, threadIdx.x, threadIdx.y);
   const int cval[3] = {cv0, cv1, cv2};
   int res[3] = {cv0, cv1, cv2};
   const bool outside = c.sx >= Wo || c.sx + 4 <= 0 || c.sy >= Ho || c.sy + 4 <= 0;
   if (!outside) {
-    int wt[16];
-    {
-      const int4* e = reinterpret_cast<const int4*>(wtab + (c.ay * TAB + c.ax) * 16);
-      const int4 e0 = __ldg(e), e1 = __ldg(e + 1);
-      const int q[8] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w};
-#pragma unroll
-      for (int k = 0; k < 8; ++k) { wt[2 * k] = (int)(short)(q[k] & 0xffff); wt[2 * k + 1] = q[k] >> 16; }
-    }
+    const int4* e = reinterpret_cast<const int4*>(wtab + (c.ay * TAB + c.ax) * 16);
+    const int4 e0 = __ldg(e), e1 = __ldg(e + 1);
+    const int q[8] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w};  // the 16 taps as (even, odd) 16-bit pairs
     int acc[3] = {cv0 * COEF_SCALE, cv1 * COEF_SCALE, cv2 * COEF_SCALE};
     const uint8_t* S = img + (long long)b * Ho * Wo * 3;
     // Interior footprint (the common case): the 4 pixels x 3 channels of a footprint row are 12 contiguous bytes.  They are
@@ -271,6 +306,13 @@ __global__ void __launch_bounds__(256) preprocess_u8_kernel(const short* __restr
     const bool fast = c.sx >= 0 && c.sx + 3 < Wo && c.sy >= 0 && c.sy + 3 < Ho && (reinterpret_cast<uintptr_t>(img) & 3) == 0 &&
                       ((off00 + 3LL * 3 * Wo) & ~3LL) + 16 <= total_bytes;
     if (fast) {
+      // the weight table stores the taps as 16-bit pairs, which is the A operand of dp2a (two 16-bit x 8-bit products
+      // per instruction): the row's bytes are regrouped per channel with two byte permutes, and a channel's four taps
+      // are two dp2a.  sum(r * w) - cv * sum(w) + cv * SCALE is the same integer as sum((r - cv) * w) + cv * SCALE.
+      int sw = 0;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) sw = dp2a_lo_su(q[k], 0x0101u, sw);
+      int a0 = cv0 * (COEF_SCALE - sw), a1 = cv1 * (COEF_SCALE - sw), a2 = cv2 * (COEF_SCALE - sw);
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const long long off = off00 + (long long)i * Wo * 3;
@@ -279,25 +321,30 @@ __global__ void __launch_bounds__(256) preprocess_u8_kernel(const short* __restr
         const uint32_t sh = (uint32_t)(off & 3) * 8u;
         const uint32_t v0 = __funnelshift_r(w0, w1, sh), v1 = __funnelshift_r(w1, w2, sh), v2 = __funnelshift_r(w2, w3, sh);
         // bytes: v0 = R0 G0 B0 R1, v1 = G1 B1 R2 G2, v2 = B2 R3 G3 B3
-        const int r0 = v0 & 255, g0 = (v0 >> 8) & 255, b0 = (v0 >> 16) & 255, r1 = v0 >> 24;
-        const int g1 = v1 & 255, b1 = (v1 >> 8) & 255, r2 = (v1 >> 16) & 255, g2 = v1 >> 24;
-        const int b2 = v2 & 255, r3 = (v2 >> 8) & 255, g3 = (v2 >> 16) & 255, b3 = v2 >> 24;
-        acc[0] += (r0 - cv0) * wt[i * 4] + (r1 - cv0) * wt[i * 4 + 1] + (r2 - cv0) * wt[i * 4 + 2] + (r3 - cv0) * wt[i * 4 + 3];
-        acc[1] += (g0 - cv1) * wt[i * 4] + (g1 - cv1) * wt[i * 4 + 1] + (g2 - cv1) * wt[i * 4 + 2] + (g3 - cv1) * wt[i * 4 + 3];
-        acc[2] += (b0 - cv2) * wt[i * 4] + (b1 - cv2) * wt[i * 4 + 1] + (b2 - cv2) * wt[i * 4 + 2] + (b3 - cv2) * wt[i * 4 + 3];
+        const uint32_t rr = __byte_perm(__byte_perm(v0, v1, 0x0630), v2, 0x5210);  // R0 R1 R2 R3
+        const uint32_t gg = __byte_perm(__byte_perm(v0, v1, 0x0741), v2, 0x6210);  // G0 G1 G2 G3
+        const uint32_t bb = __byte_perm(__byte_perm(v0, v1, 0x0052), v2, 0x7410);  // B0 B1 B2 B3
+        a0 = dp2a_hi_su(q[2 * i + 1], rr, dp2a_lo_su(q[2 * i], rr, a0));
+        a1 = dp2a_hi_su(q[2 * i + 1], gg, dp2a_lo_su(q[2 * i], gg, a1));
+        a2 = dp2a_hi_su(q[2 * i + 1], bb, dp2a_lo_su(q[2 * i], bb, a2));
       }
-    } else
+      acc[0] = a0; acc[1] = a1; acc[2] = a2;
+    } else {
+      int wt[16];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int yy = c.sy + i;
-      if (yy < 0 || yy >= Ho) continue;
+      for (int k = 0; k < 8; ++k) { wt[2 * k] = (int)(short)(q[k] & 0xffff); wt[2 * k + 1] = q[k] >> 16; }
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int xx = c.sx + j;
-        if (xx < 0 || xx >= Wo) continue;
-        const uint8_t* px = S + ((long long)yy * Wo + xx) * 3;
+      for (int i = 0; i < 4; ++i) {
+        const int yy = c.sy + i;
+        if (yy < 0 || yy >= Ho) continue;
 #pragma unroll
-        for (int ch = 0; ch < 3; ++ch) acc[ch] += ((int)__ldg(px + ch) - cval[ch]) * wt[i * 4 + j];
+        for (int j = 0; j < 4; ++j) {
+          const int xx = c.sx + j;
+          if (xx < 0 || xx >= Wo) continue;
+          const uint8_t* px = S + ((long long)yy * Wo + xx) * 3;
+#pragma unroll
+          for (int ch = 0; ch < 3; ++ch) acc[ch] += ((int)__ldg(px + ch) - cval[ch]) * wt[i * 4 + j];
+        }
       }
     }
 #pragma unroll
@@ -369,8 +416,9 @@ extern "C" int crog_preprocess_u8(const uint8_t* img, int32_t B, int32_t Ho, int
   }
   cubic_table_i16_kernel<<<(TAB * TAB + 255) / 256, 256, 0, (cudaStream_t)stream>>>((short*)workspace);
   CROG_LAUNCH_OK("cubic_table_i16");
-  dim3 grid((unsigned)(((long long)Sh * Sw + 255) / 256), (unsigned)B);
-  preprocess_u8_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const short*)workspace, img, B, Ho, Wo, minv, out, Sh, Sw, cv[0], cv[1], cv[2], mean[0],
+  CROG_REQUIRE((Sh + 7) / 8 <= 65535, CROG_E_BADSHAPE, "preprocess: output too tall");
+  dim3 grid((unsigned)((Sw + 31) / 32), (unsigned)((Sh + 7) / 8), (unsigned)B);
+  preprocess_u8_kernel<<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>((const short*)workspace, img, B, Ho, Wo, minv, out, Sh, Sw, cv[0], cv[1], cv[2], mean[0],
                                                                mean[1], mean[2], std_[0], std_[1], std_[2],
                                                                (long long)B * Ho * Wo * 3);
   CROG_LAUNCH_OK("preprocess_u8");
