@@ -163,7 +163,7 @@ __global__ void __launch_bounds__(256, 2) peak_scan_generic_kernel(const float* 
   const int c0 = warp * STRIP + (lane - 1) * 4;  // may be negative (lane 0 of warp 0) or >= W
   const bool owner = lane >= 1 && lane <= 30;
   const int y0 = band * BAND, y1 = min(y0 + BAND, H);
-  const bool vec = (W % 4 == 0) && c0 >= 0 && c0 + 3 < W;
+  const bool vec = (W % 4 == 0) && c0 >= 0 && c0 + 3 < W && (reinterpret_cast<uintptr_t>(q) & 15) == 0;
   const float NEG = -INFINITY;
 
   auto load_row = [&](int r) -> float4 {
@@ -932,7 +932,7 @@ extern "C" int crog_detect_grasps(const float* q, const float* sin_m, const floa
   CROG_REQUIRE(K >= 1 && K <= MAXK, CROG_E_BADSHAPE, "detect_grasps: 1 <= num_grasps <= %d", MAXK);
   CROG_REQUIRE(H >= 1 && W >= 1 && W <= 8 * STRIP && (long long)H * W < (1LL << 31), CROG_E_BADSHAPE, "detect_grasps: map %dx%d unsupported", H, W);
   CROG_REQUIRE(B <= 65535, CROG_E_BADSHAPE, "detect_grasps: at most 65535 maps per call");
-  CROG_REQUIRE(aligned16(q) && aligned16(workspace), CROG_E_BADALIGN, "detect_grasps: 16B alignment");
+  CROG_REQUIRE(aligned16(workspace), CROG_E_BADALIGN, "detect_grasps: the workspace must be 16B aligned");
   if (B == 0) return CROG_OK;
   int nb, nw, band;
   scan_geometry(B, H, W, &nb, &nw, &band);
@@ -958,7 +958,9 @@ extern "C" int crog_detect_grasps(const float* q, const float* sin_m, const floa
   static const int tsel_env = getenv("CROG_SCAN_TSEL") ? atoi(getenv("CROG_SCAN_TSEL")) : 0;
   const int tsel = tsel_env > 0 ? max(1, min(tsel_env, TSEL)) : TSEL;
   static const int occ_env = getenv("CROG_SCAN_OCC") ? atoi(getenv("CROG_SCAN_OCC")) : 0;
-  if (W % 4 == 0 && (long long)H * W >= 2 && !getenv("CROG_SCAN_GENERIC")) {
+  // the bulk-copy staged scan needs 16-byte aligned rows (W % 4 == 0 and an aligned base); anything else - odd widths, a
+  // plane of a larger tensor that starts at an odd offset - takes the generic kernel
+  if (W % 4 == 0 && aligned16(q) && (long long)H * W >= 2 && !getenv("CROG_SCAN_GENERIC")) {
     if (occ_env != 3) peak_scan_kernel<2><<<dim3(nb, B), (nw + 1) * 32, smem_fast, s>>>(q, H, W, threshold, nw, band, tsel, K + 1, ws);
     else peak_scan_kernel<3><<<dim3(nb, B), (nw + 1) * 32, smem_fast, s>>>(q, H, W, threshold, nw, band, tsel, K + 1, ws);
   }

@@ -237,7 +237,8 @@ int crog_sigmoid_bicubic(const float* in, float* out, int32_t NP, int32_t B, int
  * threshold_abs, num_peaks=K) + angle/width gather) batched over B maps of H x W fp32.
  *   peaks  [B,K,2] int32 (row, col), -1 padded;  n_peaks [B] int32
  *   grasps [B,K,5] float64 rows [x, y, width*100, 20, angle_deg]
- * workspace: crog_detect_workspace_bytes(B,H,W,K) bytes. */
+ * workspace: crog_detect_workspace_bytes(B,H,W,K) bytes, 16-byte aligned.  Maps with W % 4 == 0 and a 16-byte aligned base are
+ * streamed by the bulk-copy staged scan; any other width / alignment takes the generic scan kernel (same results). */
 int64_t crog_detect_workspace_bytes(int32_t B, int32_t H, int32_t W, int32_t K);
 int crog_detect_grasps(const float* q, const float* sin_m, const float* cos_m, const float* wid, int32_t B,
                        int32_t H, int32_t W, int32_t K, float threshold, int32_t* peaks, int32_t* n_peaks,

@@ -290,6 +290,30 @@ def test_sigmoid_bicubic():
 
 
 # ------------------------------------------------------------------ tail: bit-exact against the oracle
+def test_detect_grasps_unaligned_maps_and_odd_widths():
+    """Maps that are planes of a larger tensor at an odd element offset, and widths that are no multiple of 4, take the
+    generic scan kernel (the bulk-copy staged one needs 16-byte aligned rows): same peaks as the oracle."""
+    from crog_b200.utils import grasp_eval as GE
+    from oracle import grasp_tail_c as TC
+
+    for H, W, off in ((48, 64, 1), (37, 53, 0), (37, 53, 3)):
+        q, s, c, w = synth.make_tail_maps(3, "blobs", seed=31 + off, size=64)
+        q, s, c, w = [np.ascontiguousarray(a[:, :H, :W]) for a in (q, s, c, w)]
+        dev = []
+        for a in (q, s, c, w):
+            buf = torch.zeros(a.size + 8, device=DEV)
+            view = buf[off:off + a.size].view(a.shape)
+            view.copy_(torch.from_numpy(a))
+            dev.append(view)
+        assert off == 0 or dev[0].data_ptr() % 16 != 0
+        peaks, n, grasps = GE.detect_grasps_batched(*dev, 5)
+        torch.cuda.synchronize()
+        for b in range(3):
+            g_ref, rc_ref = TC.detect_grasps(q[b], s[b], c[b], w[b], 5)
+            assert int(n[b]) == len(rc_ref)
+            assert np.array_equal(peaks[b, :int(n[b])].cpu().numpy(), rc_ref.astype(np.int32))
+
+
 def _check_detect(q, s, c, w, K):
     from crog_b200.utils import grasp_eval as GE
     from oracle import grasp_tail_c as TC

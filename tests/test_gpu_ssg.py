@@ -176,6 +176,26 @@ def test_gaussian_bit_exact():
         assert np.array_equal(got[i], O.gaussian_f32(maps[i], 2.0))
 
 
+@pytest.mark.parametrize("H,W", [(97, 133), (33, 7), (5, 300), (64, 128)])
+def test_gaussian_forms_bit_identical(H, W):
+    """One-kernel form (out of place), two-pass form (in place, through the intermediate buffer) and the oracle agree bit
+    for bit on ragged sizes: maps narrower than the 17-tap window, widths that are no multiple of the 8-column groups,
+    heights that are no multiple of the 32-row tiles."""
+    from crog_b200.utils import grasp_eval as GE
+    from oracle import ssg_forward as O
+
+    rng = np.random.default_rng(H * 1000 + W)
+    maps = rng.random((3, H, W), dtype=np.float32)
+    d = torch.from_numpy(maps).cuda()
+    fused = GE.gaussian_batched(d, 2.0)
+    work = d.clone()
+    GE.gaussian_batched(work, 2.0, out=work)  # in place: the two-pass kernels
+    torch.cuda.synchronize()
+    assert torch.equal(fused, work)
+    for i in range(3):
+        assert np.array_equal(fused[i].cpu().numpy(), O.gaussian_f32(maps[i], 2.0))
+
+
 def test_fast_nms_wrapper_matches_oracle():
     from crog_b200.utils import grasp_eval as GE
     from oracle import ssg_forward as O
@@ -229,6 +249,25 @@ def test_post_processing_matches_oracle_and_golden():
     # and the decoded grasp positions agree with the reference's on this fixture
     for a, b in zip(got["grasps_top5"], ref["grasps_top5"]):
         assert [(r[0], r[1]) for r in a] == [(r[0], r[1]) for r in b]
+
+
+def test_post_processing_odd_original_size():
+    """Mask assembly at an original size whose width is no multiple of 4 (scalar stores, ragged last column group) and whose
+    height is no multiple of the 32-row blocks: same bars against the oracle as at 480 x 640."""
+    from crog_b200.utils import grasp_eval as GE
+    from oracle import ssg_forward as O
+
+    cfg = synth.ssg_cfg()
+    od = synth.make_ssg_output_dict(cfg, n_confident=5, seed=12)
+    dd = {"ori_size": (241, 323)}
+    ref = O.ssg_post_processing(cfg, od, dd, keep=True)
+    got = GE.ssg_post_processing(cfg, {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in od.items()}, dd)
+    assert np.array_equal(got["cls"], ref["cls"])
+    n = len(ref["cls"])
+    assert n > 0 and got["ins_masks"].shape == (n, 241, 323)
+    assert np.abs(got["ins_masks"] - ref["ins_masks"]).mean() <= 1e-5
+    assert np.abs(got["grasp_masks"][2] - ref["grasp_masks"][2]).max() <= 1e-5
+    assert np.abs(got["grasp_masks"][0] - ref["grasp_masks"][0]).max() <= 1e-5
 
 
 def test_post_processing_batched_equals_per_image():
