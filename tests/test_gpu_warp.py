@@ -92,9 +92,11 @@ def test_preprocess_batch_vs_oracle():
         assert np.array_equal(got[b], WA.preprocess_image(img[b], mat, (104, 104))), b
 
 
-def test_evaluator_original_resolution_matches_oracle():
-    """The real pipeline (crog_engine.py:446-527): model -> sigmoid/bicubic -> inverse letterbox to 480x640 -> mask IoU,
-    detect_grasps, Jaccard.  Given the GPU maps at 416^2, everything downstream is bit-exact vs the oracle."""
+@pytest.mark.parametrize("ori", [(480, 640), (375, 501)])
+def test_evaluator_original_resolution_matches_oracle(ori):
+    """The real pipeline (crog_engine.py:446-527): model -> sigmoid/bicubic -> inverse letterbox to the original size ->
+    mask IoU, detect_grasps, Jaccard.  Given the GPU maps at 416^2, everything downstream is bit-exact vs the oracle.
+    (375 x 501: odd sizes, so the warped planes are not 16-byte aligned and the decode takes the generic scan.)"""
     from crog_b200.engine import GraspEvaluator
     from crog_b200.model import CROG
     from oracle import grasp_tail_c as TC
@@ -107,18 +109,18 @@ def test_evaluator_original_resolution_matches_oracle():
     model = model.cuda()
     img, word = synth.make_inputs(B, Lw)
     gt, cnt = synth.make_gt_rects(B, 64, seed=4)
-    _, mat_inv = W.get_transform_mat((480, 640), (416, 416), inverse=True)
+    _, mat_inv = W.get_transform_mat(ori, (416, 416), inverse=True)
     rng = np.random.default_rng(1)
     tgt416 = (rng.random((B, 416, 416)) > 0.6).astype(np.float32)
     ev = GraspEvaluator(model)
     res = ev.step_original(img.cuda(), word.cuda(), torch.from_numpy(gt.copy()).cuda(), torch.from_numpy(cnt).cuda(),
-                           mat_inv, (480, 640), mask_target=torch.from_numpy(tgt416).cuda())
+                           mat_inv, ori, mask_target=torch.from_numpy(tgt416).cuda())
     post = res["post"].cpu().numpy()      # [5,B,416,416] as produced by the GPU
-    inv = res["maps"].cpu().numpy()       # [5,B,480,640]
+    inv = res["maps"].cpu().numpy()       # [5,B,h,w]
     for b in range(B):
         for p in range(5):
-            assert np.array_equal(inv[p, b], WA.warp_affine_cubic_f32(post[p, b], mat_inv, (640, 480), 0.0)), (p, b)
-        t = WA.warp_affine_cubic_f32(tgt416[b], mat_inv, (640, 480), 0.0)
+            assert np.array_equal(inv[p, b], WA.warp_affine_cubic_f32(post[p, b], mat_inv, (ori[1], ori[0]), 0.0)), (p, b)
+        t = WA.warp_affine_cubic_f32(tgt416[b], mat_inv, (ori[1], ori[0]), 0.0)
         assert float(res["iou"][b]) == WA.mask_iou(inv[0, b], t)
     g_ref, n_ref, j_ref, _ = TC.tail_batch(inv[1], inv[2], inv[3], inv[4], gt, cnt)
     assert np.array_equal(res["n_peaks"].cpu().numpy(), n_ref)
