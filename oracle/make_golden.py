@@ -59,7 +59,7 @@ def build_reference(cfg):
     return ref
 
 
-def run_case(tag, word_len, batch, mode, seed_w, **cfg_over):
+def run_case(tag, word_len, batch, mode, seed_w, size=416, **cfg_over):
     """cfg_over: the ablation switches of config/OCID-VLG/crog_multiple_r50_wo_contrastive.yaml (use_contrastive=False:
     no TransformerDecoder, model/crog.py:27-39,70-72) and ..._wo_grasps.yaml (use_grasp_masks=False: the mask-only
     ``Projector`` of model/layers.py:135-173, eval return ``(pred, mask)``, model/crog.py:115-133)."""
@@ -71,7 +71,7 @@ def run_case(tag, word_len, batch, mode, seed_w, **cfg_over):
     for k in sd:
         assert tuple(ref_sd[k].shape) == tuple(sd[k].shape), k
     ref.load_state_dict(sd, strict=True)
-    img, word = synth.make_inputs(batch, word_len)
+    img, word = synth.make_inputs(batch, word_len, size=size)  # size != 416: the attention pool resizes its positional embedding (clip.py:101-104)
     t0 = time.time()
     with torch.no_grad():
         (r_maps, _) = ref(img, word)
@@ -96,9 +96,9 @@ def run_case(tag, word_len, batch, mode, seed_w, **cfg_over):
     # ablation feeds the projector un-normalised features (logits up to +-104), so the bar scales with the range
     rng_scale = max(1.0, max(float(m.abs().max()) for m in r_maps) / 16.0)
     assert all(v <= 1e-4 * rng_scale for v in errs.values()), (errs, rng_scale)
-    post = O.postprocess(r_maps, (416, 416))
+    post = O.postprocess(r_maps, (size, size))
     out = {
-        "word_len": np.int64(word_len), "batch": np.int64(batch), "seed_w": np.int64(seed_w),
+        "word_len": np.int64(word_len), "batch": np.int64(batch), "seed_w": np.int64(seed_w), "size": np.int64(size),
         "maps": torch.stack([m[:, 0] for m in r_maps], 1).numpy().astype(np.float32),  # B,5,104,104
         "state": state.numpy(), "word_feat": wfeat.numpy(),
         "c5_sample": c5[:, ::16].numpy(), "c4_sample": c4[:, ::64].numpy(), "c3_sample": c3[:, ::64, ::2, ::2].numpy(),
@@ -121,3 +121,4 @@ if __name__ == "__main__":
     run_case("L20_init", 20, 1, "init", 0)
     run_case("L17_wo_contrastive", 17, 1, "perturbed", 0, use_contrastive=False)
     run_case("L17_wo_grasps", 17, 1, "perturbed", 0, use_grasp_masks=False)
+    run_case("L17_perturbed_s320", 17, 1, "perturbed", 0, size=320)

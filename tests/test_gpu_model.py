@@ -65,6 +65,38 @@ def test_forward_fp32_matches_reference_golden(golden_dir, tag):
     assert np.abs(plan.keep["c5"].interior().cpu().numpy()[:, ::16] - g["c5_sample"]).max() <= 1e-3
 
 
+@pytest.mark.parametrize("size", [320, 352])
+def test_forward_other_input_size(golden_dir, size):
+    """Input sizes other than the benchmark's 416 (any multiple of 32): other tile tails in every layer, an attention pool
+    over 10 x 10 / 11 x 11 tokens with the resized positional embedding (clip.py:101-104), odd feature-map extents in the
+    neck (11, 22, 44).  320: against a golden of the unmodified reference (oracle/make_golden.py); 352: against the CPU
+    oracle.  fp32 <= 1e-3 max-abs, bf16 the stated rel-L2 <= 5e-2 / max-abs <= 0.5."""
+    from oracle import crog_forward as O
+
+    Lw = 17
+    if size == 320:
+        g = np.load(os.path.join(golden_dir, "model_L17_perturbed_s320.npz"))
+        B = int(g["batch"])
+        img, word = synth.make_inputs(B, Lw, size=size)
+        ref = torch.from_numpy(g["maps"])
+    else:
+        B = 2
+        img, word = synth.make_inputs(B, Lw, size=size)
+        cfg, sd, _ = _build(Lw, "perturbed", "fp32")
+        ref = torch.stack([m[:, 0] for m in O.crog_forward(sd, cfg, img, word)[0]], 1)
+    for precision in ("fp32", "bf16"):
+        model = _build(Lw, "perturbed", precision)[2]
+        maps, _ = model(img.cuda(), word.cuda())
+        torch.cuda.synchronize()
+        got = torch.stack([m[:, 0] for m in maps], 1).float().cpu()
+        assert got.shape == (B, 5, size // 4, size // 4)
+        if precision == "fp32":
+            assert float((got - ref).abs().max()) <= 1e-3 * max(1.0, float(ref.abs().max()) / 16)
+        else:
+            rel = max(float((got[:, i] - ref[:, i]).norm() / ref[:, i].norm()) for i in range(5))
+            assert rel <= 5e-2 and float((got - ref).abs().max()) <= 0.5, rel
+
+
 @pytest.mark.parametrize("tag,over", [("L17_wo_contrastive", {"use_contrastive": False}), ("L17_wo_grasps", {"use_grasp_masks": False})])
 @pytest.mark.parametrize("precision", ["fp32", "bf16"])
 def test_ablation_configs_match_reference_golden(golden_dir, tag, over, precision):

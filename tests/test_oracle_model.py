@@ -18,13 +18,14 @@ def test_spec_table_counts():
     assert len({s.name for s in specs}) == 662
 
 
-@pytest.mark.parametrize("tag", ["L20_init", "L17_perturbed"])
+@pytest.mark.parametrize("tag", ["L20_init", "L17_perturbed", "L17_perturbed_s320"])
 def test_restatement_matches_reference_golden(golden_dir, tag):
     g = np.load(os.path.join(golden_dir, f"model_{tag}.npz"))
     L, B = int(g["word_len"]), int(g["batch"])
+    S = int(g["size"]) if "size" in g.files else 416  # 320: the attention pool's resized positional embedding
     cfg = synth.default_cfg(L)
     sd = synth.make_state_dict(cfg, int(g["seed_w"]), str(g["mode"]))
-    img, word = synth.make_inputs(B, L)
+    img, word = synth.make_inputs(B, L, size=S)
     torch.set_num_threads(os.cpu_count())
     maps, inter = O.crog_forward(sd, cfg, img, word, keep=True)
     got = torch.stack([m[:, 0] for m in maps], 1).numpy()
@@ -33,7 +34,7 @@ def test_restatement_matches_reference_golden(golden_dir, tag):
     assert np.abs(inter["word"].numpy() - g["word_feat"]).max() <= 1e-4
     assert np.abs(inter["c5"][:, ::16].numpy() - g["c5_sample"]).max() <= 1e-4
     assert np.abs(inter["fq_dec"][:, ::16].numpy() - g["fq_dec_sample"]).max() <= 1e-4
-    post = O.postprocess(maps, (416, 416))
+    post = O.postprocess(maps, (S, S))
     assert np.abs(post[1].sum(-1).numpy() - g["post_qua_rowsum"]).max() <= 1e-2
 
 
