@@ -65,6 +65,33 @@ def test_forward_fp32_matches_reference_golden(golden_dir, tag):
     assert np.abs(plan.keep["c5"].interior().cpu().numpy()[:, ::16] - g["c5_sample"]).max() <= 1e-3
 
 
+def test_forward_sentence_length_extremes():
+    """Sentences of one token, of the full word_len (no padding: every key of the cross-attention is valid) and one in
+    between, in one batch: EOT gather, key-padding mask and the 17-key attention tiles at their edges.  fp32 vs the oracle."""
+    from oracle import crog_forward as O
+
+    Lw, B = 17, 3
+    img, _ = synth.make_inputs(B, Lw)
+    word = torch.zeros((B, Lw), dtype=torch.int64)
+    g = torch.Generator().manual_seed(5)
+    for b, n in enumerate((1, Lw - 2, 7)):
+        word[b, 0] = synth.SOT_TOKEN
+        word[b, 1:1 + n] = torch.randint(1, synth.SOT_TOKEN, (n,), generator=g)
+        word[b, 1 + n] = synth.EOT_TOKEN
+    assert int((word[1] == 0).sum()) == 0
+    cfg, sd, model = _build(Lw, "perturbed", "fp32")
+    maps, _ = model(img.cuda(), word.cuda())
+    torch.cuda.synchronize()
+    got = torch.stack([m[:, 0] for m in maps], 1).cpu()
+    ref = torch.stack([m[:, 0] for m in O.crog_forward(sd, cfg, img, word)[0]], 1)
+    assert float((got - ref).abs().max()) <= 1e-3 * max(1.0, float(ref.abs().max()) / 16)
+    model_bf = _build(Lw, "perturbed", "bf16")[2]
+    maps_bf, _ = model_bf(img.cuda(), word.cuda())
+    got_bf = torch.stack([m[:, 0] for m in maps_bf], 1).float().cpu()
+    rel = max(float((got_bf[:, i] - ref[:, i]).norm() / ref[:, i].norm()) for i in range(5))
+    assert rel <= 5e-2 and float((got_bf - ref).abs().max()) <= 0.5, rel
+
+
 @pytest.mark.parametrize("size", [320, 352])
 def test_forward_other_input_size(golden_dir, size):
     """Input sizes other than the benchmark's 416 (any multiple of 32): other tile tails in every layer, an attention pool
