@@ -59,8 +59,7 @@ class GraspEvaluator:
         letterboxed GT masks [B,S,S] (optional).  All five maps are warped back with cv2.warpAffine semantics
         (INTER_CUBIC, borderValue 0), the mask is thresholded at 0.35 for IoU, the other four are decoded.
         Returns a dict: post [5,B,S,S], maps [5,B,h,w], iou [B] | None, peaks, n_peaks, grasps, j_flags."""
-        maps, _ = self.model(img, word)
-        post = postprocess(maps, (img.shape[-2], img.shape[-1]))
+        post = postprocess(self._logits(img, word), (img.shape[-2], img.shape[-1]))
         h, w = int(ori_size[0]), int(ori_size[1])
         inv = WP.warp_affine_cubic(post, inverse_mats, (w, h), 0.0)
         iou = None
@@ -113,11 +112,15 @@ class GraspEvaluator:
     def step(self, img: torch.Tensor, word: torch.Tensor, gt: torch.Tensor, gt_count: torch.Tensor):
         """img B x 3 x S x S, word B x L, gt B x M x 6 float64 (edited in place like the reference), gt_count B int32.
         Returns (post [5,B,S,S], peaks, n_peaks, grasps, j_flags)."""
-        maps, _ = self.model(img, word)
-        post = postprocess(maps, (img.shape[-2], img.shape[-1]))
+        post = postprocess(self._logits(img, word), (img.shape[-2], img.shape[-1]))
         peaks, n, grasps = GE.detect_grasps_batched(post[1], post[2], post[3], post[4], self.K)
         flags = GE.jacquard_batched(grasps, n, gt, gt_count, counters=self.counters)
         return post, peaks, n, grasps, flags
+
+    def _logits(self, img, word):
+        """The five logits maps as one [5, B, 1, h, w] tensor when the model offers it (no re-stacking), else its tuple."""
+        fs = getattr(self.model, "forward_stacked", None)  # wrapped models (DataParallel) only have forward
+        return fs(img, word) if fs is not None else self.model(img, word)[0]
 
     @torch.no_grad()
     def stream(self, host_batches, letterbox=None, original: bool = False):

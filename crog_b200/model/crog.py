@@ -201,6 +201,17 @@ class CROG(nn.Module):
     @torch.no_grad()
     def forward(self, img, word, mask=None, grasp_qua_mask=None, grasp_sin_mask=None, grasp_cos_mask=None,
                 grasp_wid_mask=None):
+        out = self.forward_stacked(img, word)
+        maps = tuple(out[i] for i in range(out.shape[0]))
+        if self.use_grasp_masks:
+            return maps, (mask, grasp_qua_mask, grasp_sin_mask, grasp_cos_mask, grasp_wid_mask)
+        return maps[0], mask
+
+    @torch.no_grad()
+    def forward_stacked(self, img, word) -> torch.Tensor:
+        """The forward's logits as ONE tensor [NH, B, 1, S/4, S/4] (NH = 5: mask, qua, sin, cos, wid; 1 for the mask-only
+        model) - what ``forward`` returns as a tuple of views.  The evaluator takes this form so that the glue kernel reads
+        the heads in place instead of re-stacking them."""
         if self.training:
             raise NotImplementedError("crog_b200.CROG implements the inference path only; call .eval()")
         if img.dim() != 4 or img.shape[1] != 3 or img.shape[2] != img.shape[3]:
@@ -214,11 +225,7 @@ class CROG(nn.Module):
                 plan.img[:B].copy_(img, non_blocking=True)
             plan.word[:B].copy_(word, non_blocking=True)  # rows >= B keep an earlier batch: independent samples, results unused
             self._run(plan)
-            out = plan.out[:, :B].clone()
-        maps = tuple(out[i] for i in range(plan.NH))
-        if self.use_grasp_masks:
-            return maps, (mask, grasp_qua_mask, grasp_sin_mask, grasp_cos_mask, grasp_wid_mask)
-        return maps[0], mask
+            return plan.out[:, :B].clone()
 
     def _run(self, plan):
         if not self.use_cuda_graph:
