@@ -98,6 +98,7 @@ def workload_config(B: int, Lw: int, world: int):
                         f"416x416, L={Lw}, bf16, random-init (seeded) weights",
             "global_batch": B * world, "parallelism": f"dp{world}",
             "l2": "no explicit flush: one step streams ~6 GB of activations, far above the 126 MB L2",
+            "resident_input": "the batch is resident in the model's input buffer (CROG.input_buffer): no per-step input copy",
             "protocol": "every timed arm (resident, e2e variants) starts after W warm-up steps and a 1 s idle, so all arms see the same power state"}
 
 
@@ -530,9 +531,13 @@ def main():
         sync_all()
         return float(ms.item())
 
-    # ---- device-resident arm
+    # ---- device-resident arm: the batch sits in the model's own input buffer (CROG.input_buffer, the zero-copy entry a
+    # device-side producer uses), so a step does not start with a 133 MB device-to-device copy of its input
+    d_in = model.input_buffer(B, S)
+    d_in.copy_(d_img)
+
     def step_resident():
-        ev.step(d_img, d_word, d_gt, d_cnt)
+        ev.step(d_in, d_word, d_gt, d_cnt)
 
     sampler = ClockSampler(local)
     if rank == 0:
@@ -551,7 +556,7 @@ def main():
     ev.reduce()
     counters = ev.counters.tolist()
     # the forward alone (graph replay of the plan), for the split of a step into model / glue + decode + Jaccard
-    ms_fwd = timed(lambda: model(d_img, d_word), args.steps) / args.steps
+    ms_fwd = timed(lambda: model(d_in, d_word), args.steps) / args.steps
 
     # ---- end-to-end arms: pinned host buffers in, grasps / flags out, every step
     e2e = e2e_extra = None
