@@ -278,6 +278,38 @@ def test_engine_stream_matches_step():
     assert torch.equal(ev1.counters.cpu(), ev2.counters.cpu())
 
 
+def test_engine_stream_uint8_frames_matches_step():
+    """The benchmark's end-to-end path: pinned uint8 camera frames -> device letterbox + normalisation written into the plan's
+    input -> forward -> glue -> decode -> Jaccard, double-buffered over batches.  Six DIFFERENT batches: every result must
+    be what step() gives for that batch's own pre-processed frames (a stale or prematurely overwritten input buffer would
+    show up as another batch's grasps)."""
+    from crog_b200.engine import GraspEvaluator
+    from crog_b200.utils import warp as WP
+
+    Lw, B = 17, 2
+    cfg, sd, model = _build(Lw, "perturbed", "bf16")
+    mat, mat_inv = WP.get_transform_mat((480, 640), (416, 416), inverse=True)
+    rng = np.random.default_rng(3)
+    batches = []
+    for k in range(6):
+        frames = torch.from_numpy(rng.integers(0, 256, (B, 480, 640, 3), dtype=np.uint8))
+        _, word = synth.make_inputs(B, Lw, seed_img=10 + k, seed_txt=20 + k)
+        gt, cnt = synth.make_gt_rects(B, 64, seed=30 + k)
+        batches.append((frames.pin_memory(), word.pin_memory(), torch.from_numpy(gt).pin_memory(), torch.from_numpy(cnt).pin_memory()))
+    ev1, ev2 = GraspEvaluator(model), GraspEvaluator(model)
+    want = []
+    for frames, word, gt, cnt in batches:
+        img = WP.preprocess_images(frames.cuda(), mat, (416, 416))
+        _, _, n, grasps, flags = ev1.step(img, word.cuda(), gt.cuda(), cnt.cuda())
+        want.append((n.cpu().clone(), grasps.cpu().clone(), flags.cpu().clone()))
+    got = [tuple(t.clone() for t in out) for out in ev2.stream(iter(batches), letterbox=(mat, mat_inv, (480, 640)))]
+    assert len(got) == len(want)
+    for k, ((n1, g1, f1), (n2, g2, f2)) in enumerate(zip(want, got)):
+        assert torch.equal(n1, n2) and torch.equal(g1, g2) and torch.equal(f1, f2), k
+    assert torch.equal(ev1.counters.cpu(), ev2.counters.cpu())
+    assert len({tuple(g.flatten().tolist()) for _, g, _ in want}) > 1  # the batches really differ
+
+
 def test_ragged_batch_reuses_big_plan_and_lru_bound():
     """A batch smaller than a prepared plan runs in that plan's first rows (no new buffers, no autotune) with bit-identical
     per-sample results; the plan cache is a bounded LRU; prepare() moves build + autotune + graph capture out of forward."""
