@@ -11,8 +11,9 @@ model = CROG(cfg, precision="bf16", use_cuda_graph=False)
 model.load_state_dict(synth.make_state_dict(cfg, 0, "perturbed"))
 model = model.cuda()
 model.autotune = False
-img, word = synth.make_inputs(1, 17)
-gt, cnt = synth.make_gt_rects(1, 64, seed=4)
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 1
+img, word = synth.make_inputs(B, 17)
+gt, cnt = synth.make_gt_rects(B, 64, seed=4)
 ev = GraspEvaluator(model)
 out = ev.step(img.cuda(), word.cuda(), torch.from_numpy(gt).cuda(), torch.from_numpy(cnt).cuda())
 torch.cuda.synchronize()
